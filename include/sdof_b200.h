@@ -1,0 +1,200 @@
+/*
+ * sdof_b200.h — C ABI of libsdof_b200.so: the B200 (sm_100a) flow -> warp ->
+ * mask/composite hot path of zyddnys/sd_animation_optical_flow.
+ *
+ * Plain C: device pointers, sizes and a CUDA stream handle; no torch types.
+ * Every entry point is stream-ordered, performs no host synchronisation and
+ * returns SDOF_OK (0) or an error code; sdof_last_error() gives the text.
+ * All pointers are DEVICE pointers unless a parameter says "host".
+ *
+ * Each declaration cites the reference interface (file:line under the
+ * reference checkout) that it replaces.  INTEGRATION.md shows the
+ * reference-side bindings (ctypes stubs) a maintainer would add.
+ */
+#ifndef SDOF_B200_H
+#define SDOF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDOF_ABI_VERSION 1
+#define SDOF_MAX_LEVELS 8
+
+typedef void* sdof_stream_t; /* cudaStream_t; NULL = legacy default stream */
+
+enum sdof_status {
+  SDOF_OK = 0,
+  SDOF_ERR_INVALID = 1,     /* bad argument (null pointer, size, alignment) */
+  SDOF_ERR_CUDA = 2,        /* a CUDA call or launch failed                  */
+  SDOF_ERR_UNSUPPORTED = 3  /* shape/mode not supported by this build        */
+};
+
+/* arithmetic used for the all-pairs contraction (output is always fp32) */
+enum sdof_precision {
+  SDOF_PREC_TF32 = 0,   /* tcgen05 kind::tf32, one pass, features rounded to nearest */
+  SDOF_PREC_3XTF32 = 1, /* tcgen05 kind::tf32, error-compensated (fp32-faithful) */
+  SDOF_PREC_BF16 = 2,   /* tcgen05 kind::f16 on bf16 copies of the features     */
+  SDOF_PREC_FP32 = 3    /* CUDA-core fp32 FMA (exact-order checker on device)   */
+};
+
+int sdof_abi_version(void);
+const char* sdof_last_error(void);
+
+/* ------------------------------------------------------------------ C1 + C2
+ * Layout of the correlation pyramid in HBM.  Level l holds, for each of the
+ * `rows` = B*h1*w1 source pixels, an h[l] x w[l] map (h[l]=h2>>l, w[l]=w2>>l,
+ * floor) stored row-major with row pitch wp[l] (w[l] rounded up to 4 floats so
+ * that TMA stores are 16-byte aligned).  Element (row, y, x) of level l is at
+ *   pyramid[offset[l] + row*pitch[l] + y*wp[l] + x].
+ * Replaces the list `CorrBlock.corr_pyramid` (RAFT/core/corr.py:15-27).       */
+typedef struct sdof_pyramid_layout {
+  int32_t levels;
+  int32_t h[SDOF_MAX_LEVELS];
+  int32_t w[SDOF_MAX_LEVELS];
+  int32_t wp[SDOF_MAX_LEVELS];
+  int64_t pitch[SDOF_MAX_LEVELS];
+  int64_t offset[SDOF_MAX_LEVELS];
+  int64_t total_floats;
+} sdof_pyramid_layout;
+
+int sdof_corr_pyramid_layout(int64_t rows, int h2, int w2, int levels, sdof_pyramid_layout* out /* host */);
+
+/* Scratch bytes sdof_corr_volume_pyramid needs for `precision` (rounded / split / bf16 copies of
+ * the features; 0 for FP32). */
+int64_t sdof_corr_volume_workspace_bytes(int B, int h1, int w1, int h2, int w2, int C, int precision);
+
+/* All-pairs correlation volume + its average-pooled pyramid in one pass:
+ *   level0[b, i, j] = <fmap1[b,i,:], fmap2[b,j,:]> / sqrt(C);  level l+1 = avg_pool2d(level l, 2, 2)
+ * fmap1 [B, h1*w1, C], fmap2 [B, h2*w2, C]: fp32, channels-last, contiguous, 16-byte aligned.
+ * Replaces CorrBlock.corr + CorrBlock.__init__ (RAFT/core/corr.py:12-27, 52-60):
+ * torch.matmul + divide + 3x avg_pool2d.                                      */
+int sdof_corr_volume_pyramid(const float* fmap1, const float* fmap2, int B, int h1, int w1, int h2, int w2, int C,
+                             int levels, int precision, float* pyramid, void* workspace, int64_t workspace_bytes,
+                             sdof_stream_t stream);
+
+/* ------------------------------------------------------------------------ C3
+ * Windowed bilinear lookup in all pyramid levels for one GRU iteration.
+ * coords [B,2,h1,w1] (x then y, level-0 pixels of the target map) ->
+ * out [B, levels*(2r+1)^2, h1, w1] fp32, channel = l*(2r+1)^2 + (2r+1)*ix + iy,
+ * zeros outside the map.
+ * Replaces CorrBlock.__call__ (RAFT/core/corr.py:29-50) + bilinear_sampler
+ * (RAFT/core/utils/utils.py:57-71): 4x grid_sample + cat + permute + contiguous. */
+int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
+                     int radius, float* out, sdof_stream_t stream);
+
+/* ------------------------------------------------------------------------ K1
+ * On-the-fly windowed correlation, no volume.  Same contract as the pybind op
+ *   alt_cuda_corr.forward(fmap1, fmap2, coords, radius) -> [corr]
+ * (RAFT/alt_cuda_corr/correlation.cpp:23-33,51-54; kernel
+ * correlation_kernel.cu:18-119; launcher :260-286):
+ * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C] fp32 channels-last, coords [B,N,H1,W1,2]
+ * (x,y in fmap2 pixels) -> corr [B,N,(2r+1)^2,H1,W1], UNNORMALISED, every element
+ * written (no zero-initialisation needed).  C must be a multiple of 4.          */
+int sdof_alt_corr_forward(const float* fmap1, const float* fmap2, const float* coords, int B, int H1, int W1, int H2,
+                          int W2, int C, int N, int radius, float* corr, sdof_stream_t stream);
+
+/* C4: one level of AlternateCorrBlock.__call__ (RAFT/core/corr.py:74-91) without the
+ * permute/contiguous copies: coords [B,2,H1,W1] planar, scaled by coord_scale (=1/2^l)
+ * inside the kernel; writes channels [chan_offset, chan_offset+(2r+1)^2) of
+ * out [B, out_channels, H1, W1], multiplied by out_scale (=1/sqrt(C)).            */
+int sdof_alt_corr_level(const float* fmap1, const float* fmap2_level, const float* coords, int B, int H1, int W1,
+                        int H2, int W2, int C, int radius, float coord_scale, float out_scale, int chan_offset,
+                        int out_channels, float* out, sdof_stream_t stream);
+
+/* 2x2 average pool of a channels-last map [B,H,W,C] -> [B,H/2,W/2,C] (floor), used to
+ * build AlternateCorrBlock's fmap2 pyramid (RAFT/core/corr.py:68-72).            */
+int sdof_avgpool2_nhwc(const float* in, int B, int H, int W, int C, float* out, sdof_stream_t stream);
+
+/* -------------------------------------------------------------------- W1 / W2
+ * Backward warp.  dst[b,y,x,:] = sample(src[b or 0], x + sign*flow[b,y,x,0], y + sign*flow[b,y,x,1]).
+ * The sampling map is float32(double(x) + double(sign*flow)), which is both
+ * pdcnet_of.warp_frame's map (sign=+1, pdcnet_of.py:34-42) and ofgen.warp_frame's
+ * (sign=-1, ofgen.py:37-43).  src [Bs,Hs,Ws,C] (Bs = B, or 1 to share one key frame),
+ * flow [B,H,W,2], dst [B,H,W,C]; C in 1..4.
+ * cubic: bit-exact cv2.remap(INTER_CUBIC, BORDER_CONSTANT 0) for u8 (1/32-pixel
+ * coordinates, 2^15 fixed-point weight table); same quantisation, fp32 weights for f32.
+ * bilinear: grid_sample(bilinear, zeros, align_corners=True) semantics at exact
+ * pixel coordinates (RAFT/core/utils/utils.py:57-71); u8 output = round-half-even. */
+int sdof_warp_cubic_u8(const uint8_t* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                       int W, float sign, uint8_t* dst, sdof_stream_t stream);
+int sdof_warp_cubic_f32(const float* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                        int W, float sign, float* dst, sdof_stream_t stream);
+int sdof_warp_bilinear_u8(const uint8_t* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                          int W, float sign, uint8_t* dst, sdof_stream_t stream);
+int sdof_warp_bilinear_f32(const float* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                           int W, float sign, float* dst, sdof_stream_t stream);
+
+/* Host-side copy of the 1024x16 int16 bicubic weight table the u8 kernel uses
+ * (out: host int16[16384]); lets CPU tests pin it against OpenCV without a GPU. */
+int sdof_cubic_table_i16(int16_t* out /* host */);
+/* Host-side row half-widths of cv2.getStructuringElement(MORPH_ELLIPSE,(k,k)). */
+int sdof_ellipse_half_widths(int ksize, int32_t* out /* host, ksize entries */);
+
+/* ------------------------------------------------------------------------ M1
+ * confidence = softmax(weight_map, dim=1)[:,0], log_confidence = log_softmax(...)[:,0]
+ * (pdcnet_of.py:72-74).  weight_map [B,K,H,W] -> conf, logconf [B,H,W] (either may be NULL). */
+int sdof_confidence_softmax(const float* weight_map, int B, int K, int H, int W, float* conf, float* logconf,
+                            sdof_stream_t stream);
+
+/* M2: travel distance of of_calc (ofgen_pixel_inpaint.py:105-118). flow [B,H,W,2], conf [B,H,W] -> v [B,H,W]. */
+int sdof_travel_distance(const float* flow, const float* conf, int B, int H, int W, float conf_thres, float* v,
+                         sdof_stream_t stream);
+
+/* M3: generate_mask (ofgen_pixel_inpaint.py:262-267; ofgen_keyframe_inpaint.py:317-322):
+ * mask = dilate_ellipse(255*(conf < thres), ksize); log_conf[conf < thres] = 0 in place
+ * (log_conf may be NULL).  conf [B,H,W] -> mask u8 [B,H,W].                       */
+int sdof_generate_mask(const float* conf, float* log_conf, int B, int H, int W, float thres, int ksize,
+                       uint8_t* mask, sdof_stream_t stream);
+
+/* cv2.dilate(src, getStructuringElement(MORPH_ELLIPSE,(ksize,ksize))) on u8 [B,H,W];
+ * invert != 0 dilates (255 - src) (ofgen_keyframe_inpaint.py:772-774).  ksize odd, <= 31. */
+int sdof_dilate_ellipse_u8(const uint8_t* src, int B, int H, int W, int ksize, int invert, uint8_t* dst,
+                           sdof_stream_t stream);
+
+/* M6: expand_mask (ofgen_keyframe_inpaint.py:968-973): out = mask | dilate(255*(gray(|laplacian(img)| mod 256) > 20)).
+ * mask u8 [B,H,W], image u8 [B,H,W,3], scratch u8 [B,H,W].                        */
+int sdof_expand_mask(const uint8_t* mask, const uint8_t* image, int B, int H, int W, int ksize, uint8_t* scratch,
+                     uint8_t* out, sdof_stream_t stream);
+
+/* M4: mix_propagated_ai_frame (ofgen_pixel_inpaint.py:251-260). raw, warped, out u8 [B,H,W,C]; mask u8 [B,H,W]. */
+int sdof_mix_propagated(const uint8_t* raw, const uint8_t* warped, const uint8_t* mask, int B, int H, int W, int C,
+                        float ppw, uint8_t* out, sdof_stream_t stream);
+
+/* M5 inner step: merge_images(method='naive') (ofgen_keyframe_inpaint.py:676-681): out = mask==255 ? second : base. */
+int sdof_merge_select(const uint8_t* base, const uint8_t* second, const uint8_t* mask, int B, int H, int W, int C,
+                      uint8_t* out, sdof_stream_t stream);
+
+/* M5: greedy multi-reference composite (ofgen_keyframe_inpaint.py:995-1024, :741-770).
+ * flow_mat [n,H,W,3] fp32 (flow x, flow y, confidence) is updated in place exactly as the
+ * reference does (binarise conf > thres, subtract covered pixels, clip); ai_frames u8 [n,H,W,3].
+ * Outputs: ret u8 [H,W,3], mask u8 [H,W], order int32[n] (device) = reference chosen per round.
+ * workspace: sdof_greedy_workspace_bytes(n,H,W) bytes.                             */
+int64_t sdof_greedy_workspace_bytes(int n, int H, int W);
+int sdof_greedy_composite(float* flow_mat, const uint8_t* ai_frames, int n, int H, int W, float thres, uint8_t* ret,
+                          uint8_t* mask, int32_t* order, void* workspace, sdof_stream_t stream);
+
+/* A2: KeyframeConv score (ofgen_keyframe_inpaint.py:664-668): sums[s] = sum of the confidence
+ * channel over `per_source` pixels of flow_mat [S, per_source, 3]; sums double[S] (device). */
+int sdof_confidence_sums(const float* flow_mat, int S, int64_t per_source, double* sums, sdof_stream_t stream);
+
+/* ------------------------------------------------- fused W1 + M1 + M3 + M4 (26 B/pixel)
+ * One pass per non-key frame (ofgen_pixel_inpaint.py:335-349 with ppw = 1):
+ *   conf  = softmax(weight_map)[0];  mask = dilate_ellipse(255*(conf < thres), ksize)
+ *   out   = mask > 127 ? base : cubic_warp(src, x + flow)
+ * src u8 [Bs,H,W,3] stylised key frame, base u8 [B,H,W,3], flow [B,H,W,2],
+ * weight_map [B,2,H,W] -> out u8 [B,H,W,3], mask u8 [B,H,W].                      */
+int sdof_warp_mask_composite(const uint8_t* src, const uint8_t* base, const float* flow, const float* weight_map,
+                             int B, int src_batched, int H, int W, float thres, int ksize, uint8_t* out,
+                             uint8_t* mask, sdof_stream_t stream);
+
+/* ---------------------------------------------------------------- diagnostics */
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t sdof_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDOF_B200_H */

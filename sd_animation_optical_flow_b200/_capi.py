@@ -1,0 +1,130 @@
+"""ctypes binding of libsdof_b200.so (include/sdof_b200.h).
+
+There is no fallback: if the library is missing or a call fails this module raises.
+Torch tensors are only used as device-memory handles (`data_ptr()`), and the current
+torch CUDA stream is passed to every call, so all work is stream-ordered with the
+surrounding PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int16, c_int32, c_int64, c_void_p
+
+import torch
+
+SDOF_MAX_LEVELS = 8
+PRECISIONS = {'tf32': 0, '3xtf32': 1, 'bf16': 2, 'fp32': 3}
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libsdof_b200.so')
+
+
+class PyramidLayout(ctypes.Structure):
+    _fields_ = [
+        ('levels', c_int32),
+        ('h', c_int32 * SDOF_MAX_LEVELS),
+        ('w', c_int32 * SDOF_MAX_LEVELS),
+        ('wp', c_int32 * SDOF_MAX_LEVELS),
+        ('pitch', c_int64 * SDOF_MAX_LEVELS),
+        ('offset', c_int64 * SDOF_MAX_LEVELS),
+        ('total_floats', c_int64),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/sdof_b200.h declares
+_P = c_void_p
+SIGNATURES = {
+    'sdof_abi_version': (c_int, []),
+    'sdof_last_error': (c_char_p, []),
+    'sdof_launch_count': (c_int64, []),
+    'sdof_corr_pyramid_layout': (c_int, [c_int64, c_int, c_int, c_int, POINTER(PyramidLayout)]),
+    'sdof_corr_volume_workspace_bytes': (c_int64, [c_int] * 7),
+    'sdof_corr_volume_pyramid': (c_int, [_P, _P] + [c_int] * 8 + [_P, _P, c_int64, _P]),
+    'sdof_corr_lookup': (c_int, [_P, _P] + [c_int] * 7 + [_P, _P]),
+    'sdof_alt_corr_forward': (c_int, [_P, _P, _P] + [c_int] * 8 + [_P, _P]),
+    'sdof_alt_corr_level': (c_int, [_P, _P, _P] + [c_int] * 7 + [c_float, c_float, c_int, c_int, _P, _P]),
+    'sdof_avgpool2_nhwc': (c_int, [_P] + [c_int] * 4 + [_P, _P]),
+    'sdof_warp_cubic_u8': (c_int, [_P, _P] + [c_int] * 7 + [c_float, _P, _P]),
+    'sdof_warp_cubic_f32': (c_int, [_P, _P] + [c_int] * 7 + [c_float, _P, _P]),
+    'sdof_warp_bilinear_u8': (c_int, [_P, _P] + [c_int] * 7 + [c_float, _P, _P]),
+    'sdof_warp_bilinear_f32': (c_int, [_P, _P] + [c_int] * 7 + [c_float, _P, _P]),
+    'sdof_cubic_table_i16': (c_int, [POINTER(c_int16)]),
+    'sdof_ellipse_half_widths': (c_int, [c_int, POINTER(c_int32)]),
+    'sdof_confidence_softmax': (c_int, [_P] + [c_int] * 4 + [_P, _P, _P]),
+    'sdof_travel_distance': (c_int, [_P, _P] + [c_int] * 3 + [c_float, _P, _P]),
+    'sdof_generate_mask': (c_int, [_P, _P] + [c_int] * 3 + [c_float, c_int, _P, _P]),
+    'sdof_dilate_ellipse_u8': (c_int, [_P] + [c_int] * 5 + [_P, _P]),
+    'sdof_expand_mask': (c_int, [_P, _P] + [c_int] * 4 + [_P, _P, _P]),
+    'sdof_mix_propagated': (c_int, [_P, _P, _P] + [c_int] * 4 + [c_float, _P, _P]),
+    'sdof_merge_select': (c_int, [_P, _P, _P] + [c_int] * 4 + [_P, _P]),
+    'sdof_greedy_workspace_bytes': (c_int64, [c_int] * 3),
+    'sdof_greedy_composite': (c_int, [_P, _P] + [c_int] * 3 + [c_float, _P, _P, _P, _P, _P]),
+    'sdof_confidence_sums': (c_int, [_P, c_int, c_int64, _P, _P]),
+    'sdof_warp_mask_composite': (c_int, [_P, _P, _P, _P] + [c_int] * 4 + [c_float, c_int, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class SdofError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load libsdof_b200.so and bind every entry point.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise SdofError(
+            f'{_LIB_PATH} is missing: build it with `python -m sd_animation_optical_flow_b200.build` '
+            '(needs nvcc with sm_100a support).  There is no CPU or PyTorch fallback for this path.')
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sdof_abi_version() != 1:
+        raise SdofError(f'libsdof_b200.so ABI {lib.sdof_abi_version()} != 1 expected by this package')
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().sdof_last_error()
+        raise SdofError(f'{what} failed (status {rc}): {msg.decode() if msg else "?"}')
+
+
+def stream_ptr(device=None) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    """Mirror of the reference's CHECK_INPUT (RAFT/alt_cuda_corr/correlation.cpp:19-21),
+    plus the dtype check the reference leaves to a hard accessor failure."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor')
+    if not t.is_contiguous():
+        raise RuntimeError(f'{name} must be contiguous')
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f'{name} must have dtype {dtype}, got {t.dtype}')
+    return t
+
+
+def pyramid_layout(rows: int, h2: int, w2: int, levels: int) -> PyramidLayout:
+    lay = PyramidLayout()
+    check(load().sdof_corr_pyramid_layout(rows, h2, w2, levels, ctypes.byref(lay)), 'sdof_corr_pyramid_layout')
+    return lay
+
+
+def launch_count() -> int:
+    return int(load().sdof_launch_count())

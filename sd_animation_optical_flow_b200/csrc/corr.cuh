@@ -1,0 +1,20 @@
+// Internal declarations shared by the correlation translation units.
+#pragma once
+
+#include "sdof_common.cuh"
+
+namespace sdof {
+
+// corr_simt.cu
+int launch_corr_volume_fp32(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, float* pyramid,
+                            const sdof_pyramid_layout& lay, cudaStream_t st);
+int launch_pool_levels(float* pyramid, const sdof_pyramid_layout& lay, int64_t rows, int first_level, cudaStream_t st);
+
+// corr_tc.cu: tcgen05 volume + fused pyramid.  Returns SDOF_ERR_UNSUPPORTED (without touching the
+// error text's severity) when the shape cannot go through TMA so the caller can fall back.
+int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, int precision,
+                          float* pyramid, const sdof_pyramid_layout& lay, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t st);
+int64_t corr_tc_workspace_bytes(int B, int n1, int n2, int C, int precision);
+
+}  // namespace sdof

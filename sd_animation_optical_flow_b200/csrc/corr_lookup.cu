@@ -1,0 +1,347 @@
+// Per-iteration correlation lookups.
+//
+//  corr_lookup_kernel : windowed bilinear lookup in the precomputed pyramid.
+//  alt_corr_kernel    : on-the-fly windowed correlation (no volume), warp-shuffle
+//                       reductions over the channel dimension.
+//
+// Both are gathers, so the layout work is on the OUTPUT side: a CTA owns 32 consecutive
+// source pixels, one warp per pixel; each warp stages its (2r+2)^2 integer-grid window
+// in shared memory, blends the (2r+1)^2 outputs (all taps of a level share one (fx,fy)),
+// and parks them in a [channels][32] shared tile so the [B, channels, h1, w1] result is
+// written as full 128-byte lines.  Algorithmic bytes per source pixel and iteration:
+// L*(2r+2)^2*4 read + L*(2r+1)^2*4 written = 2896 B for L=4, r=4.
+#include "corr.cuh"
+
+namespace sdof {
+
+constexpr int kLookupPx = 32;                   // source pixels per CTA = warps per CTA
+constexpr int kLookupThreads = kLookupPx * 32;  // 1024
+constexpr int kStagePitch = kLookupPx + 1;      // +1: conflict-free column writes
+
+struct LookupLevels {
+  int levels;
+  const float* base[SDOF_MAX_LEVELS];
+  long long pitch[SDOF_MAX_LEVELS];
+  int h[SDOF_MAX_LEVELS], w[SDOF_MAX_LEVELS], wp[SDOF_MAX_LEVELS];
+};
+
+// floor with NaN / huge values mapped far outside any map (whole window reads zero)
+__device__ __forceinline__ int safe_floor(float v, float* frac) {
+  if (!(v > -1.0e6f && v < 1.0e6f)) {
+    *frac = 0.f;
+    return -(1 << 24);
+  }
+  const float f = floorf(v);
+  *frac = v - f;
+  return (int)f;
+}
+
+// blend the (D+1)x(D+1) window `win` (row-major, [wy][wx]) into D*D outputs, x-major
+// channel order k = D*ix + iy (RAFT/core/corr.py:37-43), and park them in the stage tile.
+__device__ __forceinline__ void blend_window(const float* __restrict__ win, int D, float fx, float fy, float scale,
+                                             float* __restrict__ stage_col, int lane) {
+  const int T1 = D + 1;
+  const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+  for (int k = lane; k < D * D; k += 32) {
+    const int ix = k / D, iy = k - ix * D;
+    const float* q = win + iy * T1 + ix;
+    float v = q[0] * w00 + q[1] * w01 + q[T1] * w10 + q[T1 + 1] * w11;
+    stage_col[k * kStagePitch] = v * scale;
+  }
+}
+
+// coalesced write-out of the CTA's [channels][32] stage tile
+__device__ __forceinline__ void flush_stage(const float* __restrict__ stage, int channels, float* __restrict__ out,
+                                            int64_t out_chan_stride, int p0, int N1) {
+  for (int i = threadIdx.x; i < channels * kLookupPx; i += blockDim.x) {
+    const int k = i >> 5, j = i & 31;
+    if (p0 + j < N1) out[(int64_t)k * out_chan_stride + p0 + j] = stage[k * kStagePitch + j];
+  }
+}
+
+template <int R_T, int L_T>
+__global__ void __launch_bounds__(kLookupThreads) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
+                                                                     int N1, int r_rt, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int r = R_T ? R_T : r_rt;
+  const int L = L_T ? L_T : lv.levels;
+  const int D = 2 * r + 1, T1 = D + 1, T = T1 * T1, DD = D * D;
+  float* stage = smem;                           // [L*DD][kStagePitch]
+  float* win_all = smem + L * DD * kStagePitch;  // [32 warps][L][T]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kLookupPx;
+  const int p = p0 + warp;
+  float* win = win_all + warp * L * T;
+  if (p < N1) {
+    const float cx = coords[((int64_t)b * 2 + 0) * N1 + p];
+    const float cy = coords[((int64_t)b * 2 + 1) * N1 + p];
+    const int64_t row = (int64_t)b * N1 + p;
+    float fxs[L_T ? L_T : SDOF_MAX_LEVELS], fys[L_T ? L_T : SDOF_MAX_LEVELS];
+    // gather: with compile-time (r, L) every level's loads are issued before any is consumed
+    constexpr int kTrips = R_T ? ((2 * R_T + 2) * (2 * R_T + 2) + 31) / 32 : (18 * 18 + 31) / 32;
+#pragma unroll
+    for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
+      if (l >= L) break;
+      const float s = 1.0f / (float)(1 << l);  // coords / 2**l is exact
+      const int x0 = safe_floor(cx * s, &fxs[l]) - r;
+      const int y0 = safe_floor(cy * s, &fys[l]) - r;
+      const float* map = lv.base[l] + row * lv.pitch[l];
+      const int h = lv.h[l], w = lv.w[l], wp = lv.wp[l];
+#pragma unroll
+      for (int j = 0; j < kTrips; ++j) {
+        const int t = lane + 32 * j;
+        if (t < T) {
+          const int wy = t / T1, wx = t - wy * T1;
+          const int gy = y0 + wy, gx = x0 + wx;
+          float v = 0.f;
+          if ((unsigned)gy < (unsigned)h && (unsigned)gx < (unsigned)w) v = __ldg(map + (int64_t)gy * wp + gx);
+          win[l * T + t] = v;
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
+      if (l >= L) break;
+      blend_window(win + l * T, D, fxs[l], fys[l], 1.0f, stage + l * DD * kStagePitch + warp, lane);
+    }
+  }
+  __syncthreads();
+  flush_stage(stage, L * DD, out + (int64_t)b * L * DD * N1, N1, p0, N1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// On-the-fly correlation: for each of the (2r+2)^2 integer taps around floor(coords)-r take the
+// C-long dot product <fmap1[p], fmap2[tap]> (correlation_kernel.cu:59-90), then blend exactly like
+// the lookup.  One warp per source pixel: lanes split the channels (float4 per lane per 128
+// channels); 32 taps are reduced together with a transposing butterfly (31 shuffles per 32 taps).
+__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];  // lane L holds the total of tap L of the group
+}
+
+struct AltCorrArgs {
+  const float* fmap1;   // [B, N1, C]
+  const float* fmap2;   // [B, H2*W2, C]
+  const float* coords;  // element (bn, p, xy) at coords[bn*c_set + p*c_px + xy*c_xy]
+  long long c_set, c_px, c_xy;
+  int sets;  // coordinate sets per batch item (N of alt_cuda_corr.forward)
+  int N1, H2, W2, C, r;
+  float coord_scale, out_scale;
+  float* out;            // channel (chan_offset + set*DD + k) of [B, out_channels, N1]
+  int out_channels, chan_offset;
+};
+
+template <int R_T>
+__global__ void __launch_bounds__(kLookupThreads) alt_corr_kernel(AltCorrArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int r = R_T ? R_T : a.r;
+  const int D = 2 * r + 1, T1 = D + 1, T = T1 * T1, DD = D * D;
+  const int C = a.C, C4 = C >> 2;
+  float* stage = smem;                            // [DD][kStagePitch]
+  float* win_all = stage + DD * kStagePitch;      // [32][T]
+  float* f1_all = smem + ((DD * kStagePitch + kLookupPx * T + 3) & ~3);  // [32][C], 16-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = blockIdx.y, b = bn / a.sets, set = bn - b * a.sets;
+  const int p0 = blockIdx.x * kLookupPx;
+  const int p = p0 + warp;
+  float* win = win_all + warp * T;
+  if (p < a.N1) {
+    float4* f1s = reinterpret_cast<float4*>(f1_all + warp * C);
+    const float4* f1g = reinterpret_cast<const float4*>(a.fmap1 + ((int64_t)b * a.N1 + p) * C);
+    for (int c = lane; c < C4; c += 32) f1s[c] = __ldg(f1g + c);
+    const float* cp = a.coords + (int64_t)bn * a.c_set + (int64_t)p * a.c_px;
+    float fx, fy;
+    const int x0 = safe_floor(cp[0] * a.coord_scale, &fx) - r;
+    const int y0 = safe_floor(cp[a.c_xy] * a.coord_scale, &fy) - r;
+    __syncwarp();
+    const float4* f2b = reinterpret_cast<const float4*>(a.fmap2 + (int64_t)b * a.H2 * a.W2 * C);
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = 0.f;
+        const int t = t0 + i;
+        if (t < T) {
+          const int wy = t / T1, wx = t - wy * T1;
+          const int gy = y0 + wy, gx = x0 + wx;
+          if ((unsigned)gy < (unsigned)a.H2 && (unsigned)gx < (unsigned)a.W2) {  // warp-uniform
+            const float4* f2 = f2b + ((int64_t)gy * a.W2 + gx) * C4;
+            float s = 0.f;
+            for (int c = lane; c < C4; c += 32) {
+              const float4 u = f1s[c], q = __ldg(f2 + c);
+              s = fmaf(u.x, q.x, s);
+              s = fmaf(u.y, q.y, s);
+              s = fmaf(u.z, q.z, s);
+              s = fmaf(u.w, q.w, s);
+            }
+            v[i] = s;
+          }
+        }
+      }
+      const float tot = butterfly32(v, lane);
+      if (t0 + lane < T) win[t0 + lane] = tot;
+    }
+    __syncwarp();
+    blend_window(win, D, fx, fy, a.out_scale, stage + warp, lane);
+  }
+  __syncthreads();
+  flush_stage(stage, DD, a.out + ((int64_t)b * a.out_channels + a.chan_offset + (int64_t)set * DD) * a.N1, a.N1, p0, a.N1);
+}
+
+static int launch_alt_corr(const char* name, const AltCorrArgs& a, int B, cudaStream_t st) {
+  const int D = 2 * a.r + 1, T = (D + 1) * (D + 1), DD = D * D;
+  // stage + windows, rounded so the feature rows start 16-byte aligned
+  size_t floats = (size_t)DD * kStagePitch + (size_t)kLookupPx * T;
+  floats = (floats + 3) & ~(size_t)3;
+  const size_t smem = (floats + (size_t)kLookupPx * a.C) * sizeof(float);
+  SDOF_REQUIRE(smem <= 200 * 1024, "%s: C=%d / radius=%d need %zu bytes of shared memory (limit 200 KB)", name, a.C, a.r,
+               smem);
+  AltCorrArgs args = a;
+  dim3 grid(ceil_div(a.N1, kLookupPx), B * a.sets);
+  SDOF_REQUIRE(grid.y <= 65535, "%s: B*N > 65535 not supported", name);
+#define SDOF_ALT_LAUNCH(RT)                                                                                        \
+  do {                                                                                                             \
+    SDOF_CUDA(cudaFuncSetAttribute(alt_corr_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    alt_corr_kernel<RT><<<grid, kLookupThreads, smem, st>>>(args);                                                 \
+  } while (0)
+  if (a.r == 4)
+    SDOF_ALT_LAUNCH(4);
+  else if (a.r == 3)
+    SDOF_ALT_LAUNCH(3);
+  else
+    SDOF_ALT_LAUNCH(0);
+#undef SDOF_ALT_LAUNCH
+  SDOF_LAUNCH_CHECK(name);
+  return SDOF_OK;
+}
+
+}  // namespace sdof
+
+extern "C" {
+
+int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
+                     int radius, float* out, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(pyramid && coords && out, "sdof_corr_lookup: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "sdof_corr_lookup: bad sizes");
+  SDOF_REQUIRE(radius >= 0 && radius <= 8, "sdof_corr_lookup: radius must be in [0,8], got %d", radius);
+  SDOF_REQUIRE(B <= 65535, "sdof_corr_lookup: B > 65535 not supported");
+  sdof_pyramid_layout lay;
+  const int N1 = h1 * w1;
+  int rc = sdof_corr_pyramid_layout((int64_t)B * N1, h2, w2, levels, &lay);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  LookupLevels lv;
+  lv.levels = levels;
+  for (int l = 0; l < SDOF_MAX_LEVELS; ++l) {
+    const int ll = l < levels ? l : 0;
+    lv.base[l] = pyramid + lay.offset[ll];
+    lv.pitch[l] = lay.pitch[ll];
+    lv.h[l] = lay.h[ll];
+    lv.w[l] = lay.w[ll];
+    lv.wp[l] = lay.wp[ll];
+  }
+  const int D = 2 * radius + 1, T = (D + 1) * (D + 1), DD = D * D;
+  const size_t smem = ((size_t)levels * DD * kStagePitch + (size_t)kLookupPx * levels * T) * sizeof(float);
+  SDOF_REQUIRE(smem <= 200 * 1024, "sdof_corr_lookup: levels=%d radius=%d need %zu bytes of shared memory", levels, radius,
+               smem);
+  dim3 grid(ceil_div(N1, kLookupPx), B);
+  cudaStream_t st = as_stream(stream);
+#define SDOF_LOOKUP_LAUNCH(RT, LT)                                                                                      \
+  do {                                                                                                                  \
+    SDOF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    corr_lookup_kernel<RT, LT><<<grid, kLookupThreads, smem, st>>>(lv, coords, N1, radius, out);                        \
+  } while (0)
+  if (radius == 4 && levels == 4)
+    SDOF_LOOKUP_LAUNCH(4, 4);
+  else if (radius == 3 && levels == 4)
+    SDOF_LOOKUP_LAUNCH(3, 4);
+  else
+    SDOF_LOOKUP_LAUNCH(0, 0);
+#undef SDOF_LOOKUP_LAUNCH
+  SDOF_LAUNCH_CHECK("corr_lookup_kernel");
+  return SDOF_OK;
+}
+
+static int check_alt(const char* name, const float* fmap1, const float* fmap2, const float* coords, float* out, int B,
+                     int H1, int W1, int H2, int W2, int C, int radius) {
+  SDOF_REQUIRE(fmap1 && fmap2 && coords && out, "%s: NULL pointer", name);
+  SDOF_REQUIRE(B >= 0 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "%s: bad sizes", name);
+  SDOF_REQUIRE(C >= 4 && C % 4 == 0, "%s: C must be a positive multiple of 4, got %d", name, C);
+  SDOF_REQUIRE(radius >= 0 && radius <= 8, "%s: radius must be in [0,8], got %d", name, radius);
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2)) & 15) == 0,
+               "%s: feature maps must be 16-byte aligned", name);
+  return SDOF_OK;
+}
+
+int sdof_alt_corr_forward(const float* fmap1, const float* fmap2, const float* coords, int B, int H1, int W1, int H2,
+                          int W2, int C, int N, int radius, float* corr, sdof_stream_t stream) {
+  using namespace sdof;
+  int rc = check_alt("sdof_alt_corr_forward", fmap1, fmap2, coords, corr, B, H1, W1, H2, W2, C, radius);
+  if (rc) return rc;
+  SDOF_REQUIRE(N >= 1, "sdof_alt_corr_forward: N must be >= 1");
+  if (B == 0) return SDOF_OK;
+  const int D = 2 * radius + 1;
+  AltCorrArgs a;
+  a.fmap1 = fmap1;
+  a.fmap2 = fmap2;
+  a.coords = coords;
+  a.N1 = H1 * W1;
+  a.c_set = (long long)a.N1 * 2;  // [B,N,H1,W1,2]: sets are contiguous, (x,y) interleaved
+  a.c_px = 2;
+  a.c_xy = 1;
+  a.sets = N;
+  a.H2 = H2;
+  a.W2 = W2;
+  a.C = C;
+  a.r = radius;
+  a.coord_scale = 1.f;
+  a.out_scale = 1.f;
+  a.out = corr;  // [B, N*DD, N1]
+  a.out_channels = N * D * D;
+  a.chan_offset = 0;
+  return launch_alt_corr("sdof_alt_corr_forward", a, B, as_stream(stream));
+}
+
+int sdof_alt_corr_level(const float* fmap1, const float* fmap2_level, const float* coords, int B, int H1, int W1,
+                        int H2, int W2, int C, int radius, float coord_scale, float out_scale, int chan_offset,
+                        int out_channels, float* out, sdof_stream_t stream) {
+  using namespace sdof;
+  int rc = check_alt("sdof_alt_corr_level", fmap1, fmap2_level, coords, out, B, H1, W1, H2, W2, C, radius);
+  if (rc) return rc;
+  const int D = 2 * radius + 1;
+  SDOF_REQUIRE(chan_offset >= 0 && chan_offset + D * D <= out_channels, "sdof_alt_corr_level: channel window out of range");
+  if (B == 0) return SDOF_OK;
+  AltCorrArgs a;
+  a.fmap1 = fmap1;
+  a.fmap2 = fmap2_level;
+  a.coords = coords;
+  a.N1 = H1 * W1;
+  a.c_set = (long long)a.N1 * 2;  // [B,2,H1,W1] planar
+  a.c_px = 1;
+  a.c_xy = a.N1;
+  a.sets = 1;
+  a.H2 = H2;
+  a.W2 = W2;
+  a.C = C;
+  a.r = radius;
+  a.coord_scale = coord_scale;
+  a.out_scale = out_scale;
+  a.out = out;
+  a.out_channels = out_channels;
+  a.chan_offset = chan_offset;
+  return launch_alt_corr("sdof_alt_corr_level", a, B, as_stream(stream));
+}
+
+}  // extern "C"

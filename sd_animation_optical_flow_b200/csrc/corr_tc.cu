@@ -1,0 +1,679 @@
+// All-pairs correlation volume + 4-level pyramid on the 5th-gen tensor cores (SURVEY §8a C1+C2).
+//
+//   level0[b, m, n] = <fmap1[b,m,:], fmap2[b,n,:]> / sqrt(C)      m: source pixel, n: target pixel
+//   level(l+1)      = avg_pool2d(level l, 2, 2)  over the target dims
+//
+// Mapping to the hardware
+//   * Both operands are K-major in HBM (channels-last features), so TMA loads 128-byte-swizzled
+//     K-slabs straight from the feature tensors: A = 128 source pixels x 128 B, B = an 8x32
+//     SPATIAL patch of target pixels x 128 B (4-D box over [b, y, x, c]).  Because an N-tile is a
+//     spatial patch whose sides are multiples of 8, every 2x2 / 4x4 / 8x8 pooling window of the
+//     pyramid is complete inside one tile.
+//   * One elected thread issues tcgen05.mma (M=128, N=256, kind::tf32 or kind::f16) into one of
+//     two 256-column TMEM accumulators; tcgen05.commit releases smem stages / publishes the
+//     accumulator through mbarriers.
+//   * Four epilogue warps read the accumulator with tcgen05.ld (thread = source pixel, registers
+//     = the 8x32 patch), scale, build levels 1-3 in registers in ATen's summation order, stage
+//     every level in swizzled shared memory and write it with TMA stores whose tensor maps carry
+//     the true (floor-pooled) level sizes, so partial tiles and odd sizes are clipped by hardware.
+//   * Persistent grid (one CTA per SM), tiles ordered target-patch-fastest so concurrently running
+//     CTAs share the same A rows and the L2-resident fmap2.
+//
+// Roofline: 2*N1*N2*C flops on the tensor pipe vs. 4*N1*sum_l(h_l*w_l) bytes of stores to HBM
+// (S config: 19.33 GFLOP vs 200.5 MB -> the kernel is HBM-store-bound).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <string.h>
+
+#include <mutex>
+
+#include "corr.cuh"
+
+namespace sdof {
+
+constexpr int kBM = 128;             // source pixels per tile (TMEM lanes)
+constexpr int kPatchY = 8;           // target patch rows
+constexpr int kPatchX = 32;          // target patch cols
+constexpr int kBN = kPatchY * kPatchX;  // 256 accumulator columns
+constexpr int kSlabBytes = 128;      // K-slab = one 128B swizzle atom row
+constexpr int kStages = 3;
+constexpr int kAStage = kBM * kSlabBytes;  // 16384
+constexpr int kBStage = kBN * kSlabBytes;  // 32768
+constexpr int kEpiWarps = 4;
+constexpr int kEpiL0 = 0, kEpiL1 = 8192, kEpiL2 = 16384, kEpiL3 = 18432, kEpiWarpBytes = 19456;
+constexpr int kSmemOperands = kStages * (kAStage + kBStage);          // 147456
+constexpr int kSmemEpi = kEpiWarps * kEpiWarpBytes;                   // 77824
+constexpr int kSmemBars = 128;
+constexpr int kSmemTotal = kSmemOperands + kSmemEpi + kSmemBars + 1024;  // + alignment slack
+constexpr int kThreads = (kEpiWarps + 2) * 32;                        // 4 epilogue + TMA + MMA
+constexpr int kMaxTerms = 3;
+constexpr int kTcLevels = 4;
+
+struct TcMaps {
+  CUtensorMap a[kMaxTerms];
+  CUtensorMap b[kMaxTerms];
+  CUtensorMap out[kTcLevels];
+};
+
+struct TcArgs {
+  int B, n1, h2, w2;
+  int m_tiles, ty_tiles, tx_tiles;
+  int nterms, kslabs, slab_elems;
+  int levels;          // pyramid levels written by this kernel (1..4)
+  float scale;         // 1/sqrt(C)
+  float divisor;       // sqrt(C) (used when the reciprocal is not exact)
+  int use_div;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("sdof corr_tc: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (kBf16) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread i = lane base+i).
+// tcgen05.ld is asynchronous: the registers are only valid after tcgen05.wait::ld.  The wait below
+// takes every loaded register as a read-write operand so the compiler cannot schedule a consumer
+// above it.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[32], uint32_t (&b)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]), "+r"(b[16]), "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]), "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+               :
+               : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128B swizzle, 8-row atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)0 << 16;                       // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+
+// UMMA instruction descriptor (kind::tf32 / kind::f16): fp32 accumulate, K-major A and B.
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16) {
+  return (1u << 4)                        // D format: F32
+         | ((bf16 ? 1u : 2u) << 7)        // A format: BF16 (kind::f16) / TF32 (kind::tf32)
+         | ((bf16 ? 1u : 2u) << 10)       // B format
+         | (0u << 15) | (0u << 16)        // A, B K-major
+         | ((uint32_t)(kBN >> 3) << 17)   // N
+         | ((uint32_t)(kBM >> 4) << 24);  // M
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float pool4(float a, float b, float c, float d) {
+  // ATen avg_pool2d: ((a00 + a01) + a10) + a11, then / 4
+  return __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d) * 0.25f;
+}
+
+// ----------------------------------------------------------------------------- the kernel
+template <bool kBf16>
+__global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __grid_constant__ TcMaps maps,
+                                                                     const TcArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + kStages * kAStage;
+  const uint32_t smem_epi = base + kSmemOperands;
+  const uint32_t bars = base + kSmemOperands + kSmemEpi;
+  const uint32_t bar_full = bars;                  // [kStages]
+  const uint32_t bar_empty = bars + 8 * kStages;   // [kStages]
+  const uint32_t bar_tfull = bars + 16 * kStages;  // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;      // [2]
+  const uint32_t tmem_slot = bar_tempty + 16;      // u32
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = args.ty_tiles * args.tx_tiles;
+  const int total_tiles = args.B * args.m_tiles * n_tiles;
+  const int kk_total = args.nterms * args.kslabs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kEpiWarps && lane == 0) {
+    for (int t = 0; t < args.nterms; ++t) {
+      prefetch_tmap(&maps.a[t]);
+      prefetch_tmap(&maps.b[t]);
+    }
+    for (int l = 0; l < args.levels; ++l) prefetch_tmap(&maps.out[l]);
+  }
+  if (warp == kEpiWarps + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+  if (warp == kEpiWarps) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        const int mt = (tile / n_tiles) % args.m_tiles;
+        const int b = tile / (n_tiles * args.m_tiles);
+        const int ty = nt / args.tx_tiles, tx = nt - ty * args.tx_tiles;
+        for (int term = 0; term < args.nterms; ++term) {
+          for (int k = 0; k < args.kslabs; ++k) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(bar_full + 8 * stage, kAStage + kBStage);
+            tma_load_3d(smem_a + stage * kAStage, &maps.a[term], bar_full + 8 * stage, k * args.slab_elems, mt * kBM, b);
+            tma_load_4d(smem_b + stage * kBStage, &maps.b[term], bar_full + 8 * stage, k * args.slab_elems,
+                        tx * kPatchX, ty * kPatchY, b);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBf16);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * ab, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + ab * kBN;
+        for (int kk = 0; kk < kk_total; ++kk) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_a + stage * kAStage);
+          const uint64_t bdesc = make_smem_desc(smem_b + stage * kBStage);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // 4 x 32 bytes of K per 128-byte slab (UMMA_K = 8 tf32 / 16 bf16)
+            tc_mma<kBf16>(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (kk > 0 || j > 0) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(bar_tfull + 8 * ab);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps 0..3
+    const uint32_t epi = smem_epi + warp * kEpiWarpBytes;
+    const uint32_t lane_row128 = epi + kEpiL0 + lane * 128;
+    const uint32_t sw128 = lane & 7, sw64 = (lane >> 1) & 3, sw32 = (lane >> 2) & 1;
+    const int levels = args.levels;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % n_tiles;
+      const int mt = (tile / n_tiles) % args.m_tiles;
+      const int b = tile / (n_tiles * args.m_tiles);
+      const int ty = nt / args.tx_tiles, tx = nt - ty * args.tx_tiles;
+      const int m0 = mt * kBM + warp * 32;
+      const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * ab, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ab * kBN;
+      float s1[8];  // horizontal pair sums of the previous level-1 row (for level 2)
+      float s2[4];  // horizontal pair sums of the previous level-2 row (for level 3)
+#pragma unroll
+      for (int rp = 0; rp < 4; ++rp) {
+        uint32_t ua[32], ub[32];
+        tmem_ld32(taddr + rp * 64, ua);       // patch row 2*rp
+        tmem_ld32(taddr + rp * 64 + 32, ub);  // patch row 2*rp+1
+        tmem_ld_wait(ua, ub);
+        float ra[32], rb[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          ra[i] = __uint_as_float(ua[i]);
+          rb[i] = __uint_as_float(ub[i]);
+        }
+        if (rp == 3) {
+          // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+        }
+        if (args.use_div) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            ra[i] = __fdiv_rn(ra[i], args.divisor);
+            rb[i] = __fdiv_rn(rb[i], args.divisor);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            ra[i] *= args.scale;
+            rb[i] *= args.scale;
+          }
+        }
+        // the previous TMA stores must have finished READING the staging buffers
+        if (lane == 0) tma_store_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          st_shared_v4(lane_row128 + ((c ^ sw128) << 4), ra[4 * c], ra[4 * c + 1], ra[4 * c + 2], ra[4 * c + 3]);
+          st_shared_v4(lane_row128 + 4096 + ((c ^ sw128) << 4), rb[4 * c], rb[4 * c + 1], rb[4 * c + 2], rb[4 * c + 3]);
+        }
+        if (levels > 1) {
+          float l1[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) l1[j] = pool4(ra[2 * j], ra[2 * j + 1], rb[2 * j], rb[2 * j + 1]);
+          const uint32_t l1row = epi + kEpiL1 + rp * 2048 + lane * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            st_shared_v4(l1row + ((c ^ sw64) << 4), l1[4 * c], l1[4 * c + 1], l1[4 * c + 2], l1[4 * c + 3]);
+          if (levels > 2) {
+            if ((rp & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) s1[j] = __fadd_rn(l1[2 * j], l1[2 * j + 1]);
+            } else {
+              float l2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                l2[j] = __fadd_rn(__fadd_rn(s1[j], l1[2 * j]), l1[2 * j + 1]) * 0.25f;
+              const uint32_t l2row = epi + kEpiL2 + (rp >> 1) * 1024 + lane * 32;
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+                st_shared_v4(l2row + ((c ^ sw32) << 4), l2[4 * c], l2[4 * c + 1], l2[4 * c + 2], l2[4 * c + 3]);
+              if (levels > 3) {
+                if (rp == 1) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) s2[j] = __fadd_rn(l2[2 * j], l2[2 * j + 1]);
+                } else {
+                  float l3[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    l3[j] = __fadd_rn(__fadd_rn(s2[j], l2[2 * j]), l2[2 * j + 1]) * 0.25f;
+                  st_shared_v4(epi + kEpiL3 + lane * 16, l3[0], l3[1], l3[2], l3[3]);
+                }
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&maps.out[0], epi + kEpiL0, tx * kPatchX, m0, ty * kPatchY + 2 * rp, b);
+          if (rp == 3) {
+            if (levels > 1) tma_store_4d(&maps.out[1], epi + kEpiL1, tx * (kPatchX / 2), m0, ty * (kPatchY / 2), b);
+            if (levels > 2) tma_store_4d(&maps.out[2], epi + kEpiL2, tx * (kPatchX / 4), m0, ty * (kPatchY / 4), b);
+            if (levels > 3) tma_store_4d(&maps.out[3], epi + kEpiL3, tx * (kPatchX / 8), m0, ty * (kPatchY / 8), b);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- operand preparation
+// 3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); products hi*hi + hi*lo + lo*hi keep
+// ~21 mantissa bits.  Both parts are exactly representable in tf32, so the tensor core's own
+// fp32->tf32 conversion cannot change them.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, int64_t n4,
+                                                         float4* __restrict__ hi, float4* __restrict__ lo) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[k]));
+      h[k] = __uint_as_float(hb);
+      const float rem = __fsub_rn(in[k], h[k]);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+      l[k] = __uint_as_float(lb);
+    }
+    hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+    lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// Plain TF32 mode: round the features to tf32 (nearest, ties away) once, so the result does not
+// depend on how the tensor core would truncate raw fp32 bits (truncation costs ~10x in flow error).
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ x, int64_t n4,
+                                                         float4* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    uint32_t a, b, c, d;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w));
+    y[i] = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+  }
+}
+
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float4* __restrict__ x, int64_t n4, uint2* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&p0);
+    o.y = *reinterpret_cast<const uint32_t*>(&p1);
+    y[i] = o;
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SDOF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SDOF_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return SDOF_OK;
+}
+
+int64_t corr_tc_workspace_bytes(int B, int n1, int n2, int C, int precision) {
+  const int64_t e1 = (int64_t)B * n1 * C, e2 = (int64_t)B * n2 * C;
+  auto al = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+  if (precision == SDOF_PREC_3XTF32) return 2 * al(e1 * 4) + 2 * al(e2 * 4);
+  if (precision == SDOF_PREC_BF16) return al(e1 * 2) + al(e2 * 2);
+  if (precision == SDOF_PREC_TF32) return al(e1 * 4) + al(e2 * 4);
+  return 0;
+}
+
+int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, int precision,
+                          float* pyramid, const sdof_pyramid_layout& lay, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t st) {
+  const bool bf16 = precision == SDOF_PREC_BF16;
+  const int n2 = h2 * w2;
+  if (C % (bf16 ? 8 : 4) != 0) return SDOF_ERR_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2) | reinterpret_cast<uintptr_t>(pyramid)) & 15) != 0)
+    return SDOF_ERR_UNSUPPORTED;
+  if (B > 65535) return SDOF_ERR_UNSUPPORTED;
+  const int64_t need = corr_tc_workspace_bytes(B, n1, n2, C, precision);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need))
+    return fail(SDOF_ERR_INVALID, "sdof_corr_volume_pyramid: workspace of %lld bytes required, got %lld", (long long)need,
+                (long long)workspace_bytes);
+  if (need > 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return fail(SDOF_ERR_INVALID, "sdof_corr_volume_pyramid: workspace must be 256-byte aligned");
+
+  // levels this kernel writes: at most 4 and only those with a non-empty map
+  int tc_levels = 0;
+  while (tc_levels < lay.levels && tc_levels < kTcLevels && lay.h[tc_levels] >= 1 && lay.w[tc_levels] >= 1) ++tc_levels;
+  if (tc_levels < 1) return SDOF_ERR_UNSUPPORTED;
+
+  const int64_t e1 = (int64_t)B * n1 * C, e2 = (int64_t)B * n2 * C;
+  auto al = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+  const void* a_ptr[kMaxTerms];
+  const void* b_ptr[kMaxTerms];
+  int nterms = 1;
+  if (precision == SDOF_PREC_3XTF32) {
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    float* a_hi = reinterpret_cast<float*>(w);
+    float* a_lo = reinterpret_cast<float*>(w + al(e1 * 4));
+    float* b_hi = reinterpret_cast<float*>(w + 2 * al(e1 * 4));
+    float* b_lo = reinterpret_cast<float*>(w + 2 * al(e1 * 4) + al(e2 * 4));
+    split_tf32_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4,
+                                                               reinterpret_cast<float4*>(a_hi), reinterpret_cast<float4*>(a_lo));
+    SDOF_LAUNCH_CHECK("split_tf32_kernel");
+    split_tf32_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4,
+                                                               reinterpret_cast<float4*>(b_hi), reinterpret_cast<float4*>(b_lo));
+    SDOF_LAUNCH_CHECK("split_tf32_kernel");
+    // small terms first, the dominant hi*hi product last
+    a_ptr[0] = a_lo; b_ptr[0] = b_hi;
+    a_ptr[1] = a_hi; b_ptr[1] = b_lo;
+    a_ptr[2] = a_hi; b_ptr[2] = b_hi;
+    nterms = 3;
+  } else if (bf16) {
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    void* a16 = w;
+    void* b16 = w + al(e1 * 2);
+    to_bf16_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4,
+                                                            reinterpret_cast<uint2*>(a16));
+    SDOF_LAUNCH_CHECK("to_bf16_kernel");
+    to_bf16_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4,
+                                                            reinterpret_cast<uint2*>(b16));
+    SDOF_LAUNCH_CHECK("to_bf16_kernel");
+    a_ptr[0] = a16;
+    b_ptr[0] = b16;
+  } else {
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    float* a_r = reinterpret_cast<float*>(w);
+    float* b_r = reinterpret_cast<float*>(w + al(e1 * 4));
+    round_tf32_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4,
+                                                               reinterpret_cast<float4*>(a_r));
+    SDOF_LAUNCH_CHECK("round_tf32_kernel");
+    round_tf32_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4,
+                                                               reinterpret_cast<float4*>(b_r));
+    SDOF_LAUNCH_CHECK("round_tf32_kernel");
+    a_ptr[0] = a_r;
+    b_ptr[0] = b_r;
+  }
+
+  const int es = bf16 ? 2 : 4;
+  const int slab_elems = kSlabBytes / es;
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  for (int t = 0; t < nterms; ++t) {
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)n1, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)C * es, (cuuint64_t)n1 * C * es};
+      cuuint32_t box[3] = {(cuuint32_t)slab_elems, (cuuint32_t)kBM, 1};
+      if ((rc = encode_map(&maps.a[t], dt, 3, a_ptr[t], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap1"))) return rc;
+    }
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)w2 * C * es, (cuuint64_t)n2 * C * es};
+      cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)kPatchX, (cuuint32_t)kPatchY, 1};
+      if ((rc = encode_map(&maps.b[t], dt, 4, b_ptr[t], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap2"))) return rc;
+    }
+  }
+  // output maps: dims (x, m, y, b) so a [rows][32 m][x] box lands as one 128/64/32/16-byte row per source pixel
+  const CUtensorMapSwizzle out_sw[kTcLevels] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
+  const cuuint32_t out_bx[kTcLevels] = {32, 16, 8, 4};
+  const cuuint32_t out_by[kTcLevels] = {2, 4, 2, 1};
+  for (int l = 0; l < tc_levels; ++l) {
+    cuuint64_t dims[4] = {(cuuint64_t)lay.w[l], (cuuint64_t)n1, (cuuint64_t)lay.h[l], (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[l] * 4, (cuuint64_t)lay.wp[l] * 4, (cuuint64_t)n1 * lay.pitch[l] * 4};
+    cuuint32_t box[4] = {out_bx[l], 32, out_by[l], 1};
+    if ((rc = encode_map(&maps.out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyramid + lay.offset[l], dims, strides, box,
+                         out_sw[l], "pyramid level")))
+      return rc;
+  }
+
+  TcArgs args;
+  args.B = B;
+  args.n1 = n1;
+  args.h2 = h2;
+  args.w2 = w2;
+  args.m_tiles = ceil_div(n1, kBM);
+  args.ty_tiles = ceil_div(h2, kPatchY);
+  args.tx_tiles = ceil_div(w2, kPatchX);
+  args.nterms = nterms;
+  args.slab_elems = slab_elems;
+  args.kslabs = ceil_div(C, slab_elems);
+  args.levels = tc_levels;
+  const float sq = sqrtf((float)C);
+  args.scale = 1.0f / sq;
+  args.divisor = sq;
+  args.use_div = !((C & (C - 1)) == 0 && (__builtin_ctz(C) % 2 == 0));
+  const int64_t total_tiles = (int64_t)B * args.m_tiles * args.ty_tiles * args.tx_tiles;
+  if (total_tiles > 0x7fffffff) return SDOF_ERR_UNSUPPORTED;
+  const int grid = (int)(total_tiles < sm_count() ? total_tiles : sm_count());
+  if (bf16) {
+    SDOF_CUDA(cudaFuncSetAttribute(corr_volume_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    corr_volume_tc_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(maps, args);
+  } else {
+    SDOF_CUDA(cudaFuncSetAttribute(corr_volume_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    corr_volume_tc_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(maps, args);
+  }
+  SDOF_LAUNCH_CHECK("corr_volume_tc_kernel");
+  // pyramid levels beyond the four fused ones (or beyond an empty level) come from the pooling kernel
+  if (tc_levels < lay.levels) return launch_pool_levels(pyramid, lay, (int64_t)B * n1, tc_levels - 1, st);
+  return SDOF_OK;
+}
+
+}  // namespace sdof
+
+extern "C" {
+
+int64_t sdof_corr_volume_workspace_bytes(int B, int h1, int w1, int h2, int w2, int C, int precision) {
+  return sdof::corr_tc_workspace_bytes(B, h1 * w1, h2 * w2, C, precision);
+}
+
+int sdof_corr_volume_pyramid(const float* fmap1, const float* fmap2, int B, int h1, int w1, int h2, int w2, int C,
+                             int levels, int precision, float* pyramid, void* workspace, int64_t workspace_bytes,
+                             sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(fmap1 && fmap2 && pyramid, "sdof_corr_volume_pyramid: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "sdof_corr_volume_pyramid: bad sizes");
+  SDOF_REQUIRE(C >= 4 && C % 4 == 0, "sdof_corr_volume_pyramid: C must be a positive multiple of 4, got %d", C);
+  SDOF_REQUIRE(precision >= SDOF_PREC_TF32 && precision <= SDOF_PREC_FP32, "sdof_corr_volume_pyramid: unknown precision %d",
+               precision);
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2) | reinterpret_cast<uintptr_t>(pyramid)) & 15) == 0,
+               "sdof_corr_volume_pyramid: pointers must be 16-byte aligned");
+  const int n1 = h1 * w1;
+  sdof_pyramid_layout lay;
+  int rc = sdof_corr_pyramid_layout((int64_t)B * n1, h2, w2, levels, &lay);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  cudaStream_t st = as_stream(stream);
+  if (precision != SDOF_PREC_FP32) {
+    rc = launch_corr_volume_tc(fmap1, fmap2, B, n1, h2, w2, C, precision, pyramid, lay, workspace, workspace_bytes, st);
+    if (rc != SDOF_ERR_UNSUPPORTED) return rc;
+    // shapes the TMA path cannot express fall through to the CUDA-core kernel
+  }
+  return launch_corr_volume_fp32(fmap1, fmap2, B, n1, h2, w2, C, pyramid, lay, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// Shared host/device helpers for libsdof_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sdof_b200.h"
+
+namespace sdof {
+
+// ---- error plumbing (thread-local text behind sdof_last_error) -------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SDOF_REQUIRE(cond, ...)                                   \
+  do {                                                            \
+    if (!(cond)) return ::sdof::fail(SDOF_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define SDOF_CUDA(expr)                                                                            \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::sdof::fail(SDOF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                          __FILE__, __LINE__);                                                     \
+  } while (0)
+
+// after a kernel launch: surface launch-configuration errors without syncing
+#define SDOF_LAUNCH_CHECK(name)                                                                    \
+  do {                                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess)                                                                         \
+      return ::sdof::fail(SDOF_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    ::sdof::count_launch();                                                                        \
+  } while (0)
+
+inline cudaStream_t as_stream(sdof_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached multiProcessorCount of the current device
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// grid sized for a grid-stride loop: enough CTAs for `work_items` but capped at a
+// whole number of waves (multiple of the SM count).
+inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
+  int64_t need = ceil_div64(work_items, threads);
+  int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// host-side tables (cubic_table.cpp)
+const int16_t* cubic_table_i16_host();  // [1024][16]
+const float* cubic_table_f32_host();    // [1024][16]
+void ellipse_half_widths_host(int ksize, int32_t* out);
+
+}  // namespace sdof

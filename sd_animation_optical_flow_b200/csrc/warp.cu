@@ -1,0 +1,267 @@
+// Backward warp kernels: bit-exact cv2.remap(INTER_CUBIC,
+// BORDER_CONSTANT) for u8, fp32-weight cubic for float images, and a bilinear mode
+// with grid_sample(align_corners=True, zeros) semantics.
+//
+// HBM-bound byte work: 14 B/pixel algorithmic (8 flow + 3 src + 3 dst).  One thread
+// produces 4 consecutive pixels (two 16-byte flow loads, three 4-byte stores); source
+// taps are fetched as aligned 32-bit words and multiplied with packed int16 weights by
+// dp2a, so the LSU/ALU cost per pixel stays close to the HBM time.
+#include <mutex>
+
+#include "warp.cuh"
+
+namespace sdof {
+
+int get_cubic_tables(CubicTables* out) {
+  static std::mutex mu;
+  static CubicTables tabs[64] = {};
+  int dev = 0;
+  SDOF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(SDOF_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (!tabs[dev].i16) {
+    void* p = nullptr;
+    const size_t bi = sizeof(int16_t) * 1024 * 16, bf = sizeof(float) * 1024 * 16;
+    SDOF_CUDA(cudaMalloc(&p, bi + bf));
+    SDOF_CUDA(cudaMemcpy(p, cubic_table_i16_host(), bi, cudaMemcpyHostToDevice));
+    SDOF_CUDA(cudaMemcpy(static_cast<char*>(p) + bi, cubic_table_f32_host(), bf, cudaMemcpyHostToDevice));
+    tabs[dev].i16 = static_cast<const int16_t*>(p);
+    tabs[dev].f32 = reinterpret_cast<const float*>(static_cast<char*>(p) + bi);
+  }
+  *out = tabs[dev];
+  return SDOF_OK;
+}
+
+// ---------------------------------------------------------------- cubic, u8, C = 3
+// grid-stride over groups of 4 pixels of the flattened [B*H*W] output.
+__global__ void __launch_bounds__(256) warp_cubic_u8c3_kernel(const int16_t* __restrict__ tab,
+                                                              const unsigned char* __restrict__ src,
+                                                              const float* __restrict__ flow,
+                                                              unsigned char* __restrict__ dst, int B, int Hs, int Ws,
+                                                              int H, int W, int64_t src_bstride, float sign,
+                                                              const unsigned char* __restrict__ src_end,
+                                                              int dst_vec_ok) {
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t ngroups = (npix + 3) >> 2;
+  const int64_t hw = (int64_t)H * W;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = g << 2;
+    float fl[8];
+    if (p0 + 4 <= npix) {
+      const float4 f0 = __ldcs(reinterpret_cast<const float4*>(flow + p0 * 2));
+      const float4 f1 = __ldcs(reinterpret_cast<const float4*>(flow + p0 * 2) + 1);
+      fl[0] = f0.x; fl[1] = f0.y; fl[2] = f0.z; fl[3] = f0.w;
+      fl[4] = f1.x; fl[5] = f1.y; fl[6] = f1.z; fl[7] = f1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = p0 + i < npix;
+        fl[2 * i] = ok ? flow[(p0 + i) * 2] : 0.f;
+        fl[2 * i + 1] = ok ? flow[(p0 + i) * 2 + 1] : 0.f;
+      }
+    }
+    unsigned px[4];
+    int b, y, x;
+    decompose_pixel(p0, hw, W, b, y, x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (p0 + i < npix) {
+        const FixedCoord fc = fixed_coord(map_coord(x, fl[2 * i], sign), map_coord(y, fl[2 * i + 1], sign));
+        px[i] = cubic_u8_c3(tab, src + b * src_bstride, src_end, Hs, Ws, fc);
+      } else {
+        px[i] = 0;
+      }
+      if (++x == W) {
+        x = 0;
+        if (++y == H) {
+          y = 0;
+          ++b;
+        }
+      }
+    }
+    if (dst_vec_ok && p0 + 4 <= npix) {
+      // 4 pixels x 3 bytes = three aligned words
+      const unsigned w0 = px[0] | (px[1] << 24);
+      const unsigned w1 = (px[1] >> 8) | (px[2] << 16);
+      const unsigned w2 = (px[2] >> 16) | (px[3] << 8);
+      unsigned* o = reinterpret_cast<unsigned*>(dst + p0 * 3);
+      __stcs(o, w0);
+      __stcs(o + 1, w1);
+      __stcs(o + 2, w2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (p0 + i < npix) {
+          unsigned char* o = dst + (p0 + i) * 3;
+          o[0] = (unsigned char)(px[i] & 0xff);
+          o[1] = (unsigned char)((px[i] >> 8) & 0xff);
+          o[2] = (unsigned char)((px[i] >> 16) & 0xff);
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- generic paths
+template <typename T, bool kCubic>
+__global__ void __launch_bounds__(256) warp_generic_kernel(CubicTables tabs, const T* __restrict__ src,
+                                                           const float* __restrict__ flow,
+                                                           T* __restrict__ dst, int B, int Hs, int Ws, int C, int H,
+                                                           int W, int64_t src_bstride, float sign) {
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t hw = (int64_t)H * W;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    int b, y, x;
+    decompose_pixel(p, hw, W, b, y, x);
+    const float2 f = *reinterpret_cast<const float2*>(flow + p * 2);
+    const T* img = src + b * src_bstride;
+    if (kCubic) {
+      const FixedCoord fc = fixed_coord(map_coord(x, f.x, sign), map_coord(y, f.y, sign));
+      if (sizeof(T) == 1) {
+        int acc[4] = {0, 0, 0, 0};
+        const int16_t* wt = tabs.i16 + fc.fidx * 16;
+        for (int ky = 0; ky < 4; ++ky) {
+          const int yy = fc.sy + ky;
+          if ((unsigned)yy >= (unsigned)Hs) continue;
+          for (int kx = 0; kx < 4; ++kx) {
+            const int xx = fc.sx + kx;
+            if ((unsigned)xx >= (unsigned)Ws) continue;
+            const int w = wt[ky * 4 + kx];
+            const T* q = img + ((int64_t)yy * Ws + xx) * C;
+            for (int c = 0; c < C; ++c) acc[c] += w * (int)q[c];
+          }
+        }
+        for (int c = 0; c < C; ++c) dst[p * C + c] = (T)cast_q15_u8(acc[c]);
+      } else {
+        // float image: same 1/32-pixel quantisation, fp32 weights, taps accumulated in
+        // OpenCV's order (ky outer, kx inner), no FMA contraction.
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* wt = tabs.f32 + fc.fidx * 16;
+        for (int ky = 0; ky < 4; ++ky) {
+          const int yy = fc.sy + ky;
+          for (int kx = 0; kx < 4; ++kx) {
+            const int xx = fc.sx + kx;
+            const bool in = (unsigned)yy < (unsigned)Hs && (unsigned)xx < (unsigned)Ws;
+            const float w = wt[ky * 4 + kx];
+            for (int c = 0; c < C; ++c) {
+              const float v = in ? (float)img[((int64_t)yy * Ws + xx) * C + c] : 0.f;
+              acc[c] = __fadd_rn(acc[c], __fmul_rn(v, w));
+            }
+          }
+        }
+        for (int c = 0; c < C; ++c) dst[p * C + c] = (T)acc[c];
+      }
+    } else {
+      // bilinear, zeros padding, align_corners=True pixel coordinates
+      const float xs = __fadd_rn((float)x, __fmul_rn(sign, f.x));
+      const float ys = __fadd_rn((float)y, __fmul_rn(sign, f.y));
+      const float x0f = floorf(xs), y0f = floorf(ys);
+      const float ax = __fsub_rn(xs, x0f), ay = __fsub_rn(ys, y0f);
+      // clamp before the int conversion so NaN/huge coordinates land outside the image
+      const int x0 = (x0f >= -2.f && x0f <= (float)Ws + 1.f) ? (int)x0f : -2;
+      const int y0 = (y0f >= -2.f && y0f <= (float)Hs + 1.f) ? (int)y0f : -2;
+      const float w00 = __fmul_rn(__fsub_rn(1.f, ax), __fsub_rn(1.f, ay));
+      const float w01 = __fmul_rn(ax, __fsub_rn(1.f, ay));
+      const float w10 = __fmul_rn(__fsub_rn(1.f, ax), ay);
+      const float w11 = __fmul_rn(ax, ay);
+      const bool vx0 = (unsigned)x0 < (unsigned)Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)Ws;
+      const bool vy0 = (unsigned)y0 < (unsigned)Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)Hs;
+      for (int c = 0; c < C; ++c) {
+        const float v00 = (vx0 && vy0) ? (float)img[((int64_t)y0 * Ws + x0) * C + c] : 0.f;
+        const float v01 = (vx1 && vy0) ? (float)img[((int64_t)y0 * Ws + x0 + 1) * C + c] : 0.f;
+        const float v10 = (vx0 && vy1) ? (float)img[((int64_t)(y0 + 1) * Ws + x0) * C + c] : 0.f;
+        const float v11 = (vx1 && vy1) ? (float)img[((int64_t)(y0 + 1) * Ws + x0 + 1) * C + c] : 0.f;
+        float r = __fmul_rn(v00, w00);
+        r = __fadd_rn(r, __fmul_rn(v01, w01));
+        r = __fadd_rn(r, __fmul_rn(v10, w10));
+        r = __fadd_rn(r, __fmul_rn(v11, w11));
+        if (sizeof(T) == 1) {
+          float q = rintf(r);
+          q = q < 0.f ? 0.f : (q > 255.f ? 255.f : q);
+          dst[p * C + c] = (T)q;
+        } else {
+          dst[p * C + c] = (T)r;
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+static int check_warp_args(const char* name, const T* src, const float* flow, int B, int Hs, int Ws, int C, int H, int W,
+                           float sign, T* dst) {
+  SDOF_REQUIRE(src && flow && dst, "%s: NULL pointer", name);
+  SDOF_REQUIRE(B >= 0 && Hs >= 1 && Ws >= 1 && H >= 1 && W >= 1, "%s: bad sizes B=%d Hs=%d Ws=%d H=%d W=%d", name, B, Hs,
+               Ws, H, W);
+  SDOF_REQUIRE(C >= 1 && C <= 4, "%s: C must be in 1..4, got %d", name, C);
+  SDOF_REQUIRE(sign == 1.0f || sign == -1.0f, "%s: sign must be +1 or -1", name);
+  SDOF_REQUIRE((reinterpret_cast<uintptr_t>(flow) & 7) == 0, "%s: flow must be 8-byte aligned", name);
+  SDOF_REQUIRE(Ws <= 32767 && Hs <= 32767, "%s: source larger than 32767 (cv2.remap limit)", name);
+  return SDOF_OK;
+}
+
+template <typename T, bool kCubic>
+static int launch_generic(const char* name, const T* src, const float* flow, int B, int src_batched, int Hs, int Ws,
+                          int C, int H, int W, float sign, T* dst, sdof_stream_t stream) {
+  int rc = check_warp_args(name, src, flow, B, Hs, Ws, C, H, W, sign, dst);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  CubicTables tabs = {nullptr, nullptr};
+  if (kCubic && (rc = get_cubic_tables(&tabs))) return rc;
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t bstride = src_batched ? (int64_t)Hs * Ws * C : 0;
+  warp_generic_kernel<T, kCubic><<<grid_for(npix, 256, 8), 256, 0, as_stream(stream)>>>(tabs, src, flow, dst, B, Hs, Ws, C,
+                                                                                         H, W, bstride, sign);
+  SDOF_LAUNCH_CHECK(name);
+  return SDOF_OK;
+}
+
+}  // namespace sdof
+
+extern "C" {
+
+int sdof_warp_cubic_u8(const uint8_t* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                       int W, float sign, uint8_t* dst, sdof_stream_t stream) {
+  using namespace sdof;
+  if (C != 3)
+    return launch_generic<unsigned char, true>("sdof_warp_cubic_u8", src, flow, B, src_batched, Hs, Ws, C, H, W, sign,
+                                               dst, stream);
+  int rc = check_warp_args("sdof_warp_cubic_u8", src, flow, B, Hs, Ws, C, H, W, sign, dst);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  CubicTables tabs;
+  if ((rc = get_cubic_tables(&tabs))) return rc;
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t img_bytes = (int64_t)Hs * Ws * 3;
+  const int64_t bstride = src_batched ? img_bytes : 0;
+  // word-aligned fast path needs a 4-byte aligned source; otherwise force the tap loop
+  const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+  const uint8_t* src_end = src_aligned ? src + (src_batched ? (int64_t)B : 1) * img_bytes : src;
+  const int flow_vec = (reinterpret_cast<uintptr_t>(flow) & 15) == 0;
+  if (!flow_vec) return fail(SDOF_ERR_INVALID, "sdof_warp_cubic_u8: flow must be 16-byte aligned");
+  const int dst_vec = (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+  const int64_t ngroups = (npix + 3) / 4;
+  warp_cubic_u8c3_kernel<<<grid_for(ngroups, 256, 8), 256, 0, as_stream(stream)>>>(tabs.i16, src, flow, dst, B, Hs, Ws, H, W,
+                                                                                    bstride, sign, src_end, dst_vec);
+  SDOF_LAUNCH_CHECK("warp_cubic_u8c3_kernel");
+  return SDOF_OK;
+}
+
+int sdof_warp_cubic_f32(const float* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                        int W, float sign, float* dst, sdof_stream_t stream) {
+  return sdof::launch_generic<float, true>("sdof_warp_cubic_f32", src, flow, B, src_batched, Hs, Ws, C, H, W, sign, dst,
+                                           stream);
+}
+
+int sdof_warp_bilinear_u8(const uint8_t* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                          int W, float sign, uint8_t* dst, sdof_stream_t stream) {
+  return sdof::launch_generic<unsigned char, false>("sdof_warp_bilinear_u8", src, flow, B, src_batched, Hs, Ws, C, H, W,
+                                                    sign, dst, stream);
+}
+
+int sdof_warp_bilinear_f32(const float* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
+                           int W, float sign, float* dst, sdof_stream_t stream) {
+  return sdof::launch_generic<float, false>("sdof_warp_bilinear_f32", src, flow, B, src_batched, Hs, Ws, C, H, W, sign,
+                                            dst, stream);
+}
+
+}  // extern "C"

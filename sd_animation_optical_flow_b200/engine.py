@@ -1,0 +1,170 @@
+"""Device-resident flow engine: the batched, stream-ordered form of the reference's
+`RAFT_2.calc` (ofgen.py:55-79) plus the `estimate_flow()` / `warp()` call surface the
+north star names, so a clip's flow -> warp -> mask -> composite never leaves the GPU.
+
+    eng  = RaftEngine(iters=20)                       # random-init or eng.load_checkpoint(path)
+    flow = eng.estimate_flow(img1_u8, img2_u8)        # [B,H,W,3] RGB uint8 CUDA -> [B,H,W,2] fp32
+    out  = warp(stylised_key_u8, flow)                # bit-exact cv2.remap cubic on the device
+
+The convolutions run in PyTorch/cuDNN; the all-pairs correlation volume + pyramid, the
+per-iteration lookup, the warp and the mask/composite steps run in this package's sm_100a
+kernels.  The whole forward for one input shape can be captured into a CUDA graph
+(`use_cuda_graph=True`) so the ~1000 launches of a 20-iteration pass replay without host work.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .raft import RAFT, InputPadder, fill_weights_by_name
+
+
+def warp(img: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: float = 1.0) -> torch.Tensor:
+    """Backward warp of CUDA tensors (see ops.warp)."""
+    return ops.warp(img, flow, mode=mode, sign=sign)
+
+
+class RaftEngine:
+    def __init__(self, checkpoint: str | None = None, iters: int = 20, small: bool = False,
+                 corr_precision: str = 'tf32', alternate_corr: bool = False, mixed_precision: bool = False,
+                 channels_last: bool = False, use_cuda_graph: bool = False, device=None, seed: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.iters = iters
+        self.args = SimpleNamespace(small=small, mixed_precision=mixed_precision, alternate_corr=alternate_corr,
+                                    corr_precision=corr_precision)
+        model = RAFT(self.args)
+        if checkpoint is None:
+            fill_weights_by_name(model, seed)
+        else:
+            model.load_state_dict(torch.load(checkpoint, map_location='cpu'))
+        model = model.to(self.device).eval()
+        if channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        self.model = model
+        self.channels_last = channels_last
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+
+    def load_checkpoint(self, path: str):
+        self.model.load_state_dict(torch.load(path, map_location='cpu'))
+        self._graphs.clear()
+        return self
+
+    def to(self, device):
+        self.device = torch.device(device)
+        self.model = self.model.to(self.device)
+        self._graphs.clear()
+        return self
+
+    # ---------------------------------------------------------------- core
+    @torch.no_grad()
+    def _forward(self, im1: torch.Tensor, im2: torch.Tensor) -> torch.Tensor:
+        """padded float images [B,3,H,W] in 0..255 -> flow_up [B,2,H,W]."""
+        if self.channels_last:
+            im1 = im1.contiguous(memory_format=torch.channels_last)
+            im2 = im2.contiguous(memory_format=torch.channels_last)
+        _, flow_up = self.model(im1, im2, iters=self.iters, test_mode=True)
+        return flow_up.float()
+
+    @torch.no_grad()
+    def _forward_graphed(self, im1: torch.Tensor, im2: torch.Tensor) -> torch.Tensor:
+        key = (tuple(im1.shape), self.iters)
+        ent = self._graphs.get(key)
+        if ent is None:
+            s1, s2 = im1.clone(), im2.clone()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up: cuDNN autotune, table uploads, allocator
+                    self._forward(s1, s2)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward(s1, s2)
+            ent = (g, s1, s2, out)
+            self._graphs[key] = ent
+        g, s1, s2, out = ent
+        s1.copy_(im1)
+        s2.copy_(im2)
+        g.replay()
+        return out
+
+    @torch.no_grad()
+    def estimate_flow(self, img1: torch.Tensor, img2: torch.Tensor, unpad: bool = True) -> torch.Tensor:
+        """img1, img2: RGB uint8 (or float 0..255) CUDA tensors [B,H,W,3].  Returns flow of img1 -> img2
+        on img1's grid, [B,H,W,2] fp32 (x, y pixels).  Images are replicate-padded to a multiple of 8
+        like the reference (utils/utils.py:7-19); unpad=False reproduces RAFT_2.calc, which returns
+        the padded-size flow (ofgen.py:75-78)."""
+        if img1.dim() != 4 or img1.shape[-1] != 3 or img1.shape != img2.shape:
+            raise RuntimeError(f'images must both be [B,H,W,3], got {tuple(img1.shape)} and {tuple(img2.shape)}')
+        if not img1.is_cuda or not img2.is_cuda:
+            raise RuntimeError('estimate_flow takes CUDA tensors; use ofgen.RAFT_2.calc for numpy frames')
+        im1 = img1.permute(0, 3, 1, 2).float()
+        im2 = img2.permute(0, 3, 1, 2).float()
+        padder = InputPadder(im1.shape)
+        im1, im2 = padder.pad(im1, im2)
+        fwd = self._forward_graphed if self.use_cuda_graph else self._forward
+        flow_up = fwd(im1.contiguous(), im2.contiguous())
+        if unpad:
+            flow_up = padder.unpad(flow_up)
+        return flow_up.permute(0, 2, 3, 1).contiguous()
+
+
+class RaftFlowConfidence:
+    """Adapter giving a RAFT engine the DenseMatching interface the reference's PDCNetPlus
+    wraps (`estimate_flow_and_confidence_map(source, target)`, pdcnet_of.py:70):
+
+      * flow lives on the TARGET grid and points into the SOURCE (so `warp_frame(source_ai, flow)`
+        samples at x + flow, pdcnet_of.py:39-41): it is RAFT(image1=target, image2=source);
+      * RAFT has no confidence head, so `weight_map` is defined HERE (nothing in the reference to
+        match, SURVEY §8a note): forward-backward consistency,
+            err  = |f_ts(x) + f_st(x + f_ts(x))|              (bilinear warp kernel)
+            weight_map = stack([bias - err / sigma, 0])  =>  confidence = sigmoid(bias - err/sigma).
+    """
+
+    def __init__(self, engine: RaftEngine, sigma: float = 1.0, bias: float = 4.0, synthetic_logits_seed: int | None = None):
+        self.engine = engine
+        self.sigma, self.bias = sigma, bias
+        self.synthetic_logits_seed = synthetic_logits_seed
+
+    def to(self, device):
+        self.engine.to(device)
+        return self
+
+    @torch.no_grad()
+    def estimate_flow_and_confidence_map(self, source: torch.Tensor, target: torch.Tensor):
+        """source, target: [B,3,H,W] uint8/float RGB.  Returns (flow [B,2,H,W], {'weight_map': [B,2,H,W]})."""
+        dev = self.engine.device
+        src = source.to(dev).permute(0, 2, 3, 1).contiguous()
+        tgt = target.to(dev).permute(0, 2, 3, 1).contiguous()
+        f_ts = self.engine.estimate_flow(tgt, src)  # on the target grid, into the source
+        if self.synthetic_logits_seed is not None:
+            g = torch.Generator(device=dev).manual_seed(self.synthetic_logits_seed)
+            B, H, W, _ = f_ts.shape
+            wm = 2.0 * torch.randn((B, 2, H, W), generator=g, device=dev)
+        else:
+            f_st = self.engine.estimate_flow(src, tgt)  # on the source grid, into the target
+            back = ops.warp(f_st, f_ts, mode='bilinear', sign=1.0)  # f_st sampled at x + f_ts(x)
+            err = torch.linalg.vector_norm(f_ts + back, dim=-1)
+            wm = torch.stack([self.bias - err / self.sigma, torch.zeros_like(err)], dim=1)
+        return f_ts.permute(0, 3, 1, 2).contiguous(), {'weight_map': wm.contiguous()}
+
+
+_default_engine: RaftEngine | None = None
+
+
+def estimate_flow(img1: torch.Tensor, img2: torch.Tensor, iters: int = 20, engine: RaftEngine | None = None) -> torch.Tensor:
+    """Module-level convenience: flow img1 -> img2 for [B,H,W,3] CUDA images with a process-wide engine."""
+    global _default_engine
+    eng = engine
+    if eng is None:
+        if _default_engine is None:
+            _default_engine = RaftEngine(iters=iters)
+        eng = _default_engine
+    if eng.iters != iters:
+        eng.iters = iters
+    return eng.estimate_flow(img1, img2)

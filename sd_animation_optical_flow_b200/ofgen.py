@@ -1,0 +1,262 @@
+"""Drop-in for the flow / warp / mask / composite helpers of the reference's
+`ofgen.py`, `ofgen_pixel_inpaint.py` and `ofgen_keyframe_inpaint.py`: same names, numpy in /
+numpy out, arithmetic on the B200.  (The Stable-Diffusion orchestration around them is out of
+scope)
+
+| here                      | reference                                                      |
+|---------------------------|----------------------------------------------------------------|
+| warp_frame                | ofgen.py:37-43 (x - flow; dups ofgen_pixel_inpaint.py:84-90)    |
+| warp_frame_pdcnet         | pdcnet_of.py:34-42 as imported at ofgen_pixel_inpaint.py:17     |
+| RAFT_2, create_of_algo    | ofgen.py:55-83                                                  |
+| of_calc                   | ofgen.py:45-49 (RAFT flavour)                                   |
+| of_calc_pdcnet            | ofgen_pixel_inpaint.py:105-118                                  |
+| generate_mask             | ofgen_pixel_inpaint.py:262-267, ofgen_keyframe_inpaint.py:317-322 |
+| mix_propagated_ai_frame   | ofgen_pixel_inpaint.py:251-260                                  |
+| confidence_to_mask        | ofgen_pixel_inpaint.py:218-227                                  |
+| merge_images              | ofgen_keyframe_inpaint.py:676-681 (method='naive')              |
+| expand_mask               | ofgen_keyframe_inpaint.py:968-973                               |
+| composite_references      | the greedy loop of ofgen_keyframe_inpaint.py:995-1024 / 741-770 |
+| PDCNetAux                 | ofgen_keyframe_inpaint.py:549-653                               |
+| keyframe_conv_pick        | ofgen_keyframe_inpaint.py:664-668                               |
+"""
+from __future__ import annotations
+
+import glob
+import os
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import RaftEngine
+from .pdcnet_of import _device, _h2d
+from .pdcnet_of import warp_frame as warp_frame_pdcnet  # noqa: F401  (re-export under the scripts' alias)
+
+
+# ----------------------------------------------------------------------------- W2
+def warp_frame(frame: np.ndarray, flow: np.ndarray, device=None) -> np.ndarray:
+    """ofgen.warp_frame: map = grid - flow, cv2.remap INTER_CUBIC, border 0.  `flow` is not modified."""
+    dev = _device(device)
+    out = ops.warp(_h2d(frame, dev), _h2d(np.asarray(flow, dtype=np.float32), dev), mode='cv2_cubic', sign=-1.0)
+    return out.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------- F0
+class namespace:
+    def __contains__(self, m):
+        return hasattr(self, m)
+
+
+class RAFT_2:
+    """ofgen.py:55-79.  `model_path=None` keeps seeded random-init weights (no checkpoint ships with
+    the reference); otherwise the raft-things checkpoint at `model_path` is loaded."""
+
+    def __init__(self, model_path: str | None = 'RAFT/models/raft-things.pth', iters: int = 20, device=None, **engine_kw) -> None:
+        ckpt = model_path if (model_path is not None and os.path.exists(model_path)) else None
+        if model_path is not None and ckpt is None:
+            raise FileNotFoundError(f'{model_path} not found (pass model_path=None for random-init weights)')
+        self.engine = RaftEngine(checkpoint=ckpt, iters=iters, device=device, **engine_kw)
+
+    def to(self, device):
+        self.engine.to(device)
+        return self
+
+    @torch.no_grad()
+    def calc(self, img1: np.ndarray, img2: np.ndarray) -> np.ndarray:
+        """BGR uint8 [H,W,3] x2 -> flow float32 [H',W',2] on img1's grid.  Like the reference the
+        result keeps the replicate-padded size H',W' (multiples of 8; ofgen.py:75-78 never unpads)."""
+        dev = self.engine.device
+        a = _h2d(img1, dev)[None].flip(-1).contiguous()  # BGR -> RGB
+        b = _h2d(img2, dev)[None].flip(-1).contiguous()
+        return self.engine.estimate_flow(a, b, unpad=False)[0].cpu().numpy()
+
+
+def create_of_algo(model_path: str | None = 'RAFT/models/raft-things.pth', **kw):
+    """ofgen.py:81-83."""
+    return RAFT_2(model_path, **kw)
+
+
+def of_calc(frame1: np.ndarray, frame2: np.ndarray, of_algo):
+    """ofgen.py:45-49: (flow, |flow|)."""
+    flow = of_algo.calc(frame1, frame2)
+    fx, fy = flow[:, :, 0], flow[:, :, 1]
+    return flow, np.sqrt(fx * fx + fy * fy)
+
+
+def of_calc_pdcnet(frame1: np.ndarray, frame2: np.ndarray, algo, device=None):
+    """ofgen_pixel_inpaint.py:105-118: (flow, confidence, travel distance, log_confidence)."""
+    flow, confidence, log_confidence = algo.calc(frame1, frame2)
+    dev = _device(device)
+    v = ops.travel_distance(_h2d(flow, dev)[None], _h2d(confidence, dev)[None], 0.9)[0].cpu().numpy()
+    return flow, confidence, v, log_confidence
+
+
+# ----------------------------------------------------------------------------- masks
+def generate_mask(cum_confidence: np.ndarray, log_confidence: np.ndarray, thres: float = 0.8, device=None):
+    """Returns (mask u8, log_confidence); like the reference, `log_confidence` is also reset IN PLACE
+    where the confidence is below `thres`."""
+    dev = _device(device)
+    conf_d = _h2d(np.asarray(cum_confidence, dtype=np.float32), dev)[None]
+    logc_d = _h2d(np.asarray(log_confidence, dtype=np.float32), dev)[None].clone()
+    mask = ops.generate_mask(conf_d, logc_d, thres, 7)[0].cpu().numpy()
+    log_confidence[...] = logc_d[0].cpu().numpy()
+    return mask, log_confidence
+
+
+def confidence_to_mask(confidence, flow, dist, mask_aux, device=None):
+    """ofgen_pixel_inpaint.py:218-227; `mask_aux` carries .pixel_travel_dist and .thres and is updated."""
+    dev = _device(device)
+    conf_d = _h2d(np.asarray(confidence, dtype=np.float32), dev)
+    low = conf_d < 0.9
+    ptd = ops.warp(_h2d(np.asarray(mask_aux.pixel_travel_dist, dtype=np.float32), dev),
+                   _h2d(np.asarray(flow, dtype=np.float32), dev), mode='cv2_cubic', sign=1.0)
+    ptd = ptd + _h2d(np.asarray(dist, dtype=np.float32), dev)
+    ptd[low] = 0
+    far = ptd > mask_aux.thres
+    mask = torch.zeros_like(conf_d, dtype=torch.uint8)
+    mask[low | far] = 255
+    ptd[far] = 0
+    mask_aux.pixel_travel_dist = ptd.cpu().numpy()
+    return ops.dilate_ellipse(mask[None].contiguous(), 15)[0].cpu().numpy()
+
+
+def mix_propagated_ai_frame(raw_ai_frame, warped_propagated_ai_frame, mask, propagated_pixel_weight=1.0, device=None):
+    if propagated_pixel_weight < 0.001:
+        return raw_ai_frame
+    dev = _device(device)
+    out = ops.mix_propagated(_h2d(raw_ai_frame, dev)[None], _h2d(warped_propagated_ai_frame, dev)[None],
+                             _h2d(mask, dev)[None], propagated_pixel_weight)
+    return out[0].cpu().numpy()
+
+
+def merge_images(base_image, second_image, mask, method='naive', device=None):
+    if method != 'naive':
+        raise NotImplementedError("only method='naive' is on the hot path (the 'poisson' branch calls cv2.seamlessClone)")
+    dev = _device(device)
+    out = ops.merge_select(_h2d(base_image, dev)[None], _h2d(second_image, dev)[None], _h2d(mask, dev)[None])
+    return out[0].cpu().numpy()
+
+
+def expand_mask(mask: np.ndarray, ori_image: np.ndarray, device=None) -> np.ndarray:
+    dev = _device(device)
+    return ops.expand_mask(_h2d(mask, dev)[None], _h2d(ori_image, dev)[None], 7)[0].cpu().numpy()
+
+
+def invert_and_dilate(mask: np.ndarray, device=None) -> np.ndarray:
+    """mask2 = dilate(255 - mask, ellipse 7x7) (ofgen_keyframe_inpaint.py:772-774)."""
+    dev = _device(device)
+    return ops.dilate_ellipse(_h2d(mask, dev)[None], 7, invert=True)[0].cpu().numpy()
+
+
+def composite_references(flow_mat: np.ndarray, ai_frames, thres: float = 0.5, device=None):
+    """The greedy multi-reference warp+composite loop (ofgen_keyframe_inpaint.py:995-1024).
+    flow_mat [n,1,H,W,3] is updated in place exactly like the reference; ai_frames: n uint8 [H,W,3].
+    Returns (ret_frame u8 [H,W,3], mask u8 [H,W], chosen reference order)."""
+    dev = _device(device)
+    n, one, H, W, _ = flow_mat.shape
+    assert one == 1
+    fm = _h2d(flow_mat.reshape(n, H, W, 3).astype(np.float32, copy=False), dev).clone()
+    frames = _h2d(np.stack([np.asarray(f) for f in ai_frames]), dev)
+    ret, mask, order = ops.greedy_composite(fm, frames, thres)
+    flow_mat[...] = fm.cpu().numpy().reshape(flow_mat.shape)
+    return ret.cpu().numpy(), mask.cpu().numpy(), [int(i) for i in order.cpu().tolist()]
+
+
+# ----------------------------------------------------------------------------- A1 / A2
+def chunks(lst, n):
+    for i in range(0, len(lst), n):
+        yield lst[i:i + n]
+
+
+class PDCNetAux:
+    """Batched pair flow with the on-disk `.npy` pair cache (ofgen_keyframe_inpaint.py:549-653).
+    `video` needs `.size_hw` and `.get_raw_frame(i) -> BGR uint8 [H,W,3]`; `indices` arguments are
+    plain lists of frame numbers (or objects with `.indices`)."""
+
+    def __init__(self, pdcnet_model, workspace_dir: str, batch_size: int = 16, device=None) -> None:
+        self.workspace_dir = workspace_dir
+        self.cached_pair = set()
+        self.batch_size = batch_size
+        self.device = _device(device)
+        self.pdcnet_model = pdcnet_model.to(self.device)
+        self.pair_dir = os.path.join(workspace_dir, 'pdcnet')
+        os.makedirs(self.pair_dir, exist_ok=True)
+        for f in glob.glob(os.path.join(self.pair_dir, '*.npy')):
+            s, t = os.path.split(f)[-1].split('.')[0].split('-')
+            self.cached_pair.add((int(s), int(t)))
+
+    def purge(self):
+        self.cached_pair = set()
+        for f in glob.glob(os.path.join(self.pair_dir, '*.npy')):
+            os.remove(f)
+
+    def load_cached(self, s, t):
+        assert (s, t) in self.cached_pair
+        return np.load(os.path.join(self.pair_dir, f'{s:05d}-{t:05d}.npy'))
+
+    def calcualte_single(self, video, s, t):  # (sic) the reference's spelling, ofgen_keyframe_inpaint.py:576
+        if (s, t) in self.cached_pair:
+            return self.load_cached(s, t)
+        ret = np.zeros((1, 1, *video.size_hw, 3), dtype=np.float32)
+        self.calculate_given_pairs(video, [(s, t)], {s: 0}, {t: 0}, ret)
+        self.cached_pair.add((s, t))
+        return ret[0, 0]
+
+    calculate_single = calcualte_single
+
+    def calculate_given_pairs(self, video, to_calculate_pairs: List[Tuple[int, int]], s2i_map: Dict[int, int],
+                              t2i_map: Dict[int, int], ret: np.ndarray):
+        for pair_batch in chunks(to_calculate_pairs, self.batch_size):
+            src = np.stack([video.get_raw_frame(s)[:, :, ::-1] for s, _ in pair_batch])  # BGR -> RGB
+            tgt = np.stack([video.get_raw_frame(t)[:, :, ::-1] for _, t in pair_batch])
+            flow_est, confidence = self.pdcnet_model.calc_batch(_h2d(src, self.device), _h2d(tgt, self.device))
+            for i, (s, t) in enumerate(pair_batch):
+                si, ti = s2i_map[s], t2i_map[t]
+                ret[si, ti, :, :, 0:2] = flow_est[i]
+                ret[si, ti, :, :, 2] = confidence[i]
+                np.save(os.path.join(self.pair_dir, f'{s:05d}-{t:05d}.npy'), ret[si, ti])
+
+    @staticmethod
+    def _idx(indices):
+        return list(indices.indices) if hasattr(indices, 'indices') else list(indices)
+
+    def calculate_multiple_to_one(self, video, source_indices, target_index: int) -> np.ndarray:
+        """[n_sources, 1, H, W, 3] (flow x, flow y, confidence); identity pair = zero flow, confidence 1."""
+        srcs = self._idx(source_indices)
+        s2i = {s: i for i, s in enumerate(srcs)}
+        todo = [(s, target_index) for s in srcs if s != target_index and (s, target_index) not in self.cached_pair]
+        ret = np.zeros((len(srcs), 1, *video.size_hw, 3), dtype=np.float32)
+        self.calculate_given_pairs(video, todo, s2i, {target_index: 0}, ret)
+        for i, s in enumerate(srcs):
+            if s == target_index:
+                ret[i, 0, :, :, 0:2] = 0
+                ret[i, 0, :, :, 2] = 1
+            elif (s, target_index) in self.cached_pair:
+                ret[i, 0] = self.load_cached(s, target_index)
+        self.cached_pair.update(todo)
+        return ret
+
+    def calculate_pairwise(self, video, indices) -> np.ndarray:
+        """[n, n, H, W, 3] for every ordered pair of `indices`."""
+        idx = self._idx(indices)
+        s2i = {s: i for i, s in enumerate(idx)}
+        todo = [(s, t) for s in idx for t in idx if s != t and (s, t) not in self.cached_pair]
+        ret = np.zeros((len(idx), len(idx), *video.size_hw, 3), dtype=np.float32)
+        self.calculate_given_pairs(video, todo, s2i, dict(s2i), ret)
+        for i, s in enumerate(idx):
+            for j, t in enumerate(idx):
+                if s == t:
+                    ret[i, j, :, :, 0:2] = 0
+                    ret[i, j, :, :, 2] = 1
+                elif (s, t) in self.cached_pair:
+                    ret[i, j] = self.load_cached(s, t)
+        self.cached_pair.update(todo)
+        return ret
+
+
+def keyframe_conv_pick(flow_mat: np.ndarray, device=None) -> int:
+    """argmax_s sum_{t,h,w} confidence[s,t] (ofgen_keyframe_inpaint.py:664-668), reduced on the device."""
+    dev = _device(device)
+    sums = ops.confidence_sums(_h2d(np.asarray(flow_mat, dtype=np.float32), dev))
+    return int(torch.argmax(sums).item())

@@ -1,0 +1,297 @@
+"""Device-resident operators over CUDA tensors: thin, checked wrappers of the C ABI.
+
+These are the batched, stream-ordered, host-sync-free forms SURVEY §8(b) asks for next to
+the reference-named numpy entry points (pdcnet_of.py / ofgen.py in this package):
+`warp`, `confidence_softmax`, `generate_mask`, `composite`, ...  Every function launches
+this package's sm_100a kernels through libsdof_b200.so and raises if that is impossible.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _capi
+from ._capi import PRECISIONS, check, load, ptr, require_cuda, stream_ptr
+
+f32, u8 = torch.float32, torch.uint8
+
+
+# --------------------------------------------------------------------------- correlation
+class CorrPyramid:
+    """The correlation volume and its pooled levels in one HBM buffer (see
+    sdof_pyramid_layout in include/sdof_b200.h)."""
+
+    def __init__(self, buf: torch.Tensor, layout, B: int, h1: int, w1: int, h2: int, w2: int, levels: int):
+        self.buf, self.layout = buf, layout
+        self.B, self.h1, self.w1, self.h2, self.w2, self.levels = B, h1, w1, h2, w2, levels
+
+    def level(self, l: int) -> torch.Tensor:
+        """View of level l shaped like the reference's corr_pyramid[l]:
+        [B*h1*w1, 1, h_l, w_l] (RAFT/core/corr.py:21-27); strided when w_l % 4 != 0."""
+        lay = self.layout
+        rows = self.B * self.h1 * self.w1
+        return torch.as_strided(self.buf, (rows, 1, lay.h[l], lay.w[l]), (lay.pitch[l], 0, lay.wp[l], 1), lay.offset[l])
+
+
+def corr_volume_pyramid(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor, levels: int = 4,
+                        precision: str = 'tf32') -> CorrPyramid:
+    """fmap1 [B,h1,w1,C], fmap2 [B,h2,w2,C] fp32 channels-last -> CorrPyramid (C1 + C2)."""
+    require_cuda(fmap1_nhwc, 'fmap1', f32)
+    require_cuda(fmap2_nhwc, 'fmap2', f32)
+    if fmap1_nhwc.dim() != 4 or fmap2_nhwc.dim() != 4:
+        raise RuntimeError('feature maps must be [B,h,w,C]')
+    B, h1, w1, C = fmap1_nhwc.shape
+    B2, h2, w2, C2 = fmap2_nhwc.shape
+    if B != B2 or C != C2:
+        raise RuntimeError(f'fmap1 {tuple(fmap1_nhwc.shape)} and fmap2 {tuple(fmap2_nhwc.shape)} disagree on batch/channels')
+    if precision not in PRECISIONS:
+        raise ValueError(f'precision must be one of {sorted(PRECISIONS)}, got {precision!r}')
+    lib = load()
+    lay = _capi.pyramid_layout(B * h1 * w1, h2, w2, levels)
+    dev = fmap1_nhwc.device
+    buf = torch.empty(max(int(lay.total_floats), 1), dtype=f32, device=dev)
+    ws_bytes = int(lib.sdof_corr_volume_workspace_bytes(B, h1, w1, h2, w2, C, PRECISIONS[precision]))
+    ws = torch.empty(ws_bytes, dtype=u8, device=dev) if ws_bytes else None
+    check(lib.sdof_corr_volume_pyramid(ptr(fmap1_nhwc), ptr(fmap2_nhwc), B, h1, w1, h2, w2, C, levels,
+                                       PRECISIONS[precision], ptr(buf), ptr(ws), ws_bytes, stream_ptr(dev)),
+          'sdof_corr_volume_pyramid')
+    return CorrPyramid(buf, lay, B, h1, w1, h2, w2, levels)
+
+
+def corr_lookup(pyr: CorrPyramid, coords: torch.Tensor, radius: int = 4, out: torch.Tensor | None = None) -> torch.Tensor:
+    """coords [B,2,h1,w1] -> [B, levels*(2r+1)^2, h1, w1] (C3)."""
+    require_cuda(coords, 'coords', f32)
+    if tuple(coords.shape) != (pyr.B, 2, pyr.h1, pyr.w1):
+        raise RuntimeError(f'coords must be {(pyr.B, 2, pyr.h1, pyr.w1)}, got {tuple(coords.shape)}')
+    ch = pyr.levels * (2 * radius + 1) ** 2
+    if out is None:
+        out = torch.empty((pyr.B, ch, pyr.h1, pyr.w1), dtype=f32, device=coords.device)
+    else:
+        require_cuda(out, 'out', f32)
+    check(load().sdof_corr_lookup(ptr(pyr.buf), ptr(coords), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2, pyr.levels, radius,
+                                  ptr(out), stream_ptr(coords.device)), 'sdof_corr_lookup')
+    return out
+
+
+def alt_corr_forward(fmap1: torch.Tensor, fmap2: torch.Tensor, coords: torch.Tensor, radius: int) -> torch.Tensor:
+    """K1 with the reference op's contract: fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C],
+    coords [B,N,H1,W1,2] -> [B,N,(2r+1)^2,H1,W1], unnormalised."""
+    require_cuda(fmap1, 'fmap1', f32)
+    require_cuda(fmap2, 'fmap2', f32)
+    require_cuda(coords, 'coords', f32)
+    B, H1, W1, C = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    N = coords.shape[1]
+    if tuple(coords.shape) != (B, N, H1, W1, 2):
+        raise RuntimeError(f'coords must be [B,N,H1,W1,2], got {tuple(coords.shape)}')
+    out = torch.empty((B, N, (2 * radius + 1) ** 2, H1, W1), dtype=f32, device=fmap1.device)
+    check(load().sdof_alt_corr_forward(ptr(fmap1), ptr(fmap2), ptr(coords), B, H1, W1, H2, W2, C, N, radius, ptr(out),
+                                       stream_ptr(fmap1.device)), 'sdof_alt_corr_forward')
+    return out
+
+
+def alt_corr_level(fmap1: torch.Tensor, fmap2_level: torch.Tensor, coords: torch.Tensor, radius: int, coord_scale: float,
+                   out_scale: float, chan_offset: int, out: torch.Tensor) -> torch.Tensor:
+    """One level of C4 written into channels [chan_offset, +(2r+1)^2) of out [B,CH,H1,W1]."""
+    require_cuda(fmap1, 'fmap1', f32)
+    require_cuda(fmap2_level, 'fmap2', f32)
+    require_cuda(coords, 'coords', f32)
+    require_cuda(out, 'out', f32)
+    B, H1, W1, C = fmap1.shape
+    _, H2, W2, _ = fmap2_level.shape
+    check(load().sdof_alt_corr_level(ptr(fmap1), ptr(fmap2_level), ptr(coords), B, H1, W1, H2, W2, C, radius,
+                                     float(coord_scale), float(out_scale), chan_offset, out.shape[1], ptr(out),
+                                     stream_ptr(fmap1.device)), 'sdof_alt_corr_level')
+    return out
+
+
+def avgpool2_nhwc(x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, 'x', f32)
+    B, H, W, C = x.shape
+    out = torch.empty((B, H // 2, W // 2, C), dtype=f32, device=x.device)
+    check(load().sdof_avgpool2_nhwc(ptr(x), B, H, W, C, ptr(out), stream_ptr(x.device)), 'sdof_avgpool2_nhwc')
+    return out
+
+
+# --------------------------------------------------------------------------- warp
+def warp(src: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: float = 1.0) -> torch.Tensor:
+    """Backward warp on the device.  src [Bs,Hs,Ws,C] (Bs == B or 1) or [Hs,Ws,C] / [Hs,Ws],
+    u8 or f32; flow [B,H,W,2] or [H,W,2] f32.  mode 'cv2_cubic' (bit-exact cv2.remap for u8)
+    or 'bilinear' (grid_sample semantics).  sign=+1 samples at x+flow (pdcnet_of.warp_frame),
+    -1 at x-flow (ofgen.warp_frame)."""
+    require_cuda(src, 'src')
+    require_cuda(flow, 'flow', f32)
+    squeeze_b = flow.dim() == 3
+    fl = flow[None] if squeeze_b else flow
+    s = src
+    squeeze_c = False
+    if s.dim() == 2:
+        s, squeeze_c = s[None, :, :, None], True
+    elif s.dim() == 3:
+        if squeeze_b:
+            s = s[None]
+        else:  # [B,H,W] batch of single-channel images
+            s, squeeze_c = s[..., None], True
+    if s.dim() != 4 or fl.dim() != 4 or fl.shape[-1] != 2:
+        raise RuntimeError(f'bad shapes: src {tuple(src.shape)}, flow {tuple(flow.shape)}')
+    B, H, W, _ = fl.shape
+    Bs, Hs, Ws, C = s.shape
+    if Bs not in (1, B):
+        raise RuntimeError(f'src batch {Bs} must be 1 or {B}')
+    if mode not in ('cv2_cubic', 'bilinear'):
+        raise ValueError(f"mode must be 'cv2_cubic' or 'bilinear', got {mode!r}")
+    if s.dtype not in (u8, f32):
+        raise RuntimeError(f'src must be uint8 or float32, got {s.dtype}')
+    s = s.contiguous()
+    out = torch.empty((B, H, W, C), dtype=s.dtype, device=s.device)
+    lib = load()
+    fn = {('cv2_cubic', u8): lib.sdof_warp_cubic_u8, ('cv2_cubic', f32): lib.sdof_warp_cubic_f32,
+          ('bilinear', u8): lib.sdof_warp_bilinear_u8, ('bilinear', f32): lib.sdof_warp_bilinear_f32}[(mode, s.dtype)]
+    check(fn(ptr(s), ptr(fl), B, int(Bs == B and B > 0), Hs, Ws, C, H, W, float(sign), ptr(out), stream_ptr(s.device)),
+          f'sdof_warp_{mode}')
+    if squeeze_c:
+        out = out[..., 0]
+    return out[0] if squeeze_b else out
+
+
+# --------------------------------------------------------------------------- confidence / masks
+def confidence_softmax(weight_map: torch.Tensor):
+    """weight_map [B,K,H,W] -> (confidence, log_confidence) [B,H,W] (M1)."""
+    require_cuda(weight_map, 'weight_map', f32)
+    B, K, H, W = weight_map.shape
+    conf = torch.empty((B, H, W), dtype=f32, device=weight_map.device)
+    logc = torch.empty_like(conf)
+    check(load().sdof_confidence_softmax(ptr(weight_map), B, K, H, W, ptr(conf), ptr(logc), stream_ptr(weight_map.device)),
+          'sdof_confidence_softmax')
+    return conf, logc
+
+
+def travel_distance(flow: torch.Tensor, conf: torch.Tensor, conf_thres: float = 0.9) -> torch.Tensor:
+    require_cuda(flow, 'flow', f32)
+    require_cuda(conf, 'conf', f32)
+    B, H, W, _ = flow.shape
+    v = torch.empty((B, H, W), dtype=f32, device=flow.device)
+    check(load().sdof_travel_distance(ptr(flow), ptr(conf), B, H, W, float(conf_thres), ptr(v), stream_ptr(flow.device)),
+          'sdof_travel_distance')
+    return v
+
+
+def generate_mask(conf: torch.Tensor, log_conf: torch.Tensor | None, thres: float, ksize: int = 7) -> torch.Tensor:
+    """conf [B,H,W] -> dilated u8 mask; log_conf (if given) is reset in place where conf < thres (M3)."""
+    require_cuda(conf, 'conf', f32)
+    if log_conf is not None:
+        require_cuda(log_conf, 'log_conf', f32)
+    B, H, W = conf.shape
+    mask = torch.empty((B, H, W), dtype=u8, device=conf.device)
+    check(load().sdof_generate_mask(ptr(conf), ptr(log_conf), B, H, W, float(thres), ksize, ptr(mask), stream_ptr(conf.device)),
+          'sdof_generate_mask')
+    return mask
+
+
+def dilate_ellipse(mask: torch.Tensor, ksize: int = 7, invert: bool = False) -> torch.Tensor:
+    require_cuda(mask, 'mask', u8)
+    B, H, W = mask.shape
+    out = torch.empty_like(mask)
+    check(load().sdof_dilate_ellipse_u8(ptr(mask), B, H, W, ksize, int(invert), ptr(out), stream_ptr(mask.device)),
+          'sdof_dilate_ellipse_u8')
+    return out
+
+
+def expand_mask(mask: torch.Tensor, image: torch.Tensor, ksize: int = 7) -> torch.Tensor:
+    require_cuda(mask, 'mask', u8)
+    require_cuda(image, 'image', u8)
+    B, H, W = mask.shape
+    if tuple(image.shape) != (B, H, W, 3):
+        raise RuntimeError(f'image must be {(B, H, W, 3)}, got {tuple(image.shape)}')
+    scratch = torch.empty_like(mask)
+    out = torch.empty_like(mask)
+    check(load().sdof_expand_mask(ptr(mask), ptr(image), B, H, W, ksize, ptr(scratch), ptr(out), stream_ptr(mask.device)),
+          'sdof_expand_mask')
+    return out
+
+
+def mix_propagated(raw: torch.Tensor, warped: torch.Tensor, mask: torch.Tensor, ppw: float) -> torch.Tensor:
+    require_cuda(raw, 'raw', u8)
+    require_cuda(warped, 'warped', u8)
+    require_cuda(mask, 'mask', u8)
+    B, H, W, C = raw.shape
+    out = torch.empty_like(raw)
+    check(load().sdof_mix_propagated(ptr(raw), ptr(warped), ptr(mask), B, H, W, C, float(ppw), ptr(out), stream_ptr(raw.device)),
+          'sdof_mix_propagated')
+    return out
+
+
+def merge_select(base: torch.Tensor, second: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    require_cuda(base, 'base', u8)
+    require_cuda(second, 'second', u8)
+    require_cuda(mask, 'mask', u8)
+    B, H, W, C = base.shape
+    out = torch.empty_like(base)
+    check(load().sdof_merge_select(ptr(base), ptr(second), ptr(mask), B, H, W, C, ptr(out), stream_ptr(base.device)),
+          'sdof_merge_select')
+    return out
+
+
+def greedy_composite(flow_mat: torch.Tensor, ai_frames: torch.Tensor, thres: float):
+    """flow_mat [n,H,W,3] f32 (modified in place like the reference), ai_frames [n,H,W,3] u8 ->
+    (ret [H,W,3] u8, mask [H,W] u8, order [n] int32) (M5)."""
+    require_cuda(flow_mat, 'flow_mat', f32)
+    require_cuda(ai_frames, 'ai_frames', u8)
+    n, H, W, three = flow_mat.shape
+    if three != 3 or tuple(ai_frames.shape) != (n, H, W, 3):
+        raise RuntimeError('flow_mat must be [n,H,W,3] and ai_frames [n,H,W,3]')
+    dev = flow_mat.device
+    ret = torch.empty((H, W, 3), dtype=u8, device=dev)
+    mask = torch.empty((H, W), dtype=u8, device=dev)
+    order = torch.empty((n,), dtype=torch.int32, device=dev)
+    lib = load()
+    ws = torch.empty(int(lib.sdof_greedy_workspace_bytes(n, H, W)), dtype=u8, device=dev)
+    check(lib.sdof_greedy_composite(ptr(flow_mat), ptr(ai_frames), n, H, W, float(thres), ptr(ret), ptr(mask), ptr(order),
+                                    ptr(ws), stream_ptr(dev)), 'sdof_greedy_composite')
+    return ret, mask, order
+
+
+def confidence_sums(flow_mat: torch.Tensor) -> torch.Tensor:
+    """flow_mat [S, ..., 3] -> float64 [S] sums of the confidence channel (A2)."""
+    require_cuda(flow_mat, 'flow_mat', f32)
+    S = flow_mat.shape[0]
+    per = flow_mat[0].numel() // 3 if S else 0
+    sums = torch.empty((S,), dtype=torch.float64, device=flow_mat.device)
+    check(load().sdof_confidence_sums(ptr(flow_mat), S, per, ptr(sums), stream_ptr(flow_mat.device)), 'sdof_confidence_sums')
+    return sums
+
+
+def warp_mask_composite(src: torch.Tensor, base: torch.Tensor, flow: torch.Tensor, weight_map: torch.Tensor,
+                        thres: float, ksize: int = 7):
+    """Fused W1+M1+M3+M4(ppw=1): src [Bs,H,W,3] u8 key frame(s), base [B,H,W,3] u8, flow [B,H,W,2],
+    weight_map [B,2,H,W] -> (out [B,H,W,3] u8, mask [B,H,W] u8)."""
+    require_cuda(src, 'src', u8)
+    require_cuda(base, 'base', u8)
+    require_cuda(flow, 'flow', f32)
+    require_cuda(weight_map, 'weight_map', f32)
+    B, H, W, _ = flow.shape
+    if weight_map.shape[1] != 2:
+        raise RuntimeError('weight_map must have 2 mixture components')
+    if src.shape[0] not in (1, B) or tuple(src.shape[1:]) != (H, W, 3) or tuple(base.shape) != (B, H, W, 3):
+        raise RuntimeError('src must be [B or 1,H,W,3] and base [B,H,W,3]')
+    out = torch.empty_like(base)
+    mask = torch.empty((B, H, W), dtype=u8, device=base.device)
+    check(load().sdof_warp_mask_composite(ptr(src), ptr(base), ptr(flow), ptr(weight_map), B, int(src.shape[0] == B), H, W,
+                                          float(thres), ksize, ptr(out), ptr(mask), stream_ptr(base.device)),
+          'sdof_warp_mask_composite')
+    return out, mask
+
+
+def cubic_table_i16():
+    """Host copy of the kernel's bicubic weight table (no GPU needed)."""
+    import numpy as np
+    buf = (ctypes.c_int16 * (1024 * 16))()
+    check(load().sdof_cubic_table_i16(buf), 'sdof_cubic_table_i16')
+    return np.frombuffer(buf, dtype=np.int16).reshape(1024, 16).copy()
+
+
+def ellipse_half_widths(ksize: int):
+    buf = (ctypes.c_int32 * ksize)()
+    check(load().sdof_ellipse_half_widths(ksize, buf), 'sdof_ellipse_half_widths')
+    return list(buf)

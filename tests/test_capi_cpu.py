@@ -1,0 +1,117 @@
+"""The C-ABI library on a machine WITHOUT a GPU: it must load, export every symbol
+include/sdof_b200.h declares, validate arguments, and its host-side tables must equal the
+oracle's (and therefore OpenCV's).  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import mask_oracle, warp_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, 'include', 'sdof_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(sdof_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_header_symbol(lib):
+    from sd_animation_optical_flow_b200 import _capi
+    names = _header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/sdof_b200.h but not exported'
+    # and the Python binding covers exactly the header
+    assert sorted(_capi.SIGNATURES) == names
+
+
+def test_abi_version(lib):
+    assert lib.sdof_abi_version() == 1
+
+
+def test_cubic_table_matches_oracle(lib):
+    from sd_animation_optical_flow_b200 import ops
+    assert np.array_equal(ops.cubic_table_i16(), warp_oracle.cubic_table_i16())
+
+
+def test_ellipse_rows_match_oracle(lib):
+    from sd_animation_optical_flow_b200 import ops
+    for k in (1, 3, 5, 7, 9, 15, 21, 31):
+        assert ops.ellipse_half_widths(k) == mask_oracle.ellipse_half_widths(k)
+    from sd_animation_optical_flow_b200._capi import SdofError
+    with pytest.raises(SdofError):
+        ops.ellipse_half_widths(8)
+
+
+def test_pyramid_layout(lib):
+    from sd_animation_optical_flow_b200 import _capi
+    lay = _capi.pyramid_layout(6144, 96, 64, 4)
+    assert list(lay.h[:4]) == [96, 48, 24, 12] and list(lay.w[:4]) == [64, 32, 16, 8]
+    assert list(lay.wp[:4]) == [64, 32, 16, 8]
+    # 200.5 MB for the 768x512 pyramid
+    assert lay.total_floats * 4 == 6144 * (96 * 64 + 48 * 32 + 24 * 16 + 12 * 8) * 4
+    lay = _capi.pyramid_layout(14400, 90, 160, 4)   # 720x1280: floor pooling drops odd rows
+    assert list(lay.h[:4]) == [90, 45, 22, 11] and list(lay.w[:4]) == [160, 80, 40, 20]
+    lay = _capi.pyramid_layout(10, 18, 22, 4)       # rows padded to 4 floats for TMA
+    assert list(lay.w[:4]) == [22, 11, 5, 2] and list(lay.wp[:4]) == [24, 12, 8, 4]
+    for l in range(4):
+        assert lay.offset[l] % 32 == 0 and lay.pitch[l] == lay.h[l] * lay.wp[l]
+    with pytest.raises(_capi.SdofError):
+        _capi.pyramid_layout(10, 18, 22, 9)
+
+
+def test_argument_validation_without_gpu(lib):
+    """Bad arguments are rejected before any CUDA call, with a message."""
+    null = ctypes.c_void_p(0)
+    rc = lib.sdof_warp_cubic_u8(null, null, 1, 1, 8, 8, 3, 8, 8, 1.0, null, null)
+    assert rc == 1 and b'NULL' in lib.sdof_last_error()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.sdof_warp_cubic_u8(p, p, 1, 1, 8, 8, 7, 8, 8, 1.0, p, null)
+    assert rc == 1 and b'C must be in 1..4' in lib.sdof_last_error()
+    rc = lib.sdof_warp_cubic_u8(p, p, 1, 1, 8, 8, 3, 8, 8, 0.5, p, null)
+    assert rc == 1 and b'sign' in lib.sdof_last_error()
+    rc = lib.sdof_corr_volume_pyramid(p, p, 1, 4, 4, 4, 4, 6, 4, 0, p, null, 0, null)
+    assert rc == 1 and b'multiple of 4' in lib.sdof_last_error()
+    rc = lib.sdof_corr_lookup(p, p, 1, 4, 4, 4, 4, 4, 99, p, null)
+    assert rc == 1 and b'radius' in lib.sdof_last_error()
+    rc = lib.sdof_dilate_ellipse_u8(p, 1, 8, 8, 4, 0, ctypes.cast((ctypes.c_float * 64)(), ctypes.c_void_p), null)
+    assert rc == 1 and b'ksize' in lib.sdof_last_error()
+    rc = lib.sdof_alt_corr_forward(p, p, p, 1, 4, 4, 4, 4, 6, 1, 4, p, null)
+    assert rc == 1
+
+
+def test_workspace_sizes(lib):
+    n = 6144
+    assert lib.sdof_corr_volume_workspace_bytes(1, 96, 64, 96, 64, 256, 3) == 0          # fp32: none
+    assert lib.sdof_corr_volume_workspace_bytes(1, 96, 64, 96, 64, 256, 0) == 2 * n * 256 * 4   # tf32: rounded copies
+    assert lib.sdof_corr_volume_workspace_bytes(1, 96, 64, 96, 64, 256, 1) == 4 * n * 256 * 4   # 3xtf32: hi+lo
+    assert lib.sdof_corr_volume_workspace_bytes(1, 96, 64, 96, 64, 256, 2) == 2 * n * 256 * 2   # bf16 copies
+
+
+def test_product_path_has_no_cpu_fallback():
+    """CUDA-only operators must refuse CPU tensors instead of silently computing elsewhere."""
+    import torch
+    from sd_animation_optical_flow_b200 import alt_cuda_corr, corr, ops
+    f = torch.zeros(1, 8, 4, 4)
+    with pytest.raises(RuntimeError):
+        corr.CorrBlock(f, f)
+    with pytest.raises(RuntimeError):
+        corr.AlternateCorrBlock(f, f)
+    with pytest.raises(RuntimeError, match='must be a CUDA tensor'):
+        alt_cuda_corr.forward(torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 8), torch.zeros(1, 1, 4, 4, 2), 4)
+    with pytest.raises(RuntimeError):
+        ops.warp(torch.zeros(4, 4, 3, dtype=torch.uint8), torch.zeros(4, 4, 2))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'sd_animation_optical_flow_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith('.py'):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f'{fn} imports the oracle'
