@@ -155,10 +155,11 @@ __global__ void __launch_bounds__(256) warp_generic_kernel(CubicTables tabs, con
       const float xs = __fadd_rn((float)x, __fmul_rn(sign, f.x));
       const float ys = __fadd_rn((float)y, __fmul_rn(sign, f.y));
       const float x0f = floorf(xs), y0f = floorf(ys);
-      const float ax = __fsub_rn(xs, x0f), ay = __fsub_rn(ys, y0f);
-      // clamp before the int conversion so NaN/huge coordinates land outside the image
-      const int x0 = (x0f >= -2.f && x0f <= (float)Ws + 1.f) ? (int)x0f : -2;
-      const int y0 = (y0f >= -2.f && y0f <= (float)Hs + 1.f) ? (int)y0f : -2;
+      // NaN / huge coordinates land outside the image (all taps zero, finite weights)
+      const bool okx = x0f >= -2.f && x0f <= (float)Ws + 1.f, oky = y0f >= -2.f && y0f <= (float)Hs + 1.f;
+      const float ax = okx ? __fsub_rn(xs, x0f) : 0.f, ay = oky ? __fsub_rn(ys, y0f) : 0.f;
+      const int x0 = okx ? (int)x0f : -2;
+      const int y0 = oky ? (int)y0f : -2;
       const float w00 = __fmul_rn(__fsub_rn(1.f, ax), __fsub_rn(1.f, ay));
       const float w01 = __fmul_rn(ax, __fsub_rn(1.f, ay));
       const float w10 = __fmul_rn(__fsub_rn(1.f, ax), ay);

@@ -1,0 +1,94 @@
+"""End-to-end flow parity: this package's RAFT (cuDNN convs + sm_100a correlation kernels) against
+flows produced by the REFERENCE RAFT on the same name-seeded weights and seeded frames
+(tests/golden/raft.npz).  Tolerance: EPE <= 1e-2 px mean for the fp32-faithful and
+tf32 correlation modes; convolutions run in true fp32 here so the comparison isolates the path."""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_inputs as gi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _engine(name, cuda, **kw):
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    cfg = gi.RAFT_CASES[name]
+    return RaftEngine(checkpoint=None, iters=cfg['iters'], small=cfg['small'], seed=cfg['seed'], device=cuda, **kw)
+
+
+def _epe(a, b):
+    return np.sqrt(((a - b) ** 2).sum(0))
+
+
+@pytest.mark.parametrize('name', list(gi.RAFT_CASES))
+@pytest.mark.parametrize('mode', ['fp32', '3xtf32', 'tf32', 'alt'])
+def test_flow_matches_reference_raft(cuda, golden, name, mode):
+    kw = dict(alternate_corr=True) if mode == 'alt' else dict(corr_precision=mode)
+    eng = _engine(name, cuda, **kw)
+    img1, img2 = gi.raft_inputs(name)
+    a = torch.from_numpy(img1).to(cuda)[None]
+    b = torch.from_numpy(img2).to(cuda)[None]
+    flow = eng.estimate_flow(a, b, unpad=False)[0].permute(2, 0, 1).cpu().numpy()
+    ref = golden['raft'][f'{name}_flow_up']
+    assert flow.shape == ref.shape
+    epe = _epe(flow, ref)
+    print(f'{name}/{mode}: EPE mean {epe.mean():.2e} max {epe.max():.2e} (mean |flow| {np.abs(ref).mean():.1f} px)')
+    assert epe.mean() <= 1e-2 and epe.max() <= 1e-1
+
+
+def test_bf16_volume_flow_stays_close(cuda, golden):
+    eng = _engine('basic', cuda, corr_precision='bf16')
+    img1, img2 = gi.raft_inputs('basic')
+    flow = eng.estimate_flow(torch.from_numpy(img1).to(cuda)[None], torch.from_numpy(img2).to(cuda)[None], unpad=False)
+    epe = _epe(flow[0].permute(2, 0, 1).cpu().numpy(), golden['raft']['basic_flow_up'])
+    print(f'bf16: EPE mean {epe.mean():.2e} max {epe.max():.2e}')
+    assert epe.mean() <= 5e-2
+
+
+def test_raft2_calc_dropin(cuda, golden):
+    """RAFT_2.calc(img1_bgr, img2_bgr) -> float32 [H',W',2] of the PADDED size (ofgen.py:70-79)."""
+    from sd_animation_optical_flow_b200 import ofgen
+    cfg = gi.RAFT_CASES['basic_pad']
+    algo = ofgen.RAFT_2(model_path=None, iters=cfg['iters'], seed=cfg['seed'], corr_precision='3xtf32')
+    img1, img2 = gi.raft_inputs('basic_pad')
+    flow, v = ofgen.of_calc(img1[:, :, ::-1], img2[:, :, ::-1], algo)      # scripts pass BGR
+    ref = golden['raft']['basic_pad_flow_up'].transpose(1, 2, 0)
+    assert flow.shape == ref.shape == (136, 152, 2) and flow.dtype == np.float32
+    assert _epe(flow.transpose(2, 0, 1), ref.transpose(2, 0, 1)).mean() <= 1e-2
+    np.testing.assert_allclose(v, np.sqrt((flow ** 2).sum(-1)), rtol=1e-6)
+    with pytest.raises(FileNotFoundError):
+        ofgen.RAFT_2('RAFT/models/raft-things.pth')
+
+
+def test_cuda_graph_replay_equals_eager(cuda):
+    eager = _engine('basic', cuda)
+    graphed = _engine('basic', cuda, use_cuda_graph=True)
+    img1, img2 = gi.raft_inputs('basic')
+    a = torch.from_numpy(img1).to(cuda)[None]
+    b = torch.from_numpy(img2).to(cuda)[None]
+    f0 = eager.estimate_flow(a, b)
+    f1 = graphed.estimate_flow(a, b)
+    f2 = graphed.estimate_flow(b, a)      # replay with new inputs
+    f3 = graphed.estimate_flow(a, b)
+    assert torch.allclose(f0, f1, atol=1e-4) and torch.allclose(f1, f3, atol=0) and not torch.allclose(f1, f2, atol=1e-2)
+
+
+def test_batched_pairs_equal_single_pairs(cuda):
+    eng = _engine('basic', cuda, corr_precision='3xtf32')
+    i1, i2 = gi.raft_inputs('basic')
+    j1, j2 = gi.shifted_pair(128, 160, 555, dx=-2, dy=5)
+    a = torch.from_numpy(np.stack([i1, j1])).to(cuda)
+    b = torch.from_numpy(np.stack([i2, j2])).to(cuda)
+    both = eng.estimate_flow(a, b)
+    one = eng.estimate_flow(a[1:], b[1:])
+    assert float((both[1:] - one).abs().max()) <= 2e-3

@@ -1,0 +1,138 @@
+"""GPU parity of the warp kernels, through the C ABI (ctypes) and the reference-named numpy API.
+Bar: u8 cubic bit-exact vs the reference's cv2.remap outputs (golden) and vs the oracle at full
+size; float cubic 1e-5 relative to the image range; bilinear 1e-4 abs on [0,255] vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import warp_oracle as wo
+from tests import golden_inputs as gi
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize('name', gi.WARP_CASES)
+def test_numpy_api_matches_reference_golden(cuda, golden, name):
+    from sd_animation_optical_flow_b200 import ofgen, pdcnet_of
+    img, flow = gi.warp_inputs(name)
+    flow_before = flow.copy()
+    for flavour, fn in (('pdcnet', pdcnet_of.warp_frame), ('raft', ofgen.warp_frame)):
+        ref = golden['warp'][f'{name}_{flavour}']
+        out = fn(img, flow)
+        assert out.shape == ref.shape and out.dtype == ref.dtype
+        if img.dtype == np.uint8:
+            assert np.array_equal(out, ref), f'{name}/{flavour}: {(out != ref).sum()} of {ref.size} bytes differ'
+        else:
+            ok = np.isfinite(ref)
+            np.testing.assert_allclose(out[ok], ref[ok], rtol=0, atol=1e-5 * max(1.0, float(np.abs(img).max())))
+    assert np.array_equal(flow, flow_before, equal_nan=True), 'warp_frame must not modify flow'
+
+
+@pytest.mark.parametrize('hw', [(768, 512), (720, 1280), (61, 45)])
+def test_cubic_u8_full_size_bit_exact_vs_oracle(cuda, hw):
+    from sd_animation_optical_flow_b200 import ops
+    H, W = hw
+    rs = np.random.RandomState(H)
+    img = rs.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    flow = (12.0 * rs.standard_normal((H, W, 2))).astype(np.float32)
+    flow[::7, ::5] *= 40.0   # a sprinkling of far out-of-image samples
+    for sign, fn in ((1.0, wo.warp_frame_pdcnet), (-1.0, wo.warp_frame_raft)):
+        out = ops.warp(_t(img, cuda), _t(flow, cuda), 'cv2_cubic', sign).cpu().numpy()
+        ref = fn(img, flow)
+        assert np.array_equal(out, ref), f'{(out != ref).sum()} bytes differ'
+
+
+def test_cubic_u8_batched_and_shared_source(cuda):
+    from sd_animation_optical_flow_b200 import ops
+    rs = np.random.RandomState(8)
+    B, H, W = 3, 40, 36
+    imgs = rs.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
+    flows = (5.0 * rs.standard_normal((B, H, W, 2))).astype(np.float32)
+    out = ops.warp(_t(imgs, cuda), _t(flows, cuda)).cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(out[b], wo.warp_frame_pdcnet(imgs[b], flows[b]))
+    shared = ops.warp(_t(imgs[:1], cuda), _t(flows, cuda)).cpu().numpy()   # one key frame, B flows
+    for b in range(B):
+        assert np.array_equal(shared[b], wo.warp_frame_pdcnet(imgs[0], flows[b]))
+    # different source and destination sizes
+    big = rs.randint(0, 256, (64, 80, 3)).astype(np.uint8)
+    fl = (6.0 * rs.standard_normal((20, 24, 2))).astype(np.float32) + 10
+    mx, my = wo.maps_pdcnet(fl)
+    assert np.array_equal(ops.warp(_t(big, cuda), _t(fl, cuda)).cpu().numpy(), wo.remap_cubic(big, mx, my))
+
+
+@pytest.mark.parametrize('C', [1, 2, 4])
+def test_cubic_generic_channel_counts(cuda, C):
+    from sd_animation_optical_flow_b200 import ops
+    rs = np.random.RandomState(C)
+    img = rs.randint(0, 256, (33, 47, C)).astype(np.uint8)
+    flow = (7.0 * rs.standard_normal((33, 47, 2))).astype(np.float32)
+    out = ops.warp(_t(img, cuda), _t(flow, cuda)).cpu().numpy()
+    assert np.array_equal(out, wo.warp_frame_pdcnet(img, flow))
+    imgf = rs.standard_normal((33, 47, C)).astype(np.float32)
+    outf = ops.warp(_t(imgf, cuda), _t(flow, cuda)).cpu().numpy()
+    np.testing.assert_allclose(outf, wo.warp_frame_pdcnet(imgf, flow), rtol=0, atol=1e-5)
+
+
+def test_unaligned_source_pointer_takes_the_tap_loop(cuda):
+    from sd_animation_optical_flow_b200 import ops
+    rs = np.random.RandomState(2)
+    raw = torch.from_numpy(rs.randint(0, 256, (1 + 24 * 28 * 3,)).astype(np.uint8)).to(cuda)
+    img = raw[1:].view(24, 28, 3)      # data_ptr is odd
+    flow = (3.0 * rs.standard_normal((24, 28, 2))).astype(np.float32)
+    assert img.data_ptr() % 4 != 0
+    out = ops.warp(img, _t(flow, cuda)).cpu().numpy()
+    assert np.array_equal(out, wo.warp_frame_pdcnet(img.cpu().numpy(), flow))
+
+
+def test_bilinear_vs_oracle_and_grid_sample(cuda):
+    from sd_animation_optical_flow_b200 import ops
+    img = gi.texture(96, 80, 5).astype(np.float32)
+    rs = np.random.RandomState(3)
+    flow = (4.0 * rs.standard_normal((96, 80, 2))).astype(np.float32)
+    flow[0, 0] = [np.nan, 1e20]
+    d_img, d_flow = _t(img, cuda), _t(flow, cuda)
+    out = ops.warp(d_img, d_flow, 'bilinear').cpu().numpy()
+    ref = wo.warp_bilinear(img, np.nan_to_num(flow, nan=1e9, posinf=1e9))
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-4)        # tolerance: 1e-4 abs on [0,255]
+    H, W = flow.shape[:2]
+    xs = torch.arange(W, device=cuda).float()[None, :] + d_flow[..., 0]
+    ys = torch.arange(H, device=cuda).float()[:, None] + d_flow[..., 1]
+    grid = torch.stack([2 * xs / (W - 1) - 1, 2 * ys / (H - 1) - 1], -1)[None]
+    gs = torch.nn.functional.grid_sample(d_img.permute(2, 0, 1)[None], grid, mode='bilinear', padding_mode='zeros',
+                                         align_corners=True)[0].permute(1, 2, 0).cpu().numpy()
+    ok = np.isfinite(gs)
+    ok[0, 0] = False
+    np.testing.assert_allclose(out[ok], gs[ok], rtol=0, atol=5e-3)  # grid_sample's coordinate round trip
+    u8 = ops.warp(_t(gi.texture(96, 80, 5), cuda), d_flow, 'bilinear').cpu().numpy()
+    assert np.array_equal(u8, wo.warp_bilinear(gi.texture(96, 80, 5), np.nan_to_num(flow, nan=1e9, posinf=1e9)))
+
+
+def test_zero_flow_is_identity_at_config5_size(cuda):
+    from sd_animation_optical_flow_b200 import ops
+    img = torch.randint(0, 256, (2, 720, 1280, 3), dtype=torch.uint8, device=cuda)
+    flow = torch.zeros((2, 720, 1280, 2), device=cuda)
+    assert torch.equal(ops.warp(img, flow), img)
+    assert torch.equal(ops.warp(img, flow, sign=-1.0), img)
+    assert torch.equal(ops.warp(img, flow, 'bilinear'), img)
+    # integer translation = shifted copy with a zero border
+    flow[..., 0] = 5.0
+    flow[..., 1] = -3.0
+    out = ops.warp(img, flow)
+    assert torch.equal(out[:, 3:, :-5], img[:, :-3, 5:])
+    assert int(out[:, :3].max()) == 0 and int(out[:, :, -5:].max()) == 0
+
+
+def test_warp_frame_latent(cuda):
+    from sd_animation_optical_flow_b200 import pdcnet_of
+    rs = np.random.RandomState(4)
+    lat = torch.from_numpy(rs.standard_normal((1, 4, 12, 16)).astype(np.float32))
+    flow = (3.0 * rs.standard_normal((96, 128, 2))).astype(np.float32)
+    out = pdcnet_of.warp_frame_latent(lat, flow)
+    ref = wo.warp_frame_latent(lat[0].numpy(), flow)
+    assert out.shape == (1, 4, 12, 16)
+    np.testing.assert_allclose(out[0].numpy(), ref, rtol=0, atol=2e-5)
