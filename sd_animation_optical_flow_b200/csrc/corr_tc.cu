@@ -398,12 +398,13 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&maps.out[0], epi + kEpiL0, tx * kPatchX, m0, ty * kPatchY + 2 * rp, b);
-          if (rp == 3) {
-            if (levels > 1) tma_store_4d(&maps.out[1], epi + kEpiL1, tx * (kPatchX / 2), m0, ty * (kPatchY / 2), b);
-            if (levels > 2) tma_store_4d(&maps.out[2], epi + kEpiL2, tx * (kPatchX / 4), m0, ty * (kPatchY / 4), b);
-            if (levels > 3) tma_store_4d(&maps.out[3], epi + kEpiL3, tx * (kPatchX / 8), m0, ty * (kPatchY / 8), b);
-          }
+          // one [32 source pixels][row] box per staged row; the maps clip partial tiles / pooled sizes
+          tma_store_4d(&maps.out[0], epi + kEpiL0, tx * kPatchX, ty * kPatchY + 2 * rp, m0, b);
+          tma_store_4d(&maps.out[0], epi + kEpiL0 + 4096, tx * kPatchX, ty * kPatchY + 2 * rp + 1, m0, b);
+          if (levels > 1) tma_store_4d(&maps.out[1], epi + kEpiL1 + rp * 2048, tx * (kPatchX / 2), ty * (kPatchY / 2) + rp, m0, b);
+          if (levels > 2 && (rp & 1))
+            tma_store_4d(&maps.out[2], epi + kEpiL2 + (rp >> 1) * 1024, tx * (kPatchX / 4), ty * (kPatchY / 4) + (rp >> 1), m0, b);
+          if (levels > 3 && rp == 3) tma_store_4d(&maps.out[3], epi + kEpiL3, tx * (kPatchX / 8), ty * (kPatchY / 8), m0, b);
           tma_store_commit();
         }
       }
@@ -597,15 +598,15 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
       if ((rc = encode_map(&maps.b[t], dt, 4, b_ptr[t], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap2"))) return rc;
     }
   }
-  // output maps: dims (x, m, y, b) so a [rows][32 m][x] box lands as one 128/64/32/16-byte row per source pixel
+  // output maps: dims (x, y, m, b); a box is one row of one level for 32 source pixels, i.e. a
+  // [32 m][row bytes] tile in shared memory with a 128/64/32/16-byte row per source pixel
   const CUtensorMapSwizzle out_sw[kTcLevels] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B,
                                                 CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
   const cuuint32_t out_bx[kTcLevels] = {32, 16, 8, 4};
-  const cuuint32_t out_by[kTcLevels] = {2, 4, 2, 1};
   for (int l = 0; l < tc_levels; ++l) {
-    cuuint64_t dims[4] = {(cuuint64_t)lay.w[l], (cuuint64_t)n1, (cuuint64_t)lay.h[l], (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[l] * 4, (cuuint64_t)lay.wp[l] * 4, (cuuint64_t)n1 * lay.pitch[l] * 4};
-    cuuint32_t box[4] = {out_bx[l], 32, out_by[l], 1};
+    cuuint64_t dims[4] = {(cuuint64_t)lay.w[l], (cuuint64_t)lay.h[l], (cuuint64_t)n1, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)lay.wp[l] * 4, (cuuint64_t)lay.pitch[l] * 4, (cuuint64_t)n1 * lay.pitch[l] * 4};
+    cuuint32_t box[4] = {out_bx[l], 1, 32, 1};
     if ((rc = encode_map(&maps.out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyramid + lay.offset[l], dims, strides, box,
                          out_sw[l], "pyramid level")))
       return rc;

@@ -3,8 +3,11 @@
 Tolerances (stated per SURVEY §8d):
   fp32 (CUDA-core) volume vs oracle/golden : 2e-5 abs  (|corr| <= ~6 here; summation-order only)
   3xtf32 volume                            : 1e-5 relative to max|corr|
-  tf32 volume (features rounded to tf32)   : 1e-2 abs on |corr| <= 65  -> scaled 1.6e-4 * max|corr|
-  bf16 volume                              : 8e-3 * max|corr|
+  tf32 volume (features rounded to tf32)   : 4e-3 abs for unit-variance features: each operand carries a
+                                             2^-12 relative rounding error, so a C-term dot product / sqrt(C)
+                                             has sigma ~= 4e-4 and the max over ~1e7 entries stays < 4e-3
+                                             (SURVEY's bound for real features: 1e-2 abs on |corr| <= 65)
+  bf16 volume                              : 3.2e-2 abs (8x the tf32 operand error)
   pooled levels vs avg_pool2d of level 0   : 1e-6 abs (same summation order as ATen)
   lookup vs reference CorrBlock            : 3e-5 abs on top of the volume error
 """
@@ -30,7 +33,7 @@ def _nhwc(f, dev):
 
 
 def _vol_tol(precision, scale):
-    return {'fp32': 2e-5, '3xtf32': 1e-5 * scale + 2e-5, 'tf32': 1.6e-4 * scale + 1e-4, 'bf16': 8e-3 * scale}[precision]
+    return {'fp32': 2e-5, '3xtf32': 1e-5 * scale + 2e-5, 'tf32': 4e-3, 'bf16': 3.2e-2}[precision]
 
 
 @pytest.mark.parametrize('precision', ['fp32', '3xtf32', 'tf32', 'bf16'])
