@@ -276,7 +276,9 @@ def run_ours(args):
     coords = coords_grid(1, H // 8, W // 8, dev) + 2 * torch.randn((1, 2, H // 8, W // 8), generator=g, device=dev)
     look_out = torch.empty((1, 324, H // 8, W // 8), device=dev)
     t_look = time_op(lambda: ops.corr_lookup(pyr, coords, 4, out=look_out), 50, torch)
-    flow32 = torch.randn((32, H, W, 2), generator=g, device=dev) * 6
+    # flows as the path produces them: a 1/8-resolution field upsampled 8x (RAFT's output is smooth)
+    flow32 = torch.nn.functional.interpolate(torch.randn((32, 2, H // 8, W // 8), generator=g, device=dev) * 6, scale_factor=8,
+                                             mode='bilinear', align_corners=False).permute(0, 2, 3, 1).contiguous()
     src32 = torch.randint(0, 256, (32, H, W, 3), dtype=torch.uint8, device=dev)
     t_warp = time_op(lambda: ops.warp(src32, flow32), 20, torch)
     wm32 = torch.randn((32, 2, H, W), generator=g, device=dev) * 3

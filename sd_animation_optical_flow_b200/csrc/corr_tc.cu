@@ -3,27 +3,31 @@
 //   level0[b, m, n] = <fmap1[b,m,:], fmap2[b,n,:]> / sqrt(C)      m: source pixel, n: target pixel
 //   level(l+1)      = avg_pool2d(level l, 2, 2)  over the target dims
 //
-// Mapping to the hardware
-//   * Both operands are K-major in HBM (channels-last features), so TMA loads 128-byte-swizzled
-//     K-slabs straight from the feature tensors: A = 128 source pixels x 128 B, B = an 8x32
-//     SPATIAL patch of target pixels x 128 B (4-D box over [b, y, x, c]).  Because an N-tile is a
-//     spatial patch whose sides are multiples of 8, every 2x2 / 4x4 / 8x8 pooling window of the
-//     pyramid is complete inside one tile.
-//   * One elected thread issues tcgen05.mma (M=128, N=256, kind::tf32 or kind::f16) into one of
-//     two 256-column TMEM accumulators; tcgen05.commit releases smem stages / publishes the
-//     accumulator through mbarriers.
-//   * Four epilogue warps read the accumulator with tcgen05.ld (thread = source pixel, registers
-//     = the 8x32 patch), scale, build levels 1-3 in registers in ATen's summation order, stage
-//     every level in swizzled shared memory and write it with TMA stores whose tensor maps carry
-//     the true (floor-pooled) level sizes, so partial tiles and odd sizes are clipped by hardware.
+// Mapping to the hardware (round-1 redesign after profiling, see profiles/README.md):
+//   * The GEMM is issued TRANSPOSED: D[n, m] with an 8x16 SPATIAL patch of TARGET pixels on the 128
+//     TMEM lanes (MMA M) and 256 consecutive SOURCE pixels on the accumulator columns (MMA N).
+//     Both operands are K-major in HBM (channels-last features), so TMA loads 64-byte-swizzled
+//     K-slabs straight from the feature tensors: A = 4-D box (16 ch-floats, 16 x, 8 y, 1 b) of fmap2,
+//     B = 3-D box (16 ch-floats, 256 px, 1 b) of fmap1; 5-stage mbarrier ring, OOB zero-filled.
+//   * One elected thread issues tcgen05.mma (M=128, N=256, kind::tf32 or kind::f16) into one of two
+//     256-column TMEM accumulators; tcgen05.commit releases smem stages / publishes the accumulator.
+//   * TWO epilogue warpgroups alternate tiles (each owns one accumulator), so a tile's epilogue may
+//     take two MMA periods.  A warp reads 32 lanes x 32 columns with tcgen05.ld: lane = target pixel
+//     (2 rows x 16 cols of the patch), register = source pixel.  Level 0 goes straight from
+//     registers to HBM -- for each source pixel the warp writes two 64-byte row segments of that
+//     pixel's map (no shared-memory staging, no TMA store, no proxy fences).  Level 1 is pooled
+//     with three warp shuffles in ATen's summation order ((a00+a01)+a10)+a11; the level-1 tile
+//     (32 KB) is exchanged through shared memory and levels 2-3 are finished by one thread per
+//     source pixel.  Floor-pooled sizes / partial tiles are handled by predicates.
 //   * Persistent grid (one CTA per SM), tiles ordered target-patch-fastest so concurrently running
-//     CTAs share the same A rows and the L2-resident fmap2.
+//     CTAs complete each other's 128-byte lines in L2 and share the L2-resident operands.
 //
 // Roofline: 2*N1*N2*C flops on the tensor pipe vs. 4*N1*sum_l(h_l*w_l) bytes of stores to HBM
 // (S config: 19.33 GFLOP vs 200.5 MB -> the kernel is HBM-store-bound).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -32,28 +36,31 @@
 
 namespace sdof {
 
-constexpr int kBM = 128;             // source pixels per tile (TMEM lanes)
-constexpr int kPatchY = 8;           // target patch rows
-constexpr int kPatchX = 32;          // target patch cols
-constexpr int kBN = kPatchY * kPatchX;  // 256 accumulator columns
-constexpr int kSlabBytes = 128;      // K-slab = one 128B swizzle atom row
-constexpr int kStages = 3;
-constexpr int kAStage = kBM * kSlabBytes;  // 16384
-constexpr int kBStage = kBN * kSlabBytes;  // 32768
-constexpr int kEpiWarps = 4;
-constexpr int kEpiL0 = 0, kEpiL1 = 8192, kEpiL2 = 16384, kEpiL3 = 18432, kEpiWarpBytes = 19456;
-constexpr int kSmemOperands = kStages * (kAStage + kBStage);          // 147456
-constexpr int kSmemEpi = kEpiWarps * kEpiWarpBytes;                   // 77824
+constexpr int kPatchY = 8;             // target patch rows   } 128 target pixels = TMEM lanes (MMA M)
+constexpr int kPatchX = 16;            // target patch cols   }
+constexpr int kBM = kPatchY * kPatchX;  // 128
+constexpr int kBN = 256;               // source pixels per tile = accumulator columns (MMA N)
+constexpr int kSlabBytes = 64;         // K-slab = one 64B swizzle atom row (16 tf32 / 32 bf16 elements)
+constexpr int kMmaPerSlab = kSlabBytes / 32;  // UMMA_K spans 32 bytes (8 tf32 / 16 bf16)
+constexpr int kStages = 5;
+constexpr int kAStage = kBM * kSlabBytes;  // 8192
+constexpr int kBStage = kBN * kSlabBytes;  // 16384
+constexpr int kEpiGroups = 2;          // epilogue warpgroups, one per TMEM accumulator
+constexpr int kEpiWarps = 4 * kEpiGroups;
+constexpr int kXchgBytes = 4 * kBN * 8 * 4;  // per group: level-1 tile [4 row-pairs][256 src px][8 x] fp32 = 32 KB
+constexpr int kSmemOperands = kStages * (kAStage + kBStage);  // 122880
+constexpr int kL2TileBytes = 2 * kBN * 4 * 4;  // per group: level-2 tile [2 rows][256 src px][4 x] fp32 = 8 KB
+constexpr int kSmemEpi = kEpiGroups * (kXchgBytes + kL2TileBytes);  // 81920
 constexpr int kSmemBars = 128;
 constexpr int kSmemTotal = kSmemOperands + kSmemEpi + kSmemBars + 1024;  // + alignment slack
-constexpr int kThreads = (kEpiWarps + 2) * 32;                        // 4 epilogue + TMA + MMA
+constexpr int kThreads = (kEpiWarps + 2) * 32;                // 8 epilogue warps + TMA + MMA
 constexpr int kMaxTerms = 3;
 constexpr int kTcLevels = 4;
 
 struct TcMaps {
-  CUtensorMap a[kMaxTerms];
-  CUtensorMap b[kMaxTerms];
-  CUtensorMap out[kTcLevels];
+  CUtensorMap a[kMaxTerms];  // fmap2 (target patch rows)
+  CUtensorMap b[kMaxTerms];  // fmap1 (source pixel rows)
+  CUtensorMap out1, out2;    // pyramid levels 1 and 2, dims (x, y, source pixel, b)
 };
 
 struct TcArgs {
@@ -61,9 +68,13 @@ struct TcArgs {
   int m_tiles, ty_tiles, tx_tiles;
   int nterms, kslabs, slab_elems;
   int levels;          // pyramid levels written by this kernel (1..4)
-  float scale;         // 1/sqrt(C)
-  float divisor;       // sqrt(C) (used when the reciprocal is not exact)
+  float divisor;       // sqrt(C) (used when 1/sqrt(C) is not a power of two)
   int use_div;
+  int debug;           // SDOF_TC_DEBUG bit mask (profiling experiments only): 1 skip L0 stores, 2 skip pooled levels,
+                       // 4 skip MMA issue, 8 skip operand loads
+  float* out[kTcLevels];
+  long long pitch[kTcLevels];
+  int wp[kTcLevels], lh[kTcLevels], lw[kTcLevels];
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -162,22 +173,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[32], uint32_t (&b)[32]) {
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31]),
-                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]), "+r"(b[16]), "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]), "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
                :
                : "memory");
 }
 
-// UMMA shared-memory descriptor: K-major operand, 128B swizzle, 8-row atoms 1024 B apart.
+// UMMA shared-memory descriptor: K-major operand, 64B swizzle, 8-row atoms (8 x 64 B) 512 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
   d |= (uint64_t)0 << 16;                       // leading byte offset: unused for swizzled K-major
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= (uint64_t)((8 * kSlabBytes) >> 4) << 32; // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  d |= (uint64_t)(kSlabBytes == 128 ? 2 : 4) << 61;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return d;
 }
 
@@ -200,6 +210,53 @@ __device__ __forceinline__ float pool4(float a, float b, float c, float d) {
   return __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d) * 0.25f;
 }
 
+// predicated stores (forced predication: a divergent `if` around a store costs BSSY/BSYNC pairs)
+__device__ __forceinline__ void st_global_pred(float* p, float v, uint32_t pred) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.f32 [%0], %1;\n}\n" ::"l"(p), "f"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void st_shared_pred(float* p, float v, uint32_t pred) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.f32 [%0], %1;\n}\n" ::"r"(smem_u32(p)), "f"(v), "r"(pred)
+               : "memory");
+}
+
+// One accumulator column (= one source pixel) of the epilogue: level-0 store, 2x2 pooling by shuffles in
+// ATen's order ((a00+a01)+a10)+a11, level-1 store + hand-over to the level-2/3 stage.
+template <bool kAllIn0, bool kPool>
+__device__ __forceinline__ void epi_column(float v, float*& p0, long long pitch0, uint32_t in0, float*& xr, uint32_t own1) {
+  if (kAllIn0)
+    *p0 = v;  // 2 x 64-byte row segments per warp
+  else
+    st_global_pred(p0, v, in0);
+  p0 += pitch0;
+  if (kPool) {
+    const float a01 = __shfl_xor_sync(0xffffffffu, v, 1);
+    const float a10 = __shfl_xor_sync(0xffffffffu, v, 16);
+    const float a11 = __shfl_xor_sync(0xffffffffu, v, 17);
+    const float l1 = __fadd_rn(__fadd_rn(__fadd_rn(v, a01), a10), a11) * 0.25f;
+    st_shared_pred(xr, l1, own1);  // level-1 tile [row pair][source pixel][8 x] -> TMA store + levels 2/3
+    xr += 8;
+  }
+}
+
+template <bool kAllIn0, bool kPool>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&u)[32], int ncols, bool use_div, float divisor, float*& p0,
+                                          long long pitch0, uint32_t in0, float*& xr, uint32_t own1) {
+  if (ncols >= 32 && !use_div) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj)
+      epi_column<kAllIn0, kPool>(__uint_as_float(u[jj]), p0, pitch0, in0, xr, own1);
+  } else {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      if (jj < ncols) {  // warp-uniform
+        float v = __uint_as_float(u[jj]);
+        if (use_div) v = __fdiv_rn(v, divisor);  // exact power-of-two scales are folded into the operand instead
+        epi_column<kAllIn0, kPool>(v, p0, pitch0, in0, xr, own1);
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- the kernel
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __grid_constant__ TcMaps maps,
@@ -208,7 +265,6 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + kStages * kAStage;
-  const uint32_t smem_epi = base + kSmemOperands;
   const uint32_t bars = base + kSmemOperands + kSmemEpi;
   const uint32_t bar_full = bars;                  // [kStages]
   const uint32_t bar_empty = bars + 8 * kStages;   // [kStages]
@@ -229,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, kEpiWarps);
+      mbar_init(bar_tempty + 8 * i, 4);  // the 4 warps of the epilogue group that owns the accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -238,7 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
       prefetch_tmap(&maps.a[t]);
       prefetch_tmap(&maps.b[t]);
     }
-    for (int l = 0; l < args.levels; ++l) prefetch_tmap(&maps.out[l]);
+    if (args.levels > 1) prefetch_tmap(&maps.out1);
+    if (args.levels > 2) prefetch_tmap(&maps.out2);
   }
   if (warp == kEpiWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
@@ -261,10 +318,14 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
         for (int term = 0; term < args.nterms; ++term) {
           for (int k = 0; k < args.kslabs; ++k) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            mbar_expect_tx(bar_full + 8 * stage, kAStage + kBStage);
-            tma_load_3d(smem_a + stage * kAStage, &maps.a[term], bar_full + 8 * stage, k * args.slab_elems, mt * kBM, b);
-            tma_load_4d(smem_b + stage * kBStage, &maps.b[term], bar_full + 8 * stage, k * args.slab_elems,
-                        tx * kPatchX, ty * kPatchY, b);
+            if (args.debug & 8) {
+              mbar_arrive(bar_full + 8 * stage);
+            } else {
+              mbar_expect_tx(bar_full + 8 * stage, kAStage + kBStage);
+              tma_load_4d(smem_a + stage * kAStage, &maps.a[term], bar_full + 8 * stage, k * args.slab_elems,
+                          tx * kPatchX, ty * kPatchY, b);
+              tma_load_3d(smem_b + stage * kBStage, &maps.b[term], bar_full + 8 * stage, k * args.slab_elems, mt * kBN, b);
+            }
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -290,8 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
           const uint64_t adesc = make_smem_desc(smem_a + stage * kAStage);
           const uint64_t bdesc = make_smem_desc(smem_b + stage * kBStage);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // 4 x 32 bytes of K per 128-byte slab (UMMA_K = 8 tf32 / 16 bf16)
-            tc_mma<kBf16>(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (kk > 0 || j > 0) ? 1u : 0u);
+          for (int j = 0; j < kMmaPerSlab; ++j)  // 32 bytes of K per MMA (UMMA_K = 8 tf32 / 16 bf16)
+            if (!(args.debug & 4)) tc_mma<kBf16>(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (kk > 0 || j > 0) ? 1u : 0u);
           tc_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
           if (++stage == kStages) {
             stage = 0;
@@ -302,114 +363,124 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
       }
     }
   } else {
-    // ===================================================================== epilogue warps 0..3
-    const uint32_t epi = smem_epi + warp * kEpiWarpBytes;
-    const uint32_t lane_row128 = epi + kEpiL0 + lane * 128;
-    const uint32_t sw128 = lane & 7, sw64 = (lane >> 1) & 3, sw32 = (lane >> 2) & 1;
+    // ===================================================================== epilogue: 2 groups x 4 warps
+    const int grp = warp >> 2, q = warp & 3;       // q selects TMEM lanes 32q..32q+31 = patch rows 2q, 2q+1
+    const int yl = lane >> 4, xl = lane & 15;
+    float* xchg = reinterpret_cast<float*>(gen_base + kSmemOperands + grp * (kXchgBytes + kL2TileBytes));  // [4][kBN][8]
+    float* l2tile = xchg + kXchgBytes / 4;                                                                   // [2][kBN][4]
+    const uint32_t xchg_s = smem_u32(xchg), l2tile_s = smem_u32(l2tile);
     const int levels = args.levels;
+    const bool do_l0 = !(args.debug & 1);
+    const bool do_pool = levels > 1 && !(args.debug & 2);
+    const long long pitch0 = args.pitch[0];
+    const int h0 = args.lh[0], w0 = args.lw[0], wp0 = args.wp[0];
+    float* const out0 = args.out[0];
+    const bool use_div = args.use_div != 0;
+    const float divisor = args.divisor;
+    const int n1 = args.n1, m_tiles = args.m_tiles, tx_tiles = args.tx_tiles;
+    const uint32_t own1 = (lane & 17) == 0;  // even column, upper row of the pair: owns a 2x2 window
+    const bool issuer = q == 0 && lane == 0;  // the group's TMA-store thread
+    const uint32_t bar_id = 1 + grp;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
       const int nt = tile % n_tiles;
-      const int mt = (tile / n_tiles) % args.m_tiles;
-      const int b = tile / (n_tiles * args.m_tiles);
-      const int ty = nt / args.tx_tiles, tx = nt - ty * args.tx_tiles;
-      const int m0 = mt * kBM + warp * 32;
-      const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
-      mbar_wait(bar_tfull + 8 * ab, aphase);
+      const int mt = (tile / n_tiles) % m_tiles;
+      const int b = tile / (n_tiles * m_tiles);
+      const int ty = nt / tx_tiles, tx = nt - ty * tx_tiles;
+      const int m0 = mt * kBN;
+      const int mcount = min(kBN, n1 - m0);   // valid source pixels (columns) of this tile
+      const long long row0 = (long long)b * n1 + m0;
+      const int y = ty * kPatchY + 2 * q + yl, x = tx * kPatchX + xl;
+      const uint32_t in0 = do_l0 && y < h0 && x < w0;
+      float* p0 = out0 + row0 * pitch0 + (long long)y * wp0 + x;
+      float* xr = xchg + (size_t)q * kBN * 8 + (xl >> 1);
+      const bool all_in0 = __all_sync(0xffffffffu, in0);
+
+      if (do_pool) {
+        // the previous tile's TMA stores must have finished reading the exchange tiles before they are rewritten
+        if (issuer) tma_store_wait_read0();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
+      mbar_wait(bar_tfull + 8 * grp, (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ab * kBN;
-      float s1[8];  // horizontal pair sums of the previous level-1 row (for level 2)
-      float s2[4];  // horizontal pair sums of the previous level-2 row (for level 3)
-#pragma unroll
-      for (int rp = 0; rp < 4; ++rp) {
-        uint32_t ua[32], ub[32];
-        tmem_ld32(taddr + rp * 64, ua);       // patch row 2*rp
-        tmem_ld32(taddr + rp * 64 + 32, ub);  // patch row 2*rp+1
-        tmem_ld_wait(ua, ub);
-        float ra[32], rb[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          ra[i] = __uint_as_float(ua[i]);
-          rb[i] = __uint_as_float(ub[i]);
-        }
-        if (rp == 3) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kBN;
+#pragma unroll 1
+      for (int chunk = 0; chunk < kBN / 32; ++chunk) {
+        uint32_t u[32];
+        tmem_ld32(taddr + chunk * 32, u);
+        tmem_ld_wait(u);
+        if (chunk == kBN / 32 - 1) {
           // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * grp);
         }
-        if (args.use_div) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            ra[i] = __fdiv_rn(ra[i], args.divisor);
-            rb[i] = __fdiv_rn(rb[i], args.divisor);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            ra[i] *= args.scale;
-            rb[i] *= args.scale;
+        const int ncols = mcount - chunk * 32;
+        if (ncols > 0) {
+          if (do_pool) {
+            if (all_in0)
+              epi_chunk<true, true>(u, ncols, use_div, divisor, p0, pitch0, in0, xr, own1);
+            else
+              epi_chunk<false, true>(u, ncols, use_div, divisor, p0, pitch0, in0, xr, own1);
+          } else {
+            epi_chunk<false, false>(u, ncols, use_div, divisor, p0, pitch0, in0, xr, own1);
           }
         }
-        // the previous TMA stores must have finished READING the staging buffers
-        if (lane == 0) tma_store_wait_read0();
-        __syncwarp();
+      }
+      if (do_pool) {
+        // level 1: the exchange tile [r][source pixel][8 x] goes out as 4 TMA boxes (one per level-1 row);
+        // the tensor map clips columns / rows / source pixels beyond the (floor-pooled) level size
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (issuer) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          st_shared_v4(lane_row128 + ((c ^ sw128) << 4), ra[4 * c], ra[4 * c + 1], ra[4 * c + 2], ra[4 * c + 3]);
-          st_shared_v4(lane_row128 + 4096 + ((c ^ sw128) << 4), rb[4 * c], rb[4 * c + 1], rb[4 * c + 2], rb[4 * c + 3]);
+          for (int r = 0; r < 4; ++r)
+            tma_store_4d(&maps.out1, xchg_s + r * (kBN * 32), tx * (kPatchX / 2), ty * (kPatchY / 2) + r, m0, b);
+          tma_store_commit();
         }
-        if (levels > 1) {
-          float l1[16];
+        if (levels > 2) {
+          // levels 2 and 3: one thread per source pixel finishes the 4x8 level-1 tile of that pixel
+          const int t = q * 32 + lane;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) l1[j] = pool4(ra[2 * j], ra[2 * j + 1], rb[2 * j], rb[2 * j + 1]);
-          const uint32_t l1row = epi + kEpiL1 + rp * 2048 + lane * 64;
+          for (int rep = 0; rep < kBN / 128; ++rep) {
+            const int j = t + rep * 128;
+            float l1v[4][8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            st_shared_v4(l1row + ((c ^ sw64) << 4), l1[4 * c], l1[4 * c + 1], l1[4 * c + 2], l1[4 * c + 3]);
-          if (levels > 2) {
-            if ((rp & 1) == 0) {
+            for (int r = 0; r < 4; ++r) {
+              const float4 lo = *reinterpret_cast<const float4*>(xchg + ((size_t)r * kBN + j) * 8);
+              const float4 hi = *reinterpret_cast<const float4*>(xchg + ((size_t)r * kBN + j) * 8 + 4);
+              l1v[r][0] = lo.x; l1v[r][1] = lo.y; l1v[r][2] = lo.z; l1v[r][3] = lo.w;
+              l1v[r][4] = hi.x; l1v[r][5] = hi.y; l1v[r][6] = hi.z; l1v[r][7] = hi.w;
+            }
+            float l2v[2][4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) s1[j] = __fadd_rn(l1[2 * j], l1[2 * j + 1]);
-            } else {
-              float l2[8];
+            for (int r = 0; r < 2; ++r) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                l2[j] = __fadd_rn(__fadd_rn(s1[j], l1[2 * j]), l1[2 * j + 1]) * 0.25f;
-              const uint32_t l2row = epi + kEpiL2 + (rp >> 1) * 1024 + lane * 32;
+              for (int i = 0; i < 4; ++i)
+                l2v[r][i] = pool4(l1v[2 * r][2 * i], l1v[2 * r][2 * i + 1], l1v[2 * r + 1][2 * i], l1v[2 * r + 1][2 * i + 1]);
+              *reinterpret_cast<float4*>(l2tile + ((size_t)r * kBN + j) * 4) = make_float4(l2v[r][0], l2v[r][1], l2v[r][2], l2v[r][3]);
+            }
+            if (levels > 3 && j < mcount && ty < args.lh[3]) {
+              float* p3 = args.out[3] + (row0 + j) * args.pitch[3] + (long long)ty * args.wp[3];
 #pragma unroll
-              for (int c = 0; c < 2; ++c)
-                st_shared_v4(l2row + ((c ^ sw32) << 4), l2[4 * c], l2[4 * c + 1], l2[4 * c + 2], l2[4 * c + 3]);
-              if (levels > 3) {
-                if (rp == 1) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) s2[j] = __fadd_rn(l2[2 * j], l2[2 * j + 1]);
-                } else {
-                  float l3[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    l3[j] = __fadd_rn(__fadd_rn(s2[j], l2[2 * j]), l2[2 * j + 1]) * 0.25f;
-                  st_shared_v4(epi + kEpiL3 + lane * 16, l3[0], l3[1], l3[2], l3[3]);
-                }
+              for (int i = 0; i < 2; ++i) {
+                const int x3 = tx * 2 + i;
+                if (x3 < args.lw[3]) p3[x3] = pool4(l2v[0][2 * i], l2v[0][2 * i + 1], l2v[1][2 * i], l2v[1][2 * i + 1]);
               }
             }
           }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          // one [32 source pixels][row] box per staged row; the maps clip partial tiles / pooled sizes
-          tma_store_4d(&maps.out[0], epi + kEpiL0, tx * kPatchX, ty * kPatchY + 2 * rp, m0, b);
-          tma_store_4d(&maps.out[0], epi + kEpiL0 + 4096, tx * kPatchX, ty * kPatchY + 2 * rp + 1, m0, b);
-          if (levels > 1) tma_store_4d(&maps.out[1], epi + kEpiL1 + rp * 2048, tx * (kPatchX / 2), ty * (kPatchY / 2) + rp, m0, b);
-          if (levels > 2 && (rp & 1))
-            tma_store_4d(&maps.out[2], epi + kEpiL2 + (rp >> 1) * 1024, tx * (kPatchX / 4), ty * (kPatchY / 4) + (rp >> 1), m0, b);
-          if (levels > 3 && rp == 3) tma_store_4d(&maps.out[3], epi + kEpiL3, tx * (kPatchX / 8), ty * (kPatchY / 8), m0, b);
-          tma_store_commit();
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (issuer) {
+            tma_store_4d(&maps.out2, l2tile_s, tx * (kPatchX / 4), ty * (kPatchY / 4), m0, b);
+            tma_store_4d(&maps.out2, l2tile_s + kBN * 16, tx * (kPatchX / 4), ty * (kPatchY / 4) + 1, m0, b);
+            tma_store_commit();
+          }
         }
       }
     }
-    if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
+    if (issuer) tma_store_wait_all();  // global writes complete before the CTA exits
   }
 
   tc_fence_before();
@@ -424,11 +495,11 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
 // 3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); products hi*hi + hi*lo + lo*hi keep
 // ~21 mantissa bits.  Both parts are exactly representable in tf32, so the tensor core's own
 // fp32->tf32 conversion cannot change them.
-__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, int64_t n4,
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, int64_t n4, float scale,
                                                          float4* __restrict__ hi, float4* __restrict__ lo) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = x[i];
-    const float in[4] = {v.x, v.y, v.z, v.w};
+    const float in[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};  // scale is a power of two: exact
     float h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -446,23 +517,24 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
 
 // Plain TF32 mode: round the features to tf32 (nearest, ties away) once, so the result does not
 // depend on how the tensor core would truncate raw fp32 bits (truncation costs ~10x in flow error).
-__global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ x, int64_t n4,
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ x, int64_t n4, float scale,
                                                          float4* __restrict__ y) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = x[i];
     uint32_t a, b, c, d;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x * scale));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y * scale));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z * scale));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w * scale));
     y[i] = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
   }
 }
 
-__global__ void __launch_bounds__(256) to_bf16_kernel(const float4* __restrict__ x, int64_t n4, uint2* __restrict__ y) {
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float4* __restrict__ x, int64_t n4, float scale,
+                                                      uint2* __restrict__ y) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = x[i];
-    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x * scale, v.y * scale), p1 = __floats2bfloat162_rn(v.z * scale, v.w * scale);
     uint2 o;
     o.x = *reinterpret_cast<const uint32_t*>(&p0);
     o.y = *reinterpret_cast<const uint32_t*>(&p1);
@@ -532,6 +604,10 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
 
   const int64_t e1 = (int64_t)B * n1 * C, e2 = (int64_t)B * n2 * C;
   auto al = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+  // 1/sqrt(C) is a power of two when C is a power of 4: fold it (exactly) into the A operand during the
+  // rounding pre-pass; otherwise the epilogue divides by sqrt(C) like the reference
+  const bool pow4 = (C & (C - 1)) == 0 && (__builtin_ctz(C) % 2 == 0);
+  const float a_scale = pow4 ? 1.0f / sqrtf((float)C) : 1.0f;
   const void* a_ptr[kMaxTerms];
   const void* b_ptr[kMaxTerms];
   int nterms = 1;
@@ -541,10 +617,10 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
     float* a_lo = reinterpret_cast<float*>(w + al(e1 * 4));
     float* b_hi = reinterpret_cast<float*>(w + 2 * al(e1 * 4));
     float* b_lo = reinterpret_cast<float*>(w + 2 * al(e1 * 4) + al(e2 * 4));
-    split_tf32_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4,
+    split_tf32_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4, a_scale,
                                                                reinterpret_cast<float4*>(a_hi), reinterpret_cast<float4*>(a_lo));
     SDOF_LAUNCH_CHECK("split_tf32_kernel");
-    split_tf32_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4,
+    split_tf32_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4, 1.0f,
                                                                reinterpret_cast<float4*>(b_hi), reinterpret_cast<float4*>(b_lo));
     SDOF_LAUNCH_CHECK("split_tf32_kernel");
     // small terms first, the dominant hi*hi product last
@@ -556,10 +632,10 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
     uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
     void* a16 = w;
     void* b16 = w + al(e1 * 2);
-    to_bf16_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4,
+    to_bf16_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4, a_scale,
                                                             reinterpret_cast<uint2*>(a16));
     SDOF_LAUNCH_CHECK("to_bf16_kernel");
-    to_bf16_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4,
+    to_bf16_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4, 1.0f,
                                                             reinterpret_cast<uint2*>(b16));
     SDOF_LAUNCH_CHECK("to_bf16_kernel");
     a_ptr[0] = a16;
@@ -568,10 +644,10 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
     uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
     float* a_r = reinterpret_cast<float*>(w);
     float* b_r = reinterpret_cast<float*>(w + al(e1 * 4));
-    round_tf32_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4,
+    round_tf32_kernel<<<grid_for(e1 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), e1 / 4, a_scale,
                                                                reinterpret_cast<float4*>(a_r));
     SDOF_LAUNCH_CHECK("round_tf32_kernel");
-    round_tf32_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4,
+    round_tf32_kernel<<<grid_for(e2 / 4, 256, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap2), e2 / 4, 1.0f,
                                                                reinterpret_cast<float4*>(b_r));
     SDOF_LAUNCH_CHECK("round_tf32_kernel");
     a_ptr[0] = a_r;
@@ -581,34 +657,32 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
   const int es = bf16 ? 2 : 4;
   const int slab_elems = kSlabBytes / es;
   const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = kSlabBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
   for (int t = 0; t < nterms; ++t) {
-    {
-      cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)n1, (cuuint64_t)B};
-      cuuint64_t strides[2] = {(cuuint64_t)C * es, (cuuint64_t)n1 * C * es};
-      cuuint32_t box[3] = {(cuuint32_t)slab_elems, (cuuint32_t)kBM, 1};
-      if ((rc = encode_map(&maps.a[t], dt, 3, a_ptr[t], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap1"))) return rc;
-    }
-    {
+    {  // MMA A operand (TMEM lanes): an 8x16 spatial patch of fmap2
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)B};
       cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)w2 * C * es, (cuuint64_t)n2 * C * es};
       cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)kPatchX, (cuuint32_t)kPatchY, 1};
-      if ((rc = encode_map(&maps.b[t], dt, 4, b_ptr[t], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap2"))) return rc;
+      if ((rc = encode_map(&maps.a[t], dt, 4, b_ptr[t], dims, strides, box, sw, "fmap2"))) return rc;
+    }
+    {  // MMA B operand (accumulator columns): 256 consecutive source pixels of fmap1
+      cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)n1, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)C * es, (cuuint64_t)n1 * C * es};
+      cuuint32_t box[3] = {(cuuint32_t)slab_elems, (cuuint32_t)kBN, 1};
+      if ((rc = encode_map(&maps.b[t], dt, 3, a_ptr[t], dims, strides, box, sw, "fmap1"))) return rc;
     }
   }
-  // output maps: dims (x, y, m, b); a box is one row of one level for 32 source pixels, i.e. a
-  // [32 m][row bytes] tile in shared memory with a 128/64/32/16-byte row per source pixel
-  const CUtensorMapSwizzle out_sw[kTcLevels] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B,
-                                                CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
-  const cuuint32_t out_bx[kTcLevels] = {32, 16, 8, 4};
-  for (int l = 0; l < tc_levels; ++l) {
+
+  // pooled levels 1 and 2 leave through TMA: dims (x, y, source pixel, b), one box = one level row of 256 source pixels
+  for (int l = 1; l < tc_levels && l <= 2; ++l) {
     cuuint64_t dims[4] = {(cuuint64_t)lay.w[l], (cuuint64_t)lay.h[l], (cuuint64_t)n1, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)lay.wp[l] * 4, (cuuint64_t)lay.pitch[l] * 4, (cuuint64_t)n1 * lay.pitch[l] * 4};
-    cuuint32_t box[4] = {out_bx[l], 1, 32, 1};
-    if ((rc = encode_map(&maps.out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyramid + lay.offset[l], dims, strides, box,
-                         out_sw[l], "pyramid level")))
+    cuuint32_t box[4] = {(cuuint32_t)(l == 1 ? kPatchX / 2 : kPatchX / 4), 1, (cuuint32_t)kBN, 1};
+    if ((rc = encode_map(l == 1 ? &maps.out1 : &maps.out2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pyramid + lay.offset[l], dims,
+                         strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, "pyramid level")))
       return rc;
   }
 
@@ -617,17 +691,27 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
   args.n1 = n1;
   args.h2 = h2;
   args.w2 = w2;
-  args.m_tiles = ceil_div(n1, kBM);
+  args.m_tiles = ceil_div(n1, kBN);
   args.ty_tiles = ceil_div(h2, kPatchY);
   args.tx_tiles = ceil_div(w2, kPatchX);
   args.nterms = nterms;
   args.slab_elems = slab_elems;
   args.kslabs = ceil_div(C, slab_elems);
   args.levels = tc_levels;
-  const float sq = sqrtf((float)C);
-  args.scale = 1.0f / sq;
-  args.divisor = sq;
-  args.use_div = !((C & (C - 1)) == 0 && (__builtin_ctz(C) % 2 == 0));
+  args.divisor = sqrtf((float)C);
+  for (int i = 0; i < kTcLevels; ++i) {
+    const int li = i < tc_levels ? i : 0;
+    args.out[i] = pyramid + lay.offset[li];
+    args.pitch[i] = lay.pitch[li];
+    args.wp[i] = lay.wp[li];
+    args.lh[i] = lay.h[li];
+    args.lw[i] = lay.w[li];
+  }
+  args.use_div = !pow4;
+  {
+    const char* dbg = getenv("SDOF_TC_DEBUG");
+    args.debug = dbg ? atoi(dbg) : 0;
+  }
   const int64_t total_tiles = (int64_t)B * args.m_tiles * args.ty_tiles * args.tx_tiles;
   if (total_tiles > 0x7fffffff) return SDOF_ERR_UNSUPPORTED;
   const int grid = (int)(total_tiles < sm_count() ? total_tiles : sm_count());

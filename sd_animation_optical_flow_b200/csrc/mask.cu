@@ -35,10 +35,12 @@ __global__ void __launch_bounds__(256) travel_distance_kernel(const float* __res
     int b, y, x;
     decompose_pixel(i, hw, W, b, y, x);
     const float2 f = *reinterpret_cast<const float2*>(flow + i * 2);
-    const float mx = (float)((double)x + (double)f.x);
-    const float my = (float)((double)y + (double)f.y);
-    const float dx = (float)((double)mx - (double)x);
-    const float dy = (float)((double)my - (double)y);
+    // float32(float64 grid + flow) and back: single fp32 adds give the same bits (see warp.cuh map_coord;
+    // the subtraction of an integer grid value from its own rounded sum is exact or single-rounded)
+    const float mx = __fadd_rn((float)x, f.x);
+    const float my = __fadd_rn((float)y, f.y);
+    const float dx = __fsub_rn(mx, (float)x);
+    const float dy = __fsub_rn(my, (float)y);
     const float r = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
     v[i] = (conf[i] < thres) ? 0.f : r;
   }

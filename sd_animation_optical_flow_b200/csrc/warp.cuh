@@ -23,10 +23,13 @@ __device__ __forceinline__ int cv_round_x32(float v) {
 
 __device__ __forceinline__ int sat_s16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
 
-// sampling coordinate exactly as the reference builds its remap maps:
-// float32(float64 grid + flow) (pdcnet_of.py:35-40) / float32(-flow + arange) (ofgen.py:39-41)
+// Sampling coordinate exactly as the reference builds its remap maps:
+//   float32(float64 grid + flow) (pdcnet_of.py:35-40) / float32(-flow + arange) (ofgen.py:39-41).
+// A single fp32 add gives the same bits: the grid value is an integer < 2^24 and flow has a 24-bit
+// significand, so whenever the exact sum needs more than the 53 bits of a double, flow is smaller than
+// 2^-5 float-ulps of the grid value and cannot reach a rounding midpoint -- no double-rounding case exists.
 __device__ __forceinline__ float map_coord(int grid, float flow, float sign) {
-  return (float)((double)grid + (double)(sign * flow));
+  return __fadd_rn((float)grid, sign * flow);
 }
 
 // flat pixel index -> (batch, y, x); 32-bit divisions whenever the sizes allow
@@ -90,18 +93,23 @@ __device__ __forceinline__ unsigned cubic_u8_c3(const int16_t* __restrict__ tab,
   const unsigned whi[4] = {wa.y, wa.w, wb.y, wb.w};
   int a0 = 0, a1 = 0, a2 = 0;
   const bool interior = Ws > 3 && Hs > 3 && (unsigned)fc.sx < (unsigned)(Ws - 3) && (unsigned)fc.sy < (unsigned)(Hs - 3);
-  const unsigned char* p0 = img + ((int64_t)fc.sy * Ws + fc.sx) * 3;
+  const int row_bytes = Ws * 3;
+  // a single image is < 2 GB (H, W <= 32767), so byte offsets inside it fit in 32 bits
+  const unsigned char* p0 = img + (fc.sy * Ws + fc.sx) * 3;
   // the aligned 16-byte window of the last tap row must stay inside the buffer
-  const bool fast = interior && (p0 + (int64_t)3 * Ws * 3 + 16 <= buf_end);
+  const bool fast = interior && (p0 + 3 * row_bytes + 16 <= buf_end);
   if (fast) {
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p0) & 3);
+    const unsigned char* q0 = p0 - mis;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
-      const unsigned char* p = p0 + (int64_t)ky * Ws * 3;
-      const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
-      const unsigned* q = reinterpret_cast<const unsigned*>(p - mis);
+      // rows are row_bytes apart: the misalignment of row ky is (mis + ky*row_bytes) & 3
+      const unsigned off = mis + (unsigned)(ky * row_bytes);
+      const unsigned m = off & 3;
+      const unsigned* q = reinterpret_cast<const unsigned*>(q0 + (off - m));
       const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-      const unsigned w3 = mis ? __ldg(q + 3) : 0u;
-      const unsigned sh = mis * 8;
+      const unsigned w3 = m ? __ldg(q + 3) : 0u;
+      const unsigned sh = m * 8;
       const unsigned r0 = __funnelshift_r(w0, w1, sh);  // bytes b0..b3  (pixel k channel c = b[3k+c])
       const unsigned r1 = __funnelshift_r(w1, w2, sh);  // b4..b7
       const unsigned r2 = __funnelshift_r(w2, w3, sh);  // b8..b11
@@ -124,7 +132,7 @@ __device__ __forceinline__ unsigned cubic_u8_c3(const int16_t* __restrict__ tab,
         if ((unsigned)xx >= (unsigned)Ws) continue;
         const unsigned pair = (kx < 2) ? wlo[ky] : whi[ky];
         const int w = (int)(short)((kx & 1) ? (pair >> 16) : (pair & 0xffffu));
-        const unsigned char* p = img + ((int64_t)yy * Ws + xx) * 3;
+        const unsigned char* p = img + (yy * Ws + xx) * 3;
         a0 += w * (int)p[0];
         a1 += w * (int)p[1];
         a2 += w * (int)p[2];

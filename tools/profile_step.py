@@ -32,7 +32,8 @@ else:
     f2 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
     coords = coords_grid(1, 96, 64, dev) + 2 * torch.randn((1, 2, 96, 64), generator=g, device=dev)
     src = torch.randint(0, 256, (32, 768, 512, 3), dtype=torch.uint8, device=dev)
-    flow = torch.randn((32, 768, 512, 2), generator=g, device=dev) * 6
+    flow = torch.nn.functional.interpolate(torch.randn((32, 2, 96, 64), generator=g, device=dev) * 6, scale_factor=8, mode='bilinear',
+                                           align_corners=False).permute(0, 2, 3, 1).contiguous()
     wm = torch.randn((32, 2, 768, 512), generator=g, device=dev) * 3
     for _ in range(3):
         pyr = ops.corr_volume_pyramid(f1, f2, 4, prec)

@@ -1,0 +1,23 @@
+import os, sys, subprocess
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+if len(sys.argv) > 1:
+    import torch
+    from sd_animation_optical_flow_b200 import ops
+    dev = torch.device('cuda', 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    f1 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
+    f2 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
+    for prec in ('tf32', 'bf16'):
+        fn = lambda: ops.corr_volume_pyramid(f1, f2, 4, prec)
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(20): fn()
+        e.record(); torch.cuda.synchronize()
+        print(f'debug={os.environ.get("SDOF_TC_DEBUG","0"):>2s} {prec}: {s.elapsed_time(e)/20*1e3:.1f} us', flush=True)
+else:
+    for dbg in (0, 1, 2, 3, 4, 7, 8, 12, 15):
+        env = dict(os.environ, SDOF_TC_DEBUG=str(dbg))
+        subprocess.run([sys.executable, __file__, 'child'], env=env, timeout=300)
