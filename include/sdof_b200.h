@@ -37,7 +37,11 @@ enum sdof_precision {
   SDOF_PREC_TF32 = 0,   /* tcgen05 kind::tf32, one pass, features rounded to nearest */
   SDOF_PREC_3XTF32 = 1, /* tcgen05 kind::tf32, error-compensated (fp32-faithful) */
   SDOF_PREC_BF16 = 2,   /* tcgen05 kind::f16 on bf16 copies of the features     */
-  SDOF_PREC_FP32 = 3    /* CUDA-core fp32 FMA (exact-order checker on device)   */
+                        /* FP16/BF16 use the resident-operand kernel and build level l from the 2^l-pooled fmap2
+                         * (avg-pooling is linear: RAFT/core/corr.py:68-72 does the same); TF32/3XTF32/FP32 pool the
+                         * level-0 volume exactly like RAFT/core/corr.py:25-27 */
+  SDOF_PREC_FP32 = 3,   /* CUDA-core fp32 FMA (exact-order checker on device)   */
+  SDOF_PREC_FP16 = 4    /* tcgen05 kind::f16 on fp16 copies (11-bit significand = TF32 precision): the fast path */
 };
 
 int sdof_abi_version(void);
@@ -47,7 +51,7 @@ const char* sdof_last_error(void);
  * Layout of the correlation pyramid in HBM.  Level l holds, for each of the
  * `rows` = B*h1*w1 source pixels, an h[l] x w[l] map (h[l]=h2>>l, w[l]=w2>>l,
  * floor) stored row-major with row pitch wp[l] (w[l] rounded up to 4 floats so
- * that TMA stores are 16-byte aligned).  Element (row, y, x) of level l is at
+ * that TMA stores are 16-byte aligned); pitch[l] = h[l]*wp[l].  Element (row, y, x) of level l is at
  *   pyramid[offset[l] + row*pitch[l] + y*wp[l] + x].
  * Replaces the list `CorrBlock.corr_pyramid` (RAFT/core/corr.py:15-27).       */
 typedef struct sdof_pyramid_layout {
@@ -64,7 +68,7 @@ int sdof_corr_pyramid_layout(int64_t rows, int h2, int w2, int levels, sdof_pyra
 
 /* Scratch bytes sdof_corr_volume_pyramid needs for `precision` (rounded / split / bf16 copies of
  * the features; 0 for FP32). */
-int64_t sdof_corr_volume_workspace_bytes(int B, int h1, int w1, int h2, int w2, int C, int precision);
+int64_t sdof_corr_volume_workspace_bytes(int B, int h1, int w1, int h2, int w2, int C, int levels, int precision);
 
 /* All-pairs correlation volume + its average-pooled pyramid in one pass:
  *   level0[b, i, j] = <fmap1[b,i,:], fmap2[b,j,:]> / sqrt(C);  level l+1 = avg_pool2d(level l, 2, 2)
@@ -74,6 +78,21 @@ int64_t sdof_corr_volume_workspace_bytes(int B, int h1, int w1, int h2, int w2, 
 int sdof_corr_volume_pyramid(const float* fmap1, const float* fmap2, int B, int h1, int w1, int h2, int w2, int C,
                              int levels, int precision, float* pyramid, void* workspace, int64_t workspace_bytes,
                              sdof_stream_t stream);
+
+/* The FP16 / BF16 path in two steps, so that operands can be reused: in the key-frame scheme every pair of a
+ * key frame shares one feature map (RAFT is run as image1 = current frame, image2 = key frame, so fmap2 and
+ * its pooled levels are constant across those pairs).
+ *   sdof_corr_prepare_operands : 16-bit copies of fmap1 (pre-scaled by 1/sqrt(C) when that is exact) and of every
+ *                                avg-pooled level of fmap2 into `workspace`; parts: 1 = fmap1, 2 = fmap2, 3 = both
+ *                                (either pointer may be NULL when its part is not requested)
+ *   sdof_corr_pyramid_from_operands : the tcgen05 kernel alone, on a prepared workspace.
+ * workspace: sdof_corr_volume_workspace_bytes(..., precision) bytes, 256-byte aligned.  SDOF_ERR_UNSUPPORTED for
+ * other precisions or C > 256.                                                                                  */
+int sdof_corr_prepare_operands(const float* fmap1, const float* fmap2, int B, int h1, int w1, int h2, int w2, int C,
+                               int levels, int precision, int parts, void* workspace, int64_t workspace_bytes,
+                               sdof_stream_t stream);
+int sdof_corr_pyramid_from_operands(int B, int h1, int w1, int h2, int w2, int C, int levels, int precision,
+                                    float* pyramid, void* workspace, int64_t workspace_bytes, sdof_stream_t stream);
 
 /* ------------------------------------------------------------------------ C3
  * Windowed bilinear lookup in all pyramid levels for one GRU iteration.

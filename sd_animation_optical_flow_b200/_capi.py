@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int16, c_int32
 import torch
 
 SDOF_MAX_LEVELS = 8
-PRECISIONS = {'tf32': 0, '3xtf32': 1, 'bf16': 2, 'fp32': 3}
+PRECISIONS = {'tf32': 0, '3xtf32': 1, 'bf16': 2, 'fp32': 3, 'fp16': 4}
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libsdof_b200.so')
 
@@ -38,8 +38,10 @@ SIGNATURES = {
     'sdof_last_error': (c_char_p, []),
     'sdof_launch_count': (c_int64, []),
     'sdof_corr_pyramid_layout': (c_int, [c_int64, c_int, c_int, c_int, POINTER(PyramidLayout)]),
-    'sdof_corr_volume_workspace_bytes': (c_int64, [c_int] * 7),
+    'sdof_corr_volume_workspace_bytes': (c_int64, [c_int] * 8),
     'sdof_corr_volume_pyramid': (c_int, [_P, _P] + [c_int] * 8 + [_P, _P, c_int64, _P]),
+    'sdof_corr_prepare_operands': (c_int, [_P, _P] + [c_int] * 9 + [_P, c_int64, _P]),
+    'sdof_corr_pyramid_from_operands': (c_int, [c_int] * 8 + [_P, _P, c_int64, _P]),
     'sdof_corr_lookup': (c_int, [_P, _P] + [c_int] * 7 + [_P, _P]),
     'sdof_alt_corr_forward': (c_int, [_P, _P, _P] + [c_int] * 8 + [_P, _P]),
     'sdof_alt_corr_level': (c_int, [_P, _P, _P] + [c_int] * 7 + [c_float, c_float, c_int, c_int, _P, _P]),

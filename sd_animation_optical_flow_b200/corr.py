@@ -27,7 +27,7 @@ def _to_nhwc(fmap: torch.Tensor) -> torch.Tensor:
 
 class CorrBlock:
     def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4, radius: int = 4,
-                 precision: str = 'tf32'):
+                 precision: str = 'fp16'):
         if not fmap1.is_cuda or not fmap2.is_cuda:
             raise RuntimeError('CorrBlock needs CUDA feature maps: this package has no CPU path')
         self.num_levels = num_levels
@@ -44,7 +44,7 @@ class CorrBlock:
         return ops.corr_lookup(self.pyramid, coords.float().contiguous(), self.radius)
 
     @staticmethod
-    def corr(fmap1: torch.Tensor, fmap2: torch.Tensor, precision: str = 'tf32') -> torch.Tensor:
+    def corr(fmap1: torch.Tensor, fmap2: torch.Tensor, precision: str = 'fp16') -> torch.Tensor:
         """CorrBlock.corr (corr.py:52-60): [B,h,w,1,h,w] volume divided by sqrt(C)."""
         B, _, h, w = fmap1.shape
         pyr = ops.corr_volume_pyramid(_to_nhwc(fmap1), _to_nhwc(fmap2), 1, precision)

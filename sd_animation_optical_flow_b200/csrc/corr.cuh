@@ -17,4 +17,16 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
                           cudaStream_t st);
 int64_t corr_tc_workspace_bytes(int B, int n1, int n2, int C, int precision);
 
+// corr_tc_res.cu: resident-operand tcgen05 kernel, 16-bit operands (fmt 0 = fp16, 1 = bf16), pooled-feature pyramid
+int launch_corr_pyramid_resident(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, int fmt,
+                                 float* pyramid, const sdof_pyramid_layout& lay, void* workspace, int64_t workspace_bytes,
+                                 cudaStream_t st);
+int launch_corr_prepare_resident(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, int fmt,
+                                 const sdof_pyramid_layout& lay, void* workspace, int64_t workspace_bytes, int part,
+                                 cudaStream_t st);
+int launch_corr_pyramid_prepared(int B, int n1, int h2, int w2, int C, int fmt, float* pyramid, const sdof_pyramid_layout& lay,
+                                 void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int64_t corr_res_workspace_bytes(int B, int n1, int h2, int w2, int C, int levels);
+bool corr_res_supported(int C, int levels);
+
 }  // namespace sdof

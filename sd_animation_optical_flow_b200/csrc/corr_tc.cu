@@ -33,6 +33,7 @@
 #include <mutex>
 
 #include "corr.cuh"
+#include "tc_ptx.cuh"
 
 namespace sdof {
 
@@ -40,8 +41,6 @@ constexpr int kPatchY = 8;             // target patch rows   } 128 target pixel
 constexpr int kPatchX = 16;            // target patch cols   }
 constexpr int kBM = kPatchY * kPatchX;  // 128
 constexpr int kBN = 256;               // source pixels per tile = accumulator columns (MMA N)
-constexpr int kSlabBytes = 64;         // K-slab = one 64B swizzle atom row (16 tf32 / 32 bf16 elements)
-constexpr int kMmaPerSlab = kSlabBytes / 32;  // UMMA_K spans 32 bytes (8 tf32 / 16 bf16)
 constexpr int kStages = 5;
 constexpr int kAStage = kBM * kSlabBytes;  // 8192
 constexpr int kBStage = kBN * kSlabBytes;  // 16384
@@ -76,148 +75,6 @@ struct TcArgs {
   long long pitch[kTcLevels];
   int wp[kTcLevels], lh[kTcLevels], lw[kTcLevels];
 };
-
-// ----------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (true) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("sdof corr_tc: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-template <bool kBf16>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (kBf16) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  }
-}
-
-// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread i = lane base+i).
-// tcgen05.ld is asynchronous: the registers are only valid after tcgen05.wait::ld.  The wait below
-// takes every loaded register as a read-write operand so the compiler cannot schedule a consumer
-// above it.
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
-               :
-               : "memory");
-}
-
-// UMMA shared-memory descriptor: K-major operand, 64B swizzle, 8-row atoms (8 x 64 B) 512 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)0 << 16;                       // leading byte offset: unused for swizzled K-major
-  d |= (uint64_t)((8 * kSlabBytes) >> 4) << 32; // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
-  d |= (uint64_t)(kSlabBytes == 128 ? 2 : 4) << 61;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
-  return d;
-}
-
-// UMMA instruction descriptor (kind::tf32 / kind::f16): fp32 accumulate, K-major A and B.
-__host__ __device__ constexpr uint32_t make_idesc(bool bf16) {
-  return (1u << 4)                        // D format: F32
-         | ((bf16 ? 1u : 2u) << 7)        // A format: BF16 (kind::f16) / TF32 (kind::tf32)
-         | ((bf16 ? 1u : 2u) << 10)       // B format
-         | (0u << 15) | (0u << 16)        // A, B K-major
-         | ((uint32_t)(kBN >> 3) << 17)   // N
-         | ((uint32_t)(kBM >> 4) << 24);  // M
-}
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-__device__ __forceinline__ float pool4(float a, float b, float c, float d) {
-  // ATen avg_pool2d: ((a00 + a01) + a10) + a11, then / 4
-  return __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d) * 0.25f;
-}
-
-// predicated stores (forced predication: a divergent `if` around a store costs BSSY/BSYNC pairs)
-__device__ __forceinline__ void st_global_pred(float* p, float v, uint32_t pred) {
-  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.f32 [%0], %1;\n}\n" ::"l"(p), "f"(v), "r"(pred) : "memory");
-}
-__device__ __forceinline__ void st_shared_pred(float* p, float v, uint32_t pred) {
-  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.f32 [%0], %1;\n}\n" ::"r"(smem_u32(p)), "f"(v), "r"(pred)
-               : "memory");
-}
 
 // One accumulator column (= one source pixel) of the epilogue: level-0 store, 2x2 pooling by shuffles in
 // ATen's order ((a00+a01)+a10)+a11, level-1 store + hand-over to the level-2/3 stage.
@@ -337,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
   } else if (warp == kEpiWarps + 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBf16);
+      constexpr uint32_t idesc = make_idesc_fmt(kBf16 ? 1u : 2u, kBM, kBN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -560,7 +417,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims,
+int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* ptr, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(SDOF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -732,8 +589,51 @@ int launch_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int n1,
 
 extern "C" {
 
-int64_t sdof_corr_volume_workspace_bytes(int B, int h1, int w1, int h2, int w2, int C, int precision) {
-  return sdof::corr_tc_workspace_bytes(B, h1 * w1, h2 * w2, C, precision);
+int64_t sdof_corr_volume_workspace_bytes(int B, int h1, int w1, int h2, int w2, int C, int levels, int precision) {
+  using namespace sdof;
+  if (precision == SDOF_PREC_FP16 || precision == SDOF_PREC_BF16) {
+    // resident kernel; shapes it cannot take fall back to the streaming kernel (tf32 / bf16 copies)
+    const int64_t res = corr_res_workspace_bytes(B, h1 * w1, h2, w2, C, levels);
+    const int64_t str = corr_tc_workspace_bytes(B, h1 * w1, h2 * w2, C, precision == SDOF_PREC_FP16 ? SDOF_PREC_TF32 : SDOF_PREC_BF16);
+    return res > str ? res : str;
+  }
+  return corr_tc_workspace_bytes(B, h1 * w1, h2 * w2, C, precision);
+}
+
+int sdof_corr_prepare_operands(const float* fmap1, const float* fmap2, int B, int h1, int w1, int h2, int w2, int C,
+                               int levels, int precision, int parts, void* workspace, int64_t workspace_bytes,
+                               sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(parts >= 1 && parts <= 3, "sdof_corr_prepare_operands: parts must be 1, 2 or 3");
+  SDOF_REQUIRE((!(parts & 1) || fmap1) && (!(parts & 2) || fmap2) && workspace, "sdof_corr_prepare_operands: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1 && C >= 4 && C % 4 == 0, "sdof_corr_prepare_operands: bad sizes");
+  if (precision != SDOF_PREC_FP16 && precision != SDOF_PREC_BF16)
+    return fail(SDOF_ERR_UNSUPPORTED, "sdof_corr_prepare_operands: only the FP16 / BF16 paths have prepared operands");
+  sdof_pyramid_layout lay;
+  int rc = sdof_corr_pyramid_layout((int64_t)B * h1 * w1, h2, w2, levels, &lay);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  rc = launch_corr_prepare_resident(fmap1, fmap2, B, h1 * w1, h2, w2, C, precision == SDOF_PREC_FP16 ? 0 : 1, lay, workspace,
+                                    workspace_bytes, parts, as_stream(stream));
+  if (rc == SDOF_ERR_UNSUPPORTED) return fail(rc, "sdof_corr_prepare_operands: shape not supported by the resident kernel (C %% 8 == 0, C <= 256)");
+  return rc;
+}
+
+int sdof_corr_pyramid_from_operands(int B, int h1, int w1, int h2, int w2, int C, int levels, int precision,
+                                    float* pyramid, void* workspace, int64_t workspace_bytes, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(pyramid && workspace, "sdof_corr_pyramid_from_operands: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1 && C >= 4 && C % 4 == 0, "sdof_corr_pyramid_from_operands: bad sizes");
+  if (precision != SDOF_PREC_FP16 && precision != SDOF_PREC_BF16)
+    return fail(SDOF_ERR_UNSUPPORTED, "sdof_corr_pyramid_from_operands: only the FP16 / BF16 paths have prepared operands");
+  sdof_pyramid_layout lay;
+  int rc = sdof_corr_pyramid_layout((int64_t)B * h1 * w1, h2, w2, levels, &lay);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  rc = launch_corr_pyramid_prepared(B, h1 * w1, h2, w2, C, precision == SDOF_PREC_FP16 ? 0 : 1, pyramid, lay, workspace,
+                                    workspace_bytes, as_stream(stream));
+  if (rc == SDOF_ERR_UNSUPPORTED) return fail(rc, "sdof_corr_pyramid_from_operands: shape not supported by the resident kernel");
+  return rc;
 }
 
 int sdof_corr_volume_pyramid(const float* fmap1, const float* fmap2, int B, int h1, int w1, int h2, int w2, int C,
@@ -743,7 +643,7 @@ int sdof_corr_volume_pyramid(const float* fmap1, const float* fmap2, int B, int 
   SDOF_REQUIRE(fmap1 && fmap2 && pyramid, "sdof_corr_volume_pyramid: NULL pointer");
   SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "sdof_corr_volume_pyramid: bad sizes");
   SDOF_REQUIRE(C >= 4 && C % 4 == 0, "sdof_corr_volume_pyramid: C must be a positive multiple of 4, got %d", C);
-  SDOF_REQUIRE(precision >= SDOF_PREC_TF32 && precision <= SDOF_PREC_FP32, "sdof_corr_volume_pyramid: unknown precision %d",
+  SDOF_REQUIRE(precision >= SDOF_PREC_TF32 && precision <= SDOF_PREC_FP16, "sdof_corr_volume_pyramid: unknown precision %d",
                precision);
   SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2) | reinterpret_cast<uintptr_t>(pyramid)) & 15) == 0,
                "sdof_corr_volume_pyramid: pointers must be 16-byte aligned");
@@ -753,6 +653,12 @@ int sdof_corr_volume_pyramid(const float* fmap1, const float* fmap2, int B, int 
   if (rc) return rc;
   if (B == 0) return SDOF_OK;
   cudaStream_t st = as_stream(stream);
+  if (precision == SDOF_PREC_FP16 || precision == SDOF_PREC_BF16) {
+    rc = launch_corr_pyramid_resident(fmap1, fmap2, B, n1, h2, w2, C, precision == SDOF_PREC_FP16 ? 0 : 1, pyramid, lay, workspace,
+                                      workspace_bytes, st);
+    if (rc != SDOF_ERR_UNSUPPORTED) return rc;
+    precision = precision == SDOF_PREC_FP16 ? SDOF_PREC_TF32 : SDOF_PREC_BF16;  // e.g. C > 256: streaming kernel
+  }
   if (precision != SDOF_PREC_FP32) {
     rc = launch_corr_volume_tc(fmap1, fmap2, B, n1, h2, w2, C, precision, pyramid, lay, workspace, workspace_bytes, st);
     if (rc != SDOF_ERR_UNSUPPORTED) return rc;

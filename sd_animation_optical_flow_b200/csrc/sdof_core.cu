@@ -184,7 +184,7 @@ int sdof_corr_pyramid_layout(int64_t rows, int h2, int w2, int levels, sdof_pyra
     out->h[l] = h;
     out->w[l] = w;
     out->wp[l] = wp;
-    out->pitch[l] = (int64_t)h * wp;
+    out->pitch[l] = (int64_t)h * wp;  // (padding the pitch to skew L2 slices was measured: no gain, slightly slower)
     out->offset[l] = off;
     off += rows * out->pitch[l];
     off = (off + 31) & ~(int64_t)31;  // keep every level 128-byte aligned

@@ -28,7 +28,7 @@ def warp(img: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: f
 
 class RaftEngine:
     def __init__(self, checkpoint: str | None = None, iters: int = 20, small: bool = False,
-                 corr_precision: str = 'tf32', alternate_corr: bool = False, mixed_precision: bool = False,
+                 corr_precision: str = 'fp16', alternate_corr: bool = False, mixed_precision: bool = False,
                  channels_last: bool = False, use_cuda_graph: bool = False, device=None, seed: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')

@@ -35,7 +35,7 @@ class CorrPyramid:
 
 
 def corr_volume_pyramid(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor, levels: int = 4,
-                        precision: str = 'tf32') -> CorrPyramid:
+                        precision: str = 'fp16') -> CorrPyramid:
     """fmap1 [B,h1,w1,C], fmap2 [B,h2,w2,C] fp32 channels-last -> CorrPyramid (C1 + C2)."""
     require_cuda(fmap1_nhwc, 'fmap1', f32)
     require_cuda(fmap2_nhwc, 'fmap2', f32)
@@ -51,12 +51,54 @@ def corr_volume_pyramid(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor, leve
     lay = _capi.pyramid_layout(B * h1 * w1, h2, w2, levels)
     dev = fmap1_nhwc.device
     buf = torch.empty(max(int(lay.total_floats), 1), dtype=f32, device=dev)
-    ws_bytes = int(lib.sdof_corr_volume_workspace_bytes(B, h1, w1, h2, w2, C, PRECISIONS[precision]))
+    ws_bytes = int(lib.sdof_corr_volume_workspace_bytes(B, h1, w1, h2, w2, C, levels, PRECISIONS[precision]))
     ws = torch.empty(ws_bytes, dtype=u8, device=dev) if ws_bytes else None
     check(lib.sdof_corr_volume_pyramid(ptr(fmap1_nhwc), ptr(fmap2_nhwc), B, h1, w1, h2, w2, C, levels,
                                        PRECISIONS[precision], ptr(buf), ptr(ws), ws_bytes, stream_ptr(dev)),
           'sdof_corr_volume_pyramid')
     return CorrPyramid(buf, lay, B, h1, w1, h2, w2, levels)
+
+
+class CorrOperands:
+    """Prepared 16-bit operands of the fp16/bf16 correlation path (sdof_corr_prepare_operands): lets the pooled
+    feature pyramid of a key frame (fmap2) be built once and reused by every pair that shares it."""
+
+    def __init__(self, B, h1, w1, h2, w2, C, levels, precision, device):
+        if precision not in ('fp16', 'bf16'):
+            raise ValueError("prepared operands exist only for precision 'fp16' / 'bf16'")
+        self.shape = (B, h1, w1, h2, w2, C)
+        self.levels, self.precision = levels, precision
+        n = int(load().sdof_corr_volume_workspace_bytes(B, h1, w1, h2, w2, C, levels, PRECISIONS[precision]))
+        self.workspace = torch.empty(n, dtype=u8, device=device)
+
+    def prepare(self, fmap1_nhwc: torch.Tensor | None = None, fmap2_nhwc: torch.Tensor | None = None):
+        B, h1, w1, h2, w2, C = self.shape
+        parts = 0
+        if fmap1_nhwc is not None:
+            require_cuda(fmap1_nhwc, 'fmap1', f32)
+            assert tuple(fmap1_nhwc.shape) == (B, h1, w1, C)
+            parts |= 1
+        if fmap2_nhwc is not None:
+            require_cuda(fmap2_nhwc, 'fmap2', f32)
+            assert tuple(fmap2_nhwc.shape) == (B, h2, w2, C)
+            parts |= 2
+        if parts:
+            check(load().sdof_corr_prepare_operands(ptr(fmap1_nhwc), ptr(fmap2_nhwc), B, h1, w1, h2, w2, C, self.levels,
+                                                    PRECISIONS[self.precision], parts, ptr(self.workspace),
+                                                    self.workspace.numel(), stream_ptr(self.workspace.device)),
+                  'sdof_corr_prepare_operands')
+        return self
+
+    def pyramid(self, out: 'CorrPyramid | None' = None) -> 'CorrPyramid':
+        B, h1, w1, h2, w2, C = self.shape
+        if out is None:
+            lay = _capi.pyramid_layout(B * h1 * w1, h2, w2, self.levels)
+            buf = torch.empty(max(int(lay.total_floats), 1), dtype=f32, device=self.workspace.device)
+            out = CorrPyramid(buf, lay, B, h1, w1, h2, w2, self.levels)
+        check(load().sdof_corr_pyramid_from_operands(B, h1, w1, h2, w2, C, self.levels, PRECISIONS[self.precision], ptr(out.buf),
+                                                     ptr(self.workspace), self.workspace.numel(),
+                                                     stream_ptr(self.workspace.device)), 'sdof_corr_pyramid_from_operands')
+        return out
 
 
 def corr_lookup(pyr: CorrPyramid, coords: torch.Tensor, radius: int = 4, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -272,7 +272,7 @@ class RAFT(nn.Module):
     `args` may be the scripts' ad-hoc `namespace` (ofgen.py:51-66), an
     argparse Namespace or None; recognised fields: small, mixed_precision,
     alternate_corr, dropout, plus this package's `corr_precision`
-    ('tf32' | '3xtf32' | 'bf16' | 'fp32')."""
+    ('fp16' | 'tf32' | '3xtf32' | 'bf16' | 'fp32')."""
 
     def __init__(self, args=None):
         super().__init__()
@@ -313,7 +313,7 @@ class RAFT(nn.Module):
 
     def make_corr_fn(self, fmap1, fmap2):
         radius = self.args.corr_radius
-        prec = _get(self.args, 'corr_precision', 'tf32')
+        prec = _get(self.args, 'corr_precision', 'fp16')
         if self.args.alternate_corr:
             return _corr.AlternateCorrBlock(fmap1, fmap2, radius=radius)
         return _corr.CorrBlock(fmap1, fmap2, radius=radius, precision=prec)

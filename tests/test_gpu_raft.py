@@ -31,7 +31,7 @@ def _epe(a, b):
 
 
 @pytest.mark.parametrize('name', list(gi.RAFT_CASES))
-@pytest.mark.parametrize('mode', ['fp32', '3xtf32', 'tf32', 'alt'])
+@pytest.mark.parametrize('mode', ['fp32', '3xtf32', 'tf32', 'fp16', 'alt'])
 def test_flow_matches_reference_raft(cuda, golden, name, mode):
     kw = dict(alternate_corr=True) if mode == 'alt' else dict(corr_precision=mode)
     eng = _engine(name, cuda, **kw)

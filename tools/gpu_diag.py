@@ -62,7 +62,7 @@ def corr_small():
         f1 = rs.standard_normal(shape).astype(np.float32)
         f2 = rs.standard_normal(shape).astype(np.float32)
         ref = co.corr_pyramid(f1, f2, 4)
-        for prec in ('fp32', 'tf32', '3xtf32', 'bf16'):
+        for prec in ('fp32', 'fp16', 'tf32', '3xtf32', 'bf16'):
             try:
                 pyr = ops.corr_volume_pyramid(t(f1).permute(0, 2, 3, 1).contiguous(), t(f2).permute(0, 2, 3, 1).contiguous(), 4, prec)
                 torch.cuda.synchronize()
@@ -90,7 +90,7 @@ def corr_perf():
         f1 = torch.randn((1, h, w, 256), generator=g, device=dev)
         f2 = torch.randn((1, h, w, 256), generator=g, device=dev)
         n = h * w
-        for prec in ('tf32', 'bf16', '3xtf32', 'fp32'):
+        for prec in ('fp16', 'bf16', 'tf32', '3xtf32', 'fp32'):
             try:
                 us = timeit(lambda: ops.corr_volume_pyramid(f1, f2, 4, prec), 10 if prec != 'fp32' else 3)
                 lay = ops.corr_volume_pyramid(f1, f2, 4, prec).layout

@@ -8,7 +8,7 @@ if len(sys.argv) > 1:
     g = torch.Generator(device=dev).manual_seed(0)
     f1 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
     f2 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
-    for prec in ('tf32', 'bf16'):
+    for prec in ('fp16',):
         fn = lambda: ops.corr_volume_pyramid(f1, f2, 4, prec)
         for _ in range(3): fn()
         torch.cuda.synchronize()
@@ -16,8 +16,9 @@ if len(sys.argv) > 1:
         s.record()
         for _ in range(20): fn()
         e.record(); torch.cuda.synchronize()
-        print(f'debug={os.environ.get("SDOF_TC_DEBUG","0"):>2s} {prec}: {s.elapsed_time(e)/20*1e3:.1f} us', flush=True)
+        print(f'px={os.environ.get("SDOF_RES_PATCHX","-"):>2s} debug={os.environ.get("SDOF_RES_DEBUG","0"):>2s} {prec}: {s.elapsed_time(e)/20*1e3:.1f} us', flush=True)
 else:
-    for dbg in (0, 1, 2, 3, 4, 7, 8, 12, 15):
-        env = dict(os.environ, SDOF_TC_DEBUG=str(dbg))
-        subprocess.run([sys.executable, __file__, 'child'], env=env, timeout=300)
+    for px in (32,):
+        for dbg in (0, 13, 29, 16, 17, 4, 8):
+            env = dict(os.environ, SDOF_RES_DEBUG=str(dbg), SDOF_RES_PATCHX=str(px))
+            subprocess.run([sys.executable, __file__, 'child'], env=env, timeout=300)
