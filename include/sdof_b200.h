@@ -104,6 +104,12 @@ int sdof_corr_pyramid_from_operands(int B, int h1, int w1, int h2, int w2, int C
 int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
                      int radius, float* out, sdof_stream_t stream);
 
+/* Same lookup with channels-last tensors: coords [B,h1,w1,2], out [B,h1,w1,levels*(2r+1)^2] (same channel order).
+ * Used by the NHWC update loop (raft_fast.py) so that the 1x1 convolution convc1 (RAFT/core/update.py:83) reads
+ * it without a layout change.                                                                                  */
+int sdof_corr_lookup_nhwc(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
+                          int radius, float* out, sdof_stream_t stream);
+
 /* ------------------------------------------------------------------------ K1
  * On-the-fly windowed correlation, no volume.  Same contract as the pybind op
  *   alt_cuda_corr.forward(fmap1, fmap2, coords, radius) -> [corr]
@@ -208,6 +214,27 @@ int sdof_confidence_sums(const float* flow_mat, int S, int64_t per_source, doubl
 int sdof_warp_mask_composite(const uint8_t* src, const uint8_t* base, const float* flow, const float* weight_map,
                              int B, int src_batched, int H, int W, float thres, int ksize, uint8_t* out,
                              uint8_t* mask, sdof_stream_t stream);
+
+/* ------------------------------------------------ RAFT update-loop glue
+ * Element-wise steps between the cuDNN convolutions of RAFT's update block (RAFT/core/update.py:79-136) on dense
+ * channels-last buffers [npix, C]; they replace the cat / relu / sigmoid / tanh / mul / add kernels of the eager
+ * reference.  All pointers 16-byte aligned, strides/offsets in floats.
+ *   relu_scatter : dst[:, off : off+C_valid] = relu(src[:, :C_valid]) into one or two (dst2 may be NULL) buffers
+ *   gru_rh       : rhx[:, 0:hidden] = sigmoid(zr[:, hidden:2*hidden]) * h           (update.py:48-49, 55-56)
+ *   gru_update   : h = (1-sigmoid(z))*h + sigmoid(z)*tanh(q), z = zr[:, 0:hidden]; also written to hx[:, 0:hidden]
+ *   flow_update  : coords1 += delta (delta may be NULL); flow = coords1 - pixel grid -> flow [npix,2] and the
+ *                  flow slots of hx / rhx (either may be NULL)                      (raft.py:126-131)
+ *   convex_upsample : RAFT.upsample_flow (raft.py:72-83): mask [B,h,w,576] (times mask_scale), flow [B,h,w,2]
+ *                  -> up [B,8h,8w,2]                                                                           */
+int sdof_relu_scatter(const float* src, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off, float* dst2,
+                      int dst2_stride, int dst2_off, int C_valid, sdof_stream_t stream);
+int sdof_gru_rh(const float* zr, const float* h, float* rhx, int64_t npix, int hidden, int rhx_stride, sdof_stream_t stream);
+int sdof_gru_update(const float* zr, const float* q, float* h, float* hx, int64_t npix, int hidden, int hx_stride,
+                    sdof_stream_t stream);
+int sdof_flow_update(const float* delta, float* coords1, float* flow, float* hx, int hx_stride, int hx_off, float* rhx,
+                     int rhx_stride, int rhx_off, int B, int h, int w, sdof_stream_t stream);
+int sdof_convex_upsample(const float* mask, float mask_scale, const float* flow, int B, int h, int w, float* up,
+                         sdof_stream_t stream);
 
 /* ---------------------------------------------------------------- diagnostics */
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */

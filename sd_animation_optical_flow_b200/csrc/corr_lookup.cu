@@ -50,6 +50,17 @@ __device__ __forceinline__ void blend_window(const float* __restrict__ win, int 
   }
 }
 
+__device__ __forceinline__ void blend_window_strided(const float* __restrict__ win, int D, float fx, float fy,
+                                                     float* __restrict__ dst, int stride, int lane) {
+  const int T1 = D + 1;
+  const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+  for (int k = lane; k < D * D; k += 32) {
+    const int ix = k / D, iy = k - ix * D;
+    const float* q = win + iy * T1 + ix;
+    dst[k * stride] = q[0] * w00 + q[1] * w01 + q[T1] * w10 + q[T1 + 1] * w11;
+  }
+}
+
 // coalesced write-out of the CTA's [channels][32] stage tile
 __device__ __forceinline__ void flush_stage(const float* __restrict__ stage, int channels, float* __restrict__ out,
                                             int64_t out_chan_stride, int p0, int N1) {
@@ -61,7 +72,7 @@ __device__ __forceinline__ void flush_stage(const float* __restrict__ stage, int
 
 template <int R_T, int L_T>
 __global__ void __launch_bounds__(kLookupThreads) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
-                                                                     int N1, int r_rt, float* __restrict__ out) {
+                                                                     int N1, int r_rt, float* __restrict__ out, int nhwc) {
   extern __shared__ __align__(16) float smem[];
   const int r = R_T ? R_T : r_rt;
   const int L = L_T ? L_T : lv.levels;
@@ -74,8 +85,10 @@ __global__ void __launch_bounds__(kLookupThreads) corr_lookup_kernel(LookupLevel
   const int p = p0 + warp;
   float* win = win_all + warp * L * T;
   if (p < N1) {
-    const float cx = coords[((int64_t)b * 2 + 0) * N1 + p];
-    const float cy = coords[((int64_t)b * 2 + 1) * N1 + p];
+    // nhwc: coords [B,h,w,2] and out [B,h,w,CH] (channels-last, for the NHWC update loop); else the
+    // reference's planar layouts coords [B,2,h,w] / out [B,CH,h,w]
+    const float cx = nhwc ? coords[((int64_t)b * N1 + p) * 2] : coords[((int64_t)b * 2 + 0) * N1 + p];
+    const float cy = nhwc ? coords[((int64_t)b * N1 + p) * 2 + 1] : coords[((int64_t)b * 2 + 1) * N1 + p];
     const int64_t row = (int64_t)b * N1 + p;
     float fxs[L_T ? L_T : SDOF_MAX_LEVELS], fys[L_T ? L_T : SDOF_MAX_LEVELS];
     // gather: with compile-time (r, L) every level's loads are issued before any is consumed
@@ -104,9 +117,13 @@ __global__ void __launch_bounds__(kLookupThreads) corr_lookup_kernel(LookupLevel
 #pragma unroll
     for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
       if (l >= L) break;
-      blend_window(win + l * T, D, fxs[l], fys[l], 1.0f, stage + l * DD * kStagePitch + warp, lane);
+      if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
+        blend_window_strided(win + l * T, D, fxs[l], fys[l], out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane);
+      else
+        blend_window(win + l * T, D, fxs[l], fys[l], 1.0f, stage + l * DD * kStagePitch + warp, lane);
     }
   }
+  if (nhwc) return;
   __syncthreads();
   flush_stage(stage, L * DD, out + (int64_t)b * L * DD * N1, N1, p0, N1);
 }
@@ -230,13 +247,13 @@ static int launch_alt_corr(const char* name, const AltCorrArgs& a, int B, cudaSt
 
 extern "C" {
 
-int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
-                     int radius, float* out, sdof_stream_t stream) {
+static int corr_lookup_impl(const char* name, const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2,
+                            int levels, int radius, float* out, int nhwc, sdof_stream_t stream) {
   using namespace sdof;
-  SDOF_REQUIRE(pyramid && coords && out, "sdof_corr_lookup: NULL pointer");
-  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "sdof_corr_lookup: bad sizes");
-  SDOF_REQUIRE(radius >= 0 && radius <= 8, "sdof_corr_lookup: radius must be in [0,8], got %d", radius);
-  SDOF_REQUIRE(B <= 65535, "sdof_corr_lookup: B > 65535 not supported");
+  SDOF_REQUIRE(pyramid && coords && out, "%s: NULL pointer", name);
+  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "%s: bad sizes", name);
+  SDOF_REQUIRE(radius >= 0 && radius <= 8, "%s: radius must be in [0,8], got %d", name, radius);
+  SDOF_REQUIRE(B <= 65535, "%s: B > 65535 not supported", name);
   sdof_pyramid_layout lay;
   const int N1 = h1 * w1;
   int rc = sdof_corr_pyramid_layout((int64_t)B * N1, h2, w2, levels, &lay);
@@ -254,14 +271,13 @@ int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, i
   }
   const int D = 2 * radius + 1, T = (D + 1) * (D + 1), DD = D * D;
   const size_t smem = ((size_t)levels * DD * kStagePitch + (size_t)kLookupPx * levels * T) * sizeof(float);
-  SDOF_REQUIRE(smem <= 200 * 1024, "sdof_corr_lookup: levels=%d radius=%d need %zu bytes of shared memory", levels, radius,
-               smem);
+  SDOF_REQUIRE(smem <= 200 * 1024, "%s: levels=%d radius=%d need %zu bytes of shared memory", name, levels, radius, smem);
   dim3 grid(ceil_div(N1, kLookupPx), B);
   cudaStream_t st = as_stream(stream);
 #define SDOF_LOOKUP_LAUNCH(RT, LT)                                                                                      \
   do {                                                                                                                  \
     SDOF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    corr_lookup_kernel<RT, LT><<<grid, kLookupThreads, smem, st>>>(lv, coords, N1, radius, out);                        \
+    corr_lookup_kernel<RT, LT><<<grid, kLookupThreads, smem, st>>>(lv, coords, N1, radius, out, nhwc);                  \
   } while (0)
   if (radius == 4 && levels == 4)
     SDOF_LOOKUP_LAUNCH(4, 4);
@@ -272,6 +288,16 @@ int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, i
 #undef SDOF_LOOKUP_LAUNCH
   SDOF_LAUNCH_CHECK("corr_lookup_kernel");
   return SDOF_OK;
+}
+
+int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
+                     int radius, float* out, sdof_stream_t stream) {
+  return corr_lookup_impl("sdof_corr_lookup", pyramid, coords, B, h1, w1, h2, w2, levels, radius, out, 0, stream);
+}
+
+int sdof_corr_lookup_nhwc(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
+                          int radius, float* out, sdof_stream_t stream) {
+  return corr_lookup_impl("sdof_corr_lookup_nhwc", pyramid, coords, B, h1, w1, h2, w2, levels, radius, out, 1, stream);
 }
 
 static int check_alt(const char* name, const float* fmap1, const float* fmap2, const float* coords, float* out, int B,

@@ -29,7 +29,8 @@ def warp(img: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: f
 class RaftEngine:
     def __init__(self, checkpoint: str | None = None, iters: int = 20, small: bool = False,
                  corr_precision: str = 'fp16', alternate_corr: bool = False, mixed_precision: bool = False,
-                 channels_last: bool = False, use_cuda_graph: bool = False, device=None, seed: int = 0):
+                 channels_last: bool = False, use_cuda_graph: bool = False, device=None, seed: int = 0,
+                 fast: bool | None = None):
         if not torch.cuda.is_available():
             raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
@@ -48,22 +49,38 @@ class RaftEngine:
         self.channels_last = channels_last
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
+        # the hand-scheduled NHWC forward (raft_fast.py) is the default for the configuration the scripts use
+        if fast is None:
+            fast = not small and not alternate_corr and not mixed_precision and not channels_last
+        self.fast = None
+        if fast:
+            from .raft_fast import FastRaft
+            self.fast = FastRaft(self.model, corr_precision)
 
     def load_checkpoint(self, path: str):
         self.model.load_state_dict(torch.load(path, map_location='cpu'))
         self._graphs.clear()
+        if self.fast is not None:
+            from .raft_fast import FastRaft
+            self.fast = FastRaft(self.model, self.args.corr_precision)
         return self
 
     def to(self, device):
         self.device = torch.device(device)
         self.model = self.model.to(self.device)
         self._graphs.clear()
+        if self.fast is not None:
+            from .raft_fast import FastRaft
+            self.fast = FastRaft(self.model, self.args.corr_precision)
         return self
 
     # ---------------------------------------------------------------- core
     @torch.no_grad()
     def _forward(self, im1: torch.Tensor, im2: torch.Tensor) -> torch.Tensor:
         """padded float images [B,3,H,W] in 0..255 -> flow_up [B,2,H,W]."""
+        if self.fast is not None:
+            _, flow_up = self.fast.forward(im1, im2, self.iters)
+            return flow_up.permute(0, 3, 1, 2)
         if self.channels_last:
             im1 = im1.contiguous(memory_format=torch.channels_last)
             im2 = im2.contiguous(memory_format=torch.channels_last)
@@ -91,7 +108,7 @@ class RaftEngine:
         s1.copy_(im1)
         s2.copy_(im2)
         g.replay()
-        return out
+        return out.clone()  # the graph's output buffer is overwritten by the next replay
 
     @torch.no_grad()
     def estimate_flow(self, img1: torch.Tensor, img2: torch.Tensor, unpad: bool = True) -> torch.Tensor:

@@ -337,3 +337,53 @@ def ellipse_half_widths(ksize: int):
     buf = (ctypes.c_int32 * ksize)()
     check(load().sdof_ellipse_half_widths(ksize, buf), 'sdof_ellipse_half_widths')
     return list(buf)
+
+
+# --------------------------------------------------------------------------- RAFT update-loop glue (NHWC)
+def corr_lookup_nhwc(pyr: CorrPyramid, coords_nhwc: torch.Tensor, radius: int, out: torch.Tensor) -> torch.Tensor:
+    """coords [B,h1,w1,2] -> out [B,h1,w1,levels*(2r+1)^2], channels-last."""
+    check(load().sdof_corr_lookup_nhwc(ptr(pyr.buf), ptr(coords_nhwc), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2, pyr.levels, radius,
+                                       ptr(out), stream_ptr(out.device)), 'sdof_corr_lookup_nhwc')
+    return out
+
+
+def relu_scatter(src: torch.Tensor, dst1: torch.Tensor, off1: int, dst2: torch.Tensor | None = None, off2: int = 0,
+                 c_valid: int | None = None) -> None:
+    """dst[..., off:off+c_valid] = relu(src[..., :c_valid]) for dense channels-last buffers [..., C]."""
+    C = src.shape[-1]
+    npix = src.numel() // C
+    check(load().sdof_relu_scatter(ptr(src), npix, C, ptr(dst1), dst1.shape[-1], off1, ptr(dst2),
+                                   dst2.shape[-1] if dst2 is not None else 0, off2, C if c_valid is None else c_valid,
+                                   stream_ptr(src.device)), 'sdof_relu_scatter')
+
+
+def gru_rh(zr: torch.Tensor, h: torch.Tensor, rhx: torch.Tensor) -> None:
+    hidden = h.shape[-1]
+    check(load().sdof_gru_rh(ptr(zr), ptr(h), ptr(rhx), h.numel() // hidden, hidden, rhx.shape[-1], stream_ptr(h.device)), 'sdof_gru_rh')
+
+
+def gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor, hx: torch.Tensor) -> None:
+    hidden = h.shape[-1]
+    check(load().sdof_gru_update(ptr(zr), ptr(q), ptr(h), ptr(hx), h.numel() // hidden, hidden, hx.shape[-1], stream_ptr(h.device)),
+          'sdof_gru_update')
+
+
+def flow_update(delta: torch.Tensor | None, coords1: torch.Tensor, flow: torch.Tensor, hx: torch.Tensor | None, hx_off: int,
+                rhx: torch.Tensor | None, rhx_off: int) -> None:
+    B, h, w, _ = coords1.shape
+    check(load().sdof_flow_update(ptr(delta), ptr(coords1), ptr(flow), ptr(hx), hx.shape[-1] if hx is not None else 0, hx_off,
+                                  ptr(rhx), rhx.shape[-1] if rhx is not None else 0, rhx_off, B, h, w, stream_ptr(coords1.device)),
+          'sdof_flow_update')
+
+
+def convex_upsample(mask_nhwc: torch.Tensor, flow_nhwc: torch.Tensor, mask_scale: float = 0.25) -> torch.Tensor:
+    """mask [B,h,w,576], flow [B,h,w,2] -> [B,8h,8w,2] (RAFT.upsample_flow, raft.py:72-83)."""
+    require_cuda(mask_nhwc, 'mask', f32)
+    require_cuda(flow_nhwc, 'flow', f32)
+    B, h, w, _ = flow_nhwc.shape
+    if tuple(mask_nhwc.shape) != (B, h, w, 576):
+        raise RuntimeError(f'mask must be {(B, h, w, 576)}, got {tuple(mask_nhwc.shape)}')
+    up = torch.empty((B, 8 * h, 8 * w, 2), dtype=f32, device=flow_nhwc.device)
+    check(load().sdof_convex_upsample(ptr(mask_nhwc), float(mask_scale), ptr(flow_nhwc), B, h, w, ptr(up), stream_ptr(up.device)),
+          'sdof_convex_upsample')
+    return up

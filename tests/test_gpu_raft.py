@@ -46,6 +46,39 @@ def test_flow_matches_reference_raft(cuda, golden, name, mode):
     assert epe.mean() <= 1e-2 and epe.max() <= 1e-1
 
 
+def test_fast_nhwc_forward_equals_module_forward(cuda, golden):
+    """raft_fast.FastRaft (hand-scheduled NHWC loop + glue kernels) against the plain nn.Module forward with the
+    same weights and correlation mode, and against the reference's flow."""
+    cfg = gi.RAFT_CASES['basic']
+    fast = _engine('basic', cuda, corr_precision='3xtf32', fast=True)
+    slow = _engine('basic', cuda, corr_precision='3xtf32', fast=False)
+    assert fast.fast is not None and slow.fast is None
+    img1, img2 = gi.raft_inputs('basic')
+    a = torch.from_numpy(img1).to(cuda)[None]
+    b = torch.from_numpy(img2).to(cuda)[None]
+    f_fast = fast.estimate_flow(a, b, unpad=False)
+    f_slow = slow.estimate_flow(a, b, unpad=False)
+    d = (f_fast - f_slow).norm(dim=-1)
+    print(f'fast vs module: EPE mean {float(d.mean()):.2e} max {float(d.max()):.2e}')
+    assert float(d.mean()) <= 2e-3 and float(d.max()) <= 2e-2
+    epe = _epe(f_fast[0].permute(2, 0, 1).cpu().numpy(), golden['raft']['basic_flow_up'])
+    assert epe.mean() <= 1e-2 and epe.max() <= 1e-1
+    # two pairs at once
+    both = fast.estimate_flow(torch.cat([a, b]), torch.cat([b, a]), unpad=False)
+    assert float((both[:1] - f_fast).abs().max()) <= 2e-3
+
+
+def test_convex_upsample_kernel(cuda):
+    from sd_animation_optical_flow_b200 import ops
+    from sd_animation_optical_flow_b200.raft import convex_upsample
+    g = torch.Generator(device=cuda).manual_seed(3)
+    flow = torch.randn((2, 2, 12, 20), generator=g, device=cuda) * 3
+    mask = torch.randn((2, 576, 12, 20), generator=g, device=cuda) * 2
+    ref = convex_upsample(flow, 0.25 * mask)
+    out = ops.convex_upsample(mask.permute(0, 2, 3, 1).contiguous(), flow.permute(0, 2, 3, 1).contiguous(), 0.25)
+    assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=2e-5, rtol=1e-5)
+
+
 def test_bf16_volume_flow_stays_close(cuda, golden):
     eng = _engine('basic', cuda, corr_precision='bf16')
     img1, img2 = gi.raft_inputs('basic')
