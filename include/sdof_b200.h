@@ -226,15 +226,22 @@ int sdof_warp_mask_composite(const uint8_t* src, const uint8_t* base, const floa
  *                  flow slots of hx / rhx (either may be NULL)                      (raft.py:126-131)
  *   convex_upsample : RAFT.upsample_flow (raft.py:72-83): mask [B,h,w,576] (times mask_scale), flow [B,h,w,2]
  *                  -> up [B,8h,8w,2]                                                                           */
-int sdof_relu_scatter(const float* src, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off, float* dst2,
-                      int dst2_stride, int dst2_off, int C_valid, sdof_stream_t stream);
-int sdof_gru_rh(const float* zr, const float* h, float* rhx, int64_t npix, int hidden, int rhx_stride, sdof_stream_t stream);
-int sdof_gru_update(const float* zr, const float* q, float* h, float* hx, int64_t npix, int hidden, int hx_stride,
-                    sdof_stream_t stream);
-int sdof_flow_update(const float* delta, float* coords1, float* flow, float* hx, int hx_stride, int hx_off, float* rhx,
-                     int rhx_stride, int rhx_off, int B, int h, int w, sdof_stream_t stream);
-int sdof_convex_upsample(const float* mask, float mask_scale, const float* flow, int B, int h, int w, float* up,
-                         sdof_stream_t stream);
+int sdof_relu_scatter(const float* src, const float* bias, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off,
+                      float* dst2, int dst2_stride, int dst2_off, int C_valid, sdof_stream_t stream);
+int sdof_gru_rh(const float* zr, const float* bias_zr, const float* h, float* rhx, int64_t npix, int hidden, int rhx_stride,
+                sdof_stream_t stream);
+int sdof_gru_update(const float* zr, const float* bias_zr, const float* q, const float* bias_q, float* h, float* hx,
+                    int64_t npix, int hidden, int hx_stride, sdof_stream_t stream);
+int sdof_flow_update(const float* delta, float delta_bias_x, float delta_bias_y, float* coords1, float* flow, float* hx,
+                     int hx_stride, int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w,
+                     sdof_stream_t stream);
+int sdof_convex_upsample(const float* mask, const float* mask_bias, float mask_scale, const float* flow, int B, int h, int w,
+                         float* up, sdof_stream_t stream);
+/* The convolution biases (bias*, delta_bias_*, mask_bias; NULL / 0 = none) are added here, so the cuDNN convolutions
+ * run bias-free and no separate bias pass exists.
+ * InstanceNorm2d (no affine, eps) + optional ReLU over `planes` = N*C contiguous planes of hw floats (NCHW), in place
+ * or out of place: relu(norm(conv(x))) of the feature encoder (RAFT/core/extractor.py:49-50, 172-173).            */
+int sdof_instnorm_relu_nchw(const float* x, float* y, int64_t planes, int64_t hw, float eps, int relu, sdof_stream_t stream);
 
 /* ---------------------------------------------------------------- diagnostics */
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */

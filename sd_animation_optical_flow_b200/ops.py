@@ -348,42 +348,56 @@ def corr_lookup_nhwc(pyr: CorrPyramid, coords_nhwc: torch.Tensor, radius: int, o
 
 
 def relu_scatter(src: torch.Tensor, dst1: torch.Tensor, off1: int, dst2: torch.Tensor | None = None, off2: int = 0,
-                 c_valid: int | None = None) -> None:
-    """dst[..., off:off+c_valid] = relu(src[..., :c_valid]) for dense channels-last buffers [..., C]."""
+                 c_valid: int | None = None, bias: torch.Tensor | None = None) -> None:
+    """dst[..., off:off+c_valid] = relu(src[..., :c_valid] + bias) for dense channels-last buffers [..., C]."""
     C = src.shape[-1]
     npix = src.numel() // C
-    check(load().sdof_relu_scatter(ptr(src), npix, C, ptr(dst1), dst1.shape[-1], off1, ptr(dst2),
+    check(load().sdof_relu_scatter(ptr(src), ptr(bias), npix, C, ptr(dst1), dst1.shape[-1], off1, ptr(dst2),
                                    dst2.shape[-1] if dst2 is not None else 0, off2, C if c_valid is None else c_valid,
                                    stream_ptr(src.device)), 'sdof_relu_scatter')
 
 
-def gru_rh(zr: torch.Tensor, h: torch.Tensor, rhx: torch.Tensor) -> None:
+def gru_rh(zr: torch.Tensor, h: torch.Tensor, rhx: torch.Tensor, bias_zr: torch.Tensor | None = None) -> None:
     hidden = h.shape[-1]
-    check(load().sdof_gru_rh(ptr(zr), ptr(h), ptr(rhx), h.numel() // hidden, hidden, rhx.shape[-1], stream_ptr(h.device)), 'sdof_gru_rh')
+    check(load().sdof_gru_rh(ptr(zr), ptr(bias_zr), ptr(h), ptr(rhx), h.numel() // hidden, hidden, rhx.shape[-1],
+                             stream_ptr(h.device)), 'sdof_gru_rh')
 
 
-def gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor, hx: torch.Tensor) -> None:
+def gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor, hx: torch.Tensor, bias_zr: torch.Tensor | None = None,
+               bias_q: torch.Tensor | None = None) -> None:
     hidden = h.shape[-1]
-    check(load().sdof_gru_update(ptr(zr), ptr(q), ptr(h), ptr(hx), h.numel() // hidden, hidden, hx.shape[-1], stream_ptr(h.device)),
-          'sdof_gru_update')
+    check(load().sdof_gru_update(ptr(zr), ptr(bias_zr), ptr(q), ptr(bias_q), ptr(h), ptr(hx), h.numel() // hidden, hidden,
+                                 hx.shape[-1], stream_ptr(h.device)), 'sdof_gru_update')
 
 
 def flow_update(delta: torch.Tensor | None, coords1: torch.Tensor, flow: torch.Tensor, hx: torch.Tensor | None, hx_off: int,
-                rhx: torch.Tensor | None, rhx_off: int) -> None:
+                rhx: torch.Tensor | None, rhx_off: int, delta_bias=(0.0, 0.0)) -> None:
     B, h, w, _ = coords1.shape
-    check(load().sdof_flow_update(ptr(delta), ptr(coords1), ptr(flow), ptr(hx), hx.shape[-1] if hx is not None else 0, hx_off,
-                                  ptr(rhx), rhx.shape[-1] if rhx is not None else 0, rhx_off, B, h, w, stream_ptr(coords1.device)),
+    check(load().sdof_flow_update(ptr(delta), float(delta_bias[0]), float(delta_bias[1]), ptr(coords1), ptr(flow), ptr(hx),
+                                  hx.shape[-1] if hx is not None else 0, hx_off, ptr(rhx),
+                                  rhx.shape[-1] if rhx is not None else 0, rhx_off, B, h, w, stream_ptr(coords1.device)),
           'sdof_flow_update')
 
 
-def convex_upsample(mask_nhwc: torch.Tensor, flow_nhwc: torch.Tensor, mask_scale: float = 0.25) -> torch.Tensor:
-    """mask [B,h,w,576], flow [B,h,w,2] -> [B,8h,8w,2] (RAFT.upsample_flow, raft.py:72-83)."""
+def convex_upsample(mask_nhwc: torch.Tensor, flow_nhwc: torch.Tensor, mask_scale: float = 0.25,
+                    mask_bias: torch.Tensor | None = None) -> torch.Tensor:
+    """mask [B,h,w,576] (+ bias[576]), flow [B,h,w,2] -> [B,8h,8w,2] (RAFT.upsample_flow, raft.py:72-83)."""
     require_cuda(mask_nhwc, 'mask', f32)
     require_cuda(flow_nhwc, 'flow', f32)
     B, h, w, _ = flow_nhwc.shape
     if tuple(mask_nhwc.shape) != (B, h, w, 576):
         raise RuntimeError(f'mask must be {(B, h, w, 576)}, got {tuple(mask_nhwc.shape)}')
     up = torch.empty((B, 8 * h, 8 * w, 2), dtype=f32, device=flow_nhwc.device)
-    check(load().sdof_convex_upsample(ptr(mask_nhwc), float(mask_scale), ptr(flow_nhwc), B, h, w, ptr(up), stream_ptr(up.device)),
-          'sdof_convex_upsample')
+    check(load().sdof_convex_upsample(ptr(mask_nhwc), ptr(mask_bias), float(mask_scale), ptr(flow_nhwc), B, h, w, ptr(up),
+                                      stream_ptr(up.device)), 'sdof_convex_upsample')
     return up
+
+
+def instnorm_relu(x: torch.Tensor, relu: bool = True, eps: float = 1e-5, inplace: bool = True) -> torch.Tensor:
+    """InstanceNorm2d(no affine) + optional ReLU on a contiguous NCHW tensor."""
+    require_cuda(x, 'x', f32)
+    N, C, H, W = x.shape
+    y = x if inplace else torch.empty_like(x)
+    check(load().sdof_instnorm_relu_nchw(ptr(x), ptr(y), N * C, H * W, float(eps), int(relu), stream_ptr(x.device)),
+          'sdof_instnorm_relu_nchw')
+    return y

@@ -33,6 +33,69 @@ def _w(conv, pad_out_to: int | None = None):
     return w.contiguous(memory_format=CL), b.contiguous(), conv.padding
 
 
+def _fold_bn(conv, bn):
+    """Inference BatchNorm folded into the preceding convolution (exact algebra):
+    w' = w * g / sqrt(var + eps),  b' = (b - mean) * g / sqrt(var + eps) + beta."""
+    w, b = conv.weight.detach(), conv.bias.detach()
+    if isinstance(bn, torch.nn.BatchNorm2d):
+        k = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+        w = w * k.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach()) * k + bn.bias.detach()
+    return w.contiguous(), b.contiguous()
+
+
+class FastEncoder:
+    """Inference forward of raft.Encoder (basic model; RAFT/core/extractor.py:118-192) with the normalisation
+    collapsed: BatchNorm (cnet) folded into the conv weights with the ReLU fused by cuDNN, InstanceNorm (fnet)
+    + ReLU as ONE kernel per layer (csrc/raft_glue.cu) instead of four."""
+
+    def __init__(self, enc):
+        self.kind = enc.norm_fn
+        if self.kind not in ('instance', 'batch', 'none'):
+            raise ValueError(f'unsupported norm {self.kind}')
+        self.stem = self._layer(enc.conv1, enc.norm1)
+        self.units = []
+        for layer in (enc.layer1, enc.layer2, enc.layer3):
+            for u in layer:
+                ds = self._layer(u.downsample[0], u.downsample[1]) if u.downsample is not None else None
+                self.units.append((self._layer(u.conv1, u.norm1), self._layer(u.conv2, u.norm2), ds))
+        self.out = (enc.conv2.weight.detach(), enc.conv2.bias.detach(), enc.conv2.stride, enc.conv2.padding)
+        self._fused_ok = None
+
+    def _layer(self, conv, norm):
+        w, b = _fold_bn(conv, norm)
+        return (w, b, conv.stride, conv.padding)
+
+    def _cnr(self, x, layer, relu: bool):
+        w, b, stride, pad = layer
+        if self.kind == 'instance':
+            return ops.instnorm_relu(F.conv2d(x, w, b, stride=stride, padding=pad), relu=relu)
+        if relu:
+            if self._fused_ok is not False:
+                try:
+                    y = torch.cudnn_convolution_relu(x, w, b, tuple(stride), tuple(pad), (1, 1), 1)
+                    if self._fused_ok is None:
+                        ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=pad))
+                        self._fused_ok = bool(torch.allclose(y, ref, atol=1e-3, rtol=1e-3))
+                        if not self._fused_ok:
+                            return ref
+                    return y
+                except RuntimeError:
+                    self._fused_ok = False
+            return F.relu_(F.conv2d(x, w, b, stride=stride, padding=pad))
+        return F.conv2d(x, w, b, stride=stride, padding=pad)
+
+    def __call__(self, x):
+        x = self._cnr(x, self.stem, True)
+        for c1, c2, ds in self.units:
+            y = self._cnr(self._cnr(x, c1, True), c2, True)
+            if ds is not None:
+                x = self._cnr(x, ds, False)
+            x = torch.relu_(x + y)
+        w, b, stride, pad = self.out
+        return F.conv2d(x, w, b, stride=stride, padding=pad)
+
+
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16'):
         if model.small:
@@ -52,15 +115,20 @@ class FastRaft:
             self.zr.append((wzr, bzr, cz.padding))
             self.q.append(_w(cq))
         self.fh1, self.fh2 = _w(fh.conv1), _w(fh.conv2)
+        self._fh2_bias = tuple(float(v) for v in fh.conv2.bias.detach().cpu().tolist())
         self.mask0, self.mask2 = _w(ub.mask[0]), _w(ub.mask[2])
         self.hidden = model.hidden_dim
         self._fused_relu_ok = None
+        self.fnet = FastEncoder(model.fnet)
+        self.cnet = FastEncoder(model.cnet)
 
     # ---- cuDNN convolutions on dense NHWC buffers ---------------------------------------------------
     @staticmethod
-    def _conv(x_nhwc: torch.Tensor, wbp) -> torch.Tensor:
+    def _conv(x_nhwc: torch.Tensor, wbp, bias: bool = False) -> torch.Tensor:
+        """cuDNN convolution on a dense NHWC buffer.  By default WITHOUT the bias: the consumer glue kernel adds it
+        (a separate strided bias pass costs as much as the convolution at this size)."""
         w, b, pad = wbp
-        y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), w, b, padding=pad)
+        y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), w, b if bias else None, padding=pad)
         if not y.is_contiguous(memory_format=CL):
             y = y.contiguous(memory_format=CL)
         return y.permute(0, 2, 3, 1)
@@ -91,9 +159,10 @@ class FastRaft:
         m = self.model
         im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
-        fmap1, fmap2 = m.fnet([im1, im2])
-        pyr = ops.corr_volume_pyramid(_to_nhwc(fmap1), _to_nhwc(fmap2), 4, self.corr_precision)
-        cnet = m.cnet(im1)
+        n = im1.shape[0]
+        fmaps = self.fnet(torch.cat([im1, im2], 0))
+        pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps[:n]), _to_nhwc(fmaps[n:]), 4, self.corr_precision)
+        cnet = self.cnet(im1)
         B, _, h, w = cnet.shape
         hd = self.hidden
         dev = cnet.device
@@ -117,17 +186,17 @@ class FastRaft:
         for _ in range(iters):
             ops.corr_lookup_nhwc(pyr, coords1, 4, corr)
             c2 = self._conv(self._conv_relu(corr, self.convc1), self.convc2)
-            ops.relu_scatter(c2, CF, 0)
+            ops.relu_scatter(c2, CF, 0, bias=self.convc2[1])
             f2 = self._conv(self._conv_relu(flow, self.convf1), self.convf2)
-            ops.relu_scatter(f2, CF, 192)
+            ops.relu_scatter(f2, CF, 192, bias=self.convf2[1])
             mot = self._conv(CF, self.conv)                               # 126 (+2 zero) channels
-            ops.relu_scatter(mot, HX, mo, RHX, mo, c_valid=126)
+            ops.relu_scatter(mot, HX, mo, RHX, mo, c_valid=126, bias=self.conv[1])
             for p in (0, 1):                                              # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
                 zr = self._conv(HX, self.zr[p])
-                ops.gru_rh(zr, H, RHX)
+                ops.gru_rh(zr, H, RHX, bias_zr=self.zr[p][1])
                 q = self._conv(RHX, self.q[p])
-                ops.gru_update(zr, q, H, HX)
+                ops.gru_update(zr, q, H, HX, bias_zr=self.zr[p][1], bias_q=self.q[p][1])
             delta = self._conv(self._conv_relu(H, self.fh1), self.fh2)
-            ops.flow_update(delta.contiguous(), coords1, flow, HX, fo, RHX, fo)
+            ops.flow_update(delta.contiguous(), coords1, flow, HX, fo, RHX, fo, delta_bias=self._fh2_bias)
         mask = self._conv(self._conv_relu(H, self.mask0), self.mask2)
-        return flow, ops.convex_upsample(mask.contiguous(), flow, 0.25)
+        return flow, ops.convex_upsample(mask.contiguous(), flow, 0.25, mask_bias=self.mask2[1])

@@ -68,6 +68,16 @@ def test_fast_nhwc_forward_equals_module_forward(cuda, golden):
     assert float((both[:1] - f_fast).abs().max()) <= 2e-3
 
 
+def test_instnorm_relu_kernel(cuda):
+    from sd_animation_optical_flow_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(4)
+    for shape in ((2, 8, 37, 41), (1, 64, 96, 64), (2, 3, 5, 3)):
+        x = torch.randn(shape, generator=g, device=cuda) * 3 + 1.5
+        ref = torch.nn.functional.instance_norm(x, eps=1e-5)
+        assert torch.allclose(ops.instnorm_relu(x.clone(), relu=False), ref, atol=2e-5, rtol=1e-5)
+        assert torch.allclose(ops.instnorm_relu(x, relu=True, inplace=False), torch.relu(ref), atol=2e-5, rtol=1e-5)
+
+
 def test_convex_upsample_kernel(cuda):
     from sd_animation_optical_flow_b200 import ops
     from sd_animation_optical_flow_b200.raft import convex_upsample
