@@ -227,7 +227,9 @@ def run_ours(args):
     # ---- e2e: the reference-facing numpy API with HOST buffers (H2D / D2H inside the timed region)
     algo = ofgen.RAFT_2.__new__(ofgen.RAFT_2)
     algo.engine = eng
-    bgr1, bgr2, bgrs = f1[:, :, ::-1].copy(), f2[:, :, ::-1].copy(), sty[:, :, ::-1].copy()
+    # host buffers live in pinned memory (numpy views of pinned tensors), as the contract asks
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    bgr1, bgr2, bgrs = pin(f1[:, :, ::-1]), pin(f2[:, :, ::-1]), pin(sty[:, :, ::-1])
 
     def e2e_step():
         flow = algo.calc(bgr1, bgr2)                      # H2D 2 frames, D2H flow
@@ -295,7 +297,9 @@ def run_ours(args):
     hbm = peaks['hbm_gbs']
     corr_gbs = (in_bytes + out_bytes) / t_corr / 1e9
     roofline = {'kernel': corr_kernel + ', 1 pair, N=6144, C=256, 4 levels', 'us_per_op_with_prepass': t_corr_op * 1e6, 'bound': 'hbm',
-                'achieved': corr_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': corr_gbs / hbm, 'traffic': None,
+                'achieved': corr_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': corr_gbs / hbm,
+                'traffic': 151629824 if args.corr_precision == 'fp16' else None,
+                'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_kernels_ncu_summary.txt); below the algorithmic bytes because part of the 200 MB pyramid is still dirty in the 126 MB L2 when the kernel ends',
                 'peak_source': peaks['source'], 'us_per_launch': t_corr * 1e6,
                 'algorithmic_bytes': in_bytes + out_bytes}
     tf = corr_flops / t_corr / 1e12

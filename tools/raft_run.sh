@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "=== pytest raft"; timeout 900 python -m pytest tests/test_gpu_raft.py tests/test_gpu_corr.py -m gpu -q -x --timeout 300 -p no:cacheprovider -s > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; grep -E "EPE|passed|failed|Error" gpurun_out/pytest.log | tail -30
 echo "=== raft perf"; timeout 600 python - <<'PY'
 import sys, time, torch
 sys.path.insert(0, '.')
@@ -14,8 +13,10 @@ def timeit(fn, n=5):
     for _ in range(n): fn()
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
-for kw in (dict(fast=False, use_cuda_graph=True), dict(fast=True), dict(fast=True, use_cuda_graph=True)):
+for bench_mode in (False, True):
+  torch.backends.cudnn.benchmark = bench_mode
+  for kw in (dict(fast=True, use_cuda_graph=True),):
     eng = RaftEngine(iters=20, device=dev, **kw)
     eng.estimate_flow(img, img.flip(1)); torch.cuda.synchronize()
-    print(kw, f'{timeit(lambda: eng.estimate_flow(img, img.flip(1))):.2f} ms/pair', 'fused conv+relu:', getattr(eng.fast, '_fused_relu_ok', None) if eng.fast else None, flush=True)
+    print('cudnn.benchmark', bench_mode, kw, f'{timeit(lambda: eng.estimate_flow(img, img.flip(1))):.2f} ms/pair', 'fused conv+relu:', getattr(eng.fast, '_fused_relu_ok', None) if eng.fast else None, flush=True)
 PY
