@@ -8,7 +8,7 @@
 // dp2a, so the LSU/ALU cost per pixel stays close to the HBM time.
 #include <mutex>
 
-#include "warp.cuh"
+#include "warp_tiled.cuh"
 
 namespace sdof {
 
@@ -33,70 +33,75 @@ int get_cubic_tables(CubicTables* out) {
 }
 
 // ---------------------------------------------------------------- cubic, u8, C = 3
-// grid-stride over groups of 4 pixels of the flattened [B*H*W] output.
-__global__ void __launch_bounds__(256) warp_cubic_u8c3_kernel(const int16_t* __restrict__ tab,
-                                                              const unsigned char* __restrict__ src,
-                                                              const float* __restrict__ flow,
-                                                              unsigned char* __restrict__ dst, int B, int Hs, int Ws,
-                                                              int H, int W, int64_t src_bstride, float sign,
-                                                              const unsigned char* __restrict__ src_end,
-                                                              int dst_vec_ok) {
-  const int64_t npix = (int64_t)B * H * W;
-  const int64_t ngroups = (npix + 3) >> 2;
-  const int64_t hw = (int64_t)H * W;
-  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p0 = g << 2;
-    float fl[8];
-    if (p0 + 4 <= npix) {
-      const float4 f0 = __ldcs(reinterpret_cast<const float4*>(flow + p0 * 2));
-      const float4 f1 = __ldcs(reinterpret_cast<const float4*>(flow + p0 * 2) + 1);
-      fl[0] = f0.x; fl[1] = f0.y; fl[2] = f0.z; fl[3] = f0.w;
-      fl[4] = f1.x; fl[5] = f1.y; fl[6] = f1.z; fl[7] = f1.w;
-    } else {
+// per-pixel global-memory path for tiles whose source rectangle does not fit shared memory; kept out of
+// line so the staged path's register allocation is not shaped by it
+__device__ __noinline__ unsigned cubic_u8_c3_outlined(const int16_t* __restrict__ tab, const unsigned char* __restrict__ img,
+                                                      const unsigned char* __restrict__ buf_end, int Hs, int Ws, int sx,
+                                                      int sy, int fidx) {
+  FixedCoord fc;
+  fc.sx = sx;
+  fc.sy = sy;
+  fc.fidx = fidx;
+  return cubic_u8_c3(tab, img, buf_end, Hs, Ws, fc);
+}
+
+// Persistent CTAs (one per SM, 4 groups of 256 threads); a group walks 32x32 output tiles
+// (warp_tiled.cuh).  `old_src_end` is the bound of the per-pixel fallback path (cubic_u8_c3).
+__global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
+    const int16_t* __restrict__ tab, const unsigned char* __restrict__ src, const float* __restrict__ flow,
+    unsigned char* __restrict__ dst, int B, int Hs, int Ws, int H, int W, int64_t src_bstride, float sign,
+    const unsigned char* __restrict__ src_lo, const unsigned char* __restrict__ src_hi,
+    const unsigned char* __restrict__ old_src_end, int dst_vec_ok) {
+  extern __shared__ __align__(16) unsigned char wt_smem_raw[];
+  WtSmem& S = *reinterpret_cast<WtSmem*>(wt_smem_raw);
+  wt_load_table(S, tab);
+  __syncthreads();
+  const int grp = threadIdx.x >> 8, gt = threadIdx.x & 255, gw = gt >> 5, lane = gt & 31;
+  uint2* region = S.region[grp];
+  const int tilesX = (W + kWtTile - 1) / kWtTile, tilesY = (H + kWtTile - 1) / kWtTile;
+  const int64_t tiles_per_img = (int64_t)tilesX * tilesY;
+  const int64_t ntiles = tiles_per_img * B;
+  for (int64_t t = (int64_t)blockIdx.x * kWtGroups + grp; t < ntiles; t += (int64_t)gridDim.x * kWtGroups) {
+    const int b = (int)(t / tiles_per_img);
+    const int rem = (int)(t - (int64_t)b * tiles_per_img);
+    const int tyi = rem / tilesX, txi = rem - tyi * tilesX;
+    const int gx = txi * kWtTile + lane;
+    const int gy0 = tyi * kWtTile + gw * 4;
+    const int64_t row0 = ((int64_t)b * H + gy0) * W;  // flat pixel index of (b, gy0, 0)
+    // ---- A: flow -> quantised coordinates
+    float2 f[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool ok = p0 + i < npix;
-        fl[2 * i] = ok ? flow[(p0 + i) * 2] : 0.f;
-        fl[2 * i + 1] = ok ? flow[(p0 + i) * 2 + 1] : 0.f;
-      }
+    for (int k = 0; k < 4; ++k) {
+      f[k] = make_float2(0.f, 0.f);
+      if (gx < W && gy0 + k < H) f[k] = __ldcs(reinterpret_cast<const float2*>(flow) + row0 + (int64_t)k * W + gx);
     }
-    unsigned px[4];
-    int b, y, x;
-    decompose_pixel(p0, hw, W, b, y, x);
+    WtPixels px;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (p0 + i < npix) {
-        const FixedCoord fc = fixed_coord(map_coord(x, fl[2 * i], sign), map_coord(y, fl[2 * i + 1], sign));
-        px[i] = cubic_u8_c3(tab, src + b * src_bstride, src_end, Hs, Ws, fc);
-      } else {
-        px[i] = 0;
-      }
-      if (++x == W) {
-        x = 0;
-        if (++y == H) {
-          y = 0;
-          ++b;
+    for (int k = 0; k < 4; ++k) {
+      const FixedCoord fc = fixed_coord(map_coord(gx, f[k].x, sign), map_coord(gy0 + k, f[k].y, sign));
+      px.sx[k] = fc.sx;
+      px.sy[k] = fc.sy;
+      px.fid[k] = (gx < W && gy0 + k < H) ? fc.fidx : -1;
+    }
+    const WtRegion R = wt_bbox(S, grp, gw, lane, px);
+    // ---- B: stage the source rectangle
+    const unsigned char* img = src + b * src_bstride;
+    wt_stage(region, R, img, Hs, Ws, src_lo, src_hi, gt, grp);
+    // ---- C: taps from shared memory, packed row stores
+    const bool seg_full = dst_vec_ok && (txi * kWtTile + kWtTile <= W);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (gy0 + k >= H) break;  // warp-uniform
+      unsigned v = 0;
+      if (px.fid[k] >= 0) {
+        if (R.staged) {
+          v = wt_pixel(S, region, R, px.sx[k], px.sy[k], px.fid[k]);
+        } else {
+          v = cubic_u8_c3_outlined(tab, img, old_src_end, Hs, Ws, px.sx[k], px.sy[k], px.fid[k]);
         }
       }
-    }
-    if (dst_vec_ok && p0 + 4 <= npix) {
-      // 4 pixels x 3 bytes = three aligned words
-      const unsigned w0 = px[0] | (px[1] << 24);
-      const unsigned w1 = (px[1] >> 8) | (px[2] << 16);
-      const unsigned w2 = (px[2] >> 16) | (px[3] << 8);
-      unsigned* o = reinterpret_cast<unsigned*>(dst + p0 * 3);
-      __stcs(o, w0);
-      __stcs(o + 1, w1);
-      __stcs(o + 2, w2);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (p0 + i < npix) {
-          unsigned char* o = dst + (p0 + i) * 3;
-          o[0] = (unsigned char)(px[i] & 0xff);
-          o[1] = (unsigned char)((px[i] >> 8) & 0xff);
-          o[2] = (unsigned char)((px[i] >> 16) & 0xff);
-        }
+      unsigned char* o = dst + (row0 + (int64_t)k * W + txi * kWtTile) * 3;
+      wt_store_row(o, v, lane, seg_full, px.fid[k] >= 0);
     }
   }
 }
@@ -231,19 +236,28 @@ int sdof_warp_cubic_u8(const uint8_t* src, const float* flow, int B, int src_bat
   if (B == 0) return SDOF_OK;
   CubicTables tabs;
   if ((rc = get_cubic_tables(&tabs))) return rc;
-  const int64_t npix = (int64_t)B * H * W;
   const int64_t img_bytes = (int64_t)Hs * Ws * 3;
   const int64_t bstride = src_batched ? img_bytes : 0;
-  // word-aligned fast path needs a 4-byte aligned source; otherwise force the tap loop
+  const uint8_t* src_hi = src + (src_batched ? (int64_t)B : 1) * img_bytes;
+  // per-pixel fallback path: its word loads assume a 4-byte aligned source; otherwise it takes the tap loop
   const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 3) == 0;
-  const uint8_t* src_end = src_aligned ? src + (src_batched ? (int64_t)B : 1) * img_bytes : src;
-  const int flow_vec = (reinterpret_cast<uintptr_t>(flow) & 15) == 0;
-  if (!flow_vec) return fail(SDOF_ERR_INVALID, "sdof_warp_cubic_u8: flow must be 16-byte aligned");
-  const int dst_vec = (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
-  const int64_t ngroups = (npix + 3) / 4;
-  warp_cubic_u8c3_kernel<<<grid_for(ngroups, 256, 8), 256, 0, as_stream(stream)>>>(tabs.i16, src, flow, dst, B, Hs, Ws, H, W,
-                                                                                    bstride, sign, src_end, dst_vec);
-  SDOF_LAUNCH_CHECK("warp_cubic_u8c3_kernel");
+  const uint8_t* old_src_end = src_aligned ? src_hi : src;
+  // packed 96-byte row stores need every 32-pixel segment word-aligned
+  const int dst_vec = (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (W & 3) == 0;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  SDOF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    SDOF_CUDA(cudaFuncSetAttribute(warp_cubic_u8c3_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(WtSmem)));
+    attr_set[dev] = true;
+  }
+  const int64_t ntiles = (int64_t)ceil_div(W, kWtTile) * ceil_div(H, kWtTile) * B;
+  const int64_t want = ceil_div64(ntiles, kWtGroups);
+  const int grid = (int)(want < sm_count() ? want : sm_count());
+  warp_cubic_u8c3_tiled_kernel<<<grid, kWtThreads, sizeof(WtSmem), as_stream(stream)>>>(
+      tabs.i16, src, flow, dst, B, Hs, Ws, H, W, bstride, sign, src, src_hi, old_src_end, dst_vec);
+  SDOF_LAUNCH_CHECK("warp_cubic_u8c3_tiled_kernel");
   return SDOF_OK;
 }
 
