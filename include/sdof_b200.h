@@ -242,6 +242,26 @@ int sdof_convex_upsample(const float* mask, const float* mask_bias, float mask_s
  * InstanceNorm2d (no affine, eps) + optional ReLU over `planes` = N*C contiguous planes of hw floats (NCHW), in place
  * or out of place: relu(norm(conv(x))) of the feature encoder (RAFT/core/extractor.py:49-50, 172-173).            */
 int sdof_instnorm_relu_nchw(const float* x, float* y, int64_t planes, int64_t hw, float eps, int relu, sdof_stream_t stream);
+/* Channels-last (NHWC) form of the same layer, so the encoder convolutions run without layout transposes:
+ *   stats [N][C][2] fp64 (sum, sum of squares over the hw pixels of each image and channel), ZEROED by the caller;
+ *   apply: y = relu?((x - mean) * rsqrt(var + eps)); with `residual` != NULL additionally y = relu(residual + y),
+ *   the tail of ResidualBlock.forward (RAFT/core/extractor.py:49-58).  x, y, residual: dense [N, hw, C], C % 4 == 0.
+ *   sdof_add_relu: y = relu(a + b) over n floats (the same tail for cnet, whose BatchNorm is folded into the convs). */
+int sdof_instnorm_stats_nhwc(const float* x, int N, int64_t hw, int C, double* stats, sdof_stream_t stream);
+int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* residual, float* y, int N, int64_t hw, int C,
+                             float eps, int relu, sdof_stream_t stream);
+int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stream_t stream);
+/* The two convolutions of the update block that are too small / too thin for a tensor-core library kernel:
+ *   sdof_conv7x7_c2_relu : BasicMotionEncoder.convf1 (RAFT/core/update.py:85,93): out[B,h,w,128] =
+ *                          relu(conv7x7(flow[B,h,w,2], pad 3) + bias); wT = weight[128,2,7,7] permuted to [7,7,2,128].
+ *   sdof_flowhead2_update: FlowHead.conv2 (update.py:10,14) + the coords update of RAFT.forward (raft.py:128-131):
+ *                          delta = conv3x3(x[B,h,w,256], pad 1) + bias; coords1 += delta; flow = coords1 - grid, written to
+ *                          `flow` and the flow slots of hx / rhx like sdof_flow_update; w2 = weight[2,256,3,3] permuted
+ *                          to [3,3,2,256].  fp32 FMA accumulation. */
+int sdof_conv7x7_c2_relu(const float* flow, const float* wT, const float* bias, float* out, int B, int h, int w, sdof_stream_t stream);
+int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float bias_y, float* coords1, float* flow, float* hx,
+                          int hx_stride, int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w,
+                          sdof_stream_t stream);
 
 /* ---------------------------------------------------------------- diagnostics */
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */

@@ -298,3 +298,329 @@ int sdof_convex_upsample(const float* mask, const float* mask_bias, float mask_s
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Channels-last feature encoders (RAFT/core/extractor.py:118-192).  Eager PyTorch / cuDNN wrap every NCHW
+// convolution of the encoders in an NCHW->NHWC and an NHWC->NCHW transpose (round-1 launch list: 0.86 ms of a
+// 5.9 ms step); with the activations kept NHWC the tensor-core convolutions run directly, and the
+// normalisation between them is the three kernels below.
+//
+//   instnorm_stats_nhwc : per (image, channel) sum and sum of squares over H*W, fp32 partials per thread,
+//                         fp64 atomics into stats[N][C][2] (zeroed by the caller)
+//   instnorm_apply_nhwc : y = relu?((x - mean) * rsqrt(var + eps)), optionally followed by the residual
+//                         y = relu(res + y) of the ResidualBlock (extractor.py:49-58)
+//   add_relu            : y = relu(a + b)   (cnet, whose BatchNorm is folded into the convolutions)
+namespace sdof {
+
+constexpr int kInThreads = 256;
+
+__global__ void __launch_bounds__(kInThreads) instnorm_stats_nhwc_kernel(const float4* __restrict__ x, double* __restrict__ stats,
+                                                                        int64_t hw, int C4, int px_per_cta) {
+  __shared__ float4 red_s[kInThreads], red_q[kInThreads];
+  const int n = blockIdx.y;
+  const int npl = kInThreads / C4;          // pixel lanes
+  const int T = npl * C4;                   // active threads (a multiple of C4, so a thread keeps its channel quad)
+  const int64_t p0 = (int64_t)blockIdx.x * px_per_cta;
+  const int64_t p1 = p0 + px_per_cta < hw ? p0 + px_per_cta : hw;
+  const float4* xs = x + ((int64_t)n * hw + p0) * C4;
+  const int64_t cnt = (p1 - p0) * C4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if ((int)threadIdx.x < T)
+    for (int64_t i = threadIdx.x; i < cnt; i += T) {
+      const float4 v = xs[i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+    }
+  red_s[threadIdx.x] = s;
+  red_q[threadIdx.x] = q;
+  __syncthreads();
+  if ((int)threadIdx.x < C4) {
+    for (int l = 1; l < npl; ++l) {
+      const float4 a = red_s[l * C4 + threadIdx.x], b = red_q[l * C4 + threadIdx.x];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+    }
+    double* o = stats + ((int64_t)n * C4 + threadIdx.x) * 8;   // [c][2] for 4 channels
+    atomicAdd(o + 0, (double)s.x); atomicAdd(o + 1, (double)q.x);
+    atomicAdd(o + 2, (double)s.y); atomicAdd(o + 3, (double)q.y);
+    atomicAdd(o + 4, (double)s.z); atomicAdd(o + 5, (double)q.z);
+    atomicAdd(o + 6, (double)s.w); atomicAdd(o + 7, (double)q.w);
+  }
+}
+
+__global__ void __launch_bounds__(kInThreads) instnorm_apply_nhwc_kernel(const float4* __restrict__ x, const double* __restrict__ stats,
+                                                                        const float4* __restrict__ res, float4* __restrict__ y,
+                                                                        int64_t hw, int C4, int px_per_cta, float eps, int relu) {
+  __shared__ float mean_s[512], rstd_s[512];
+  const int n = blockIdx.y;
+  const int C = C4 * 4;
+  for (int c = threadIdx.x; c < C; c += kInThreads) {
+    const double s = stats[((int64_t)n * C + c) * 2], q = stats[((int64_t)n * C + c) * 2 + 1];
+    const double m = s / (double)hw;
+    double var = q / (double)hw - m * m;
+    if (var < 0.0) var = 0.0;
+    mean_s[c] = (float)m;
+    rstd_s[c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int npl = kInThreads / C4;
+  const int T = npl * C4;
+  if ((int)threadIdx.x >= T) return;
+  const int cq = threadIdx.x % C4;
+  const float4 m = *reinterpret_cast<const float4*>(mean_s + 4 * cq);
+  const float4 r = *reinterpret_cast<const float4*>(rstd_s + 4 * cq);
+  const int64_t p0 = (int64_t)blockIdx.x * px_per_cta;
+  const int64_t p1 = p0 + px_per_cta < hw ? p0 + px_per_cta : hw;
+  const int64_t base = ((int64_t)n * hw + p0) * C4;
+  const int64_t cnt = (p1 - p0) * C4;
+  for (int64_t i = threadIdx.x; i < cnt; i += T) {
+    const float4 v = x[base + i];
+    float4 o;
+    o.x = (v.x - m.x) * r.x; o.y = (v.y - m.y) * r.y; o.z = (v.z - m.z) * r.z; o.w = (v.w - m.w) * r.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (res) {
+      const float4 a = res[base + i];
+      o.x = fmaxf(a.x + o.x, 0.f); o.y = fmaxf(a.y + o.y, 0.f); o.z = fmaxf(a.z + o.z, 0.f); o.w = fmaxf(a.w + o.w, 0.f);
+    }
+    y[base + i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) add_relu_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y,
+                                                       int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 u = a[i], v = b[i];
+    y[i] = make_float4(fmaxf(u.x + v.x, 0.f), fmaxf(u.y + v.y, 0.f), fmaxf(u.z + v.z, 0.f), fmaxf(u.w + v.w, 0.f));
+  }
+}
+
+static int instnorm_px_per_cta(int N, int64_t hw) {
+  // ~4 CTAs per SM over the whole tensor, at least 64 pixels each
+  int64_t want = ((int64_t)N * hw) / ((int64_t)sm_count() * 4);
+  if (want < 64) want = 64;
+  if (want > 4096) want = 4096;
+  return (int)want;
+}
+
+}  // namespace sdof
+
+extern "C" {
+
+int sdof_instnorm_stats_nhwc(const float* x, int N, int64_t hw, int C, double* stats, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(x && stats, "sdof_instnorm_stats_nhwc: NULL pointer");
+  SDOF_REQUIRE(N >= 0 && N <= 65535 && hw >= 1 && C >= 4 && C % 4 == 0 && C <= 512, "sdof_instnorm_stats_nhwc: need C %% 4 == 0, 4 <= C <= 512");
+  SDOF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sdof_instnorm_stats_nhwc: x must be 16-byte aligned");
+  if (N == 0) return SDOF_OK;
+  const int ppc = instnorm_px_per_cta(N, hw);
+  dim3 grid((unsigned)ceil_div64(hw, ppc), N);
+  instnorm_stats_nhwc_kernel<<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), stats, hw, C / 4, ppc);
+  SDOF_LAUNCH_CHECK("instnorm_stats_nhwc_kernel");
+  return SDOF_OK;
+}
+
+int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* residual, float* y, int N, int64_t hw, int C, float eps,
+                             int relu, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(x && stats && y, "sdof_instnorm_apply_nhwc: NULL pointer");
+  SDOF_REQUIRE(N >= 0 && N <= 65535 && hw >= 1 && C >= 4 && C % 4 == 0 && C <= 512, "sdof_instnorm_apply_nhwc: need C %% 4 == 0, 4 <= C <= 512");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0,
+               "sdof_instnorm_apply_nhwc: pointers must be 16-byte aligned");
+  if (N == 0) return SDOF_OK;
+  const int ppc = instnorm_px_per_cta(N, hw);
+  dim3 grid((unsigned)ceil_div64(hw, ppc), N);
+  instnorm_apply_nhwc_kernel<<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), stats,
+                                                                        reinterpret_cast<const float4*>(residual),
+                                                                        reinterpret_cast<float4*>(y), hw, C / 4, ppc, eps, relu);
+  SDOF_LAUNCH_CHECK("instnorm_apply_nhwc_kernel");
+  return SDOF_OK;
+}
+
+int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(a && b && y, "sdof_add_relu: NULL pointer");
+  SDOF_REQUIRE(n >= 0 && n % 4 == 0, "sdof_add_relu: n must be a multiple of 4");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+               "sdof_add_relu: pointers must be 16-byte aligned");
+  if (n == 0) return SDOF_OK;
+  add_relu_kernel<<<grid_for(n / 4, 256, 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                                         reinterpret_cast<float4*>(y), n / 4);
+  SDOF_LAUNCH_CHECK("add_relu_kernel");
+  return SDOF_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// The two convolutions of the update block that cuDNN serves badly (round-1 launch list, per GRU iteration):
+//   convf1  : 7x7, 2 -> 128 channels on the flow (update.py:85,93): cuDNN falls back to a non-tensor-core
+//             engine, 14 us for 0.15 GFLOP;
+//   fh.conv2: 3x3, 256 -> 2 channels (update.py:10,14): 13.7 us + two cuDNN padding kernels (6 us) for 0.06 GFLOP,
+//             followed by the flow_update kernel.
+// Both are tiny and fp32 CUDA-core work here (closer to the fp32 reference than cuDNN's TF32):
+//   conv7x7_c2_relu_kernel     : out = relu(conv(flow) + bias), NHWC, register tile 4 px x 8 channels per thread
+//   flowhead2_update_kernel    : delta = conv3x3(x) + bias (warp per pixel, lanes split the 256 channels), then
+//                                the flow_update step in the same kernel
+namespace sdof {
+
+constexpr int kC7Tile = 8;                 // 8x8 output pixels per CTA
+constexpr int kC7Threads = 256;            // 16 pixel groups (row, half) x 16 channel groups of 8
+constexpr int kC7Patch = kC7Tile + 6;      // 14
+constexpr int kC7K = 98;                   // 7*7*2
+constexpr size_t kC7Smem = (size_t)kC7K * 128 * 4 + (size_t)kC7Patch * kC7Patch * 8;
+
+__global__ void __launch_bounds__(kC7Threads) conv7x7_c2_relu_kernel(const float2* __restrict__ flow, const float* __restrict__ wT,
+                                                                    const float* __restrict__ bias, float* __restrict__ out,
+                                                                    int h, int w, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(16) unsigned char c7_smem[];
+  float* ws = reinterpret_cast<float*>(c7_smem);                                   // [98][128]
+  float2* patch = reinterpret_cast<float2*>(c7_smem + (size_t)kC7K * 128 * 4);     // [14][14]
+  const int tile = blockIdx.x;
+  const int b = tile / (tiles_x * tiles_y);
+  const int trem = tile - b * tiles_x * tiles_y;
+  const int ty0 = (trem / tiles_x) * kC7Tile, tx0 = (trem % tiles_x) * kC7Tile;
+  for (int i = threadIdx.x; i < kC7K * 128 / 4; i += kC7Threads)
+    reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wT) + i);
+  const float2* fb = flow + (int64_t)b * h * w;
+  for (int i = threadIdx.x; i < kC7Patch * kC7Patch; i += kC7Threads) {
+    const int py = i / kC7Patch, pxx = i - py * kC7Patch;
+    const int y = ty0 + py - 3, x = tx0 + pxx - 3;
+    patch[i] = ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) ? fb[y * w + x] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 15, pg = threadIdx.x >> 4;
+  const int r = pg >> 1, c0 = (pg & 1) * 4;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky) {
+    float in[20];  // 10 pixels x 2 channels of patch row r+ky, columns c0 .. c0+9
+    const float4* prow = reinterpret_cast<const float4*>(patch + (r + ky) * kC7Patch + c0);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const float4 v = prow[q];
+      in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const float4* wp = reinterpret_cast<const float4*>(ws + ((ky * 7 + kx) * 2 + ci) * 128 + cg * 8);
+        const float4 wa = wp[0], wb = wp[1];
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float v = in[2 * (i + kx) + ci];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(v, wv[c], acc[i][c]);
+        }
+      }
+  }
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + cg * 2), b1 = __ldg(reinterpret_cast<const float4*>(bias) + cg * 2 + 1);
+  const int y = ty0 + r;
+  if (y >= h) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = tx0 + c0 + i;
+    if (x >= w) continue;
+    float4* o = reinterpret_cast<float4*>(out + (((int64_t)b * h + y) * w + x) * 128 + cg * 8);
+    o[0] = make_float4(fmaxf(acc[i][0] + b0.x, 0.f), fmaxf(acc[i][1] + b0.y, 0.f), fmaxf(acc[i][2] + b0.z, 0.f), fmaxf(acc[i][3] + b0.w, 0.f));
+    o[1] = make_float4(fmaxf(acc[i][4] + b1.x, 0.f), fmaxf(acc[i][5] + b1.y, 0.f), fmaxf(acc[i][6] + b1.z, 0.f), fmaxf(acc[i][7] + b1.w, 0.f));
+  }
+}
+
+// x [B,h,w,256] (already activated), w2 [9][2][256] (tap row-major, output, input channel), warp per pixel.
+__global__ void __launch_bounds__(256) flowhead2_update_kernel(const float* __restrict__ x, const float* __restrict__ w2, float2 bias,
+                                                               float2* __restrict__ coords1, float2* __restrict__ flow,
+                                                               float* __restrict__ hx, int hx_stride, int hx_off,
+                                                               float* __restrict__ rhx, int rhx_stride, int rhx_off,
+                                                               int B, int h, int w) {
+  __shared__ __align__(16) float ws[9 * 2 * 256];
+  for (int i = threadIdx.x; i < 9 * 2 * 256 / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t npix = (int64_t)B * h * w;
+  for (int64_t p = (int64_t)blockIdx.x * 8 + wib; p < npix; p += (int64_t)gridDim.x * 8) {
+    const int rem = (int)(p % ((int64_t)h * w));
+    const int y = rem / w, xx = rem - y * w;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xq = xx + t % 3 - 1;
+      if ((unsigned)yy >= (unsigned)h || (unsigned)xq >= (unsigned)w) continue;  // warp-uniform (zero padding)
+      const float4* xp = reinterpret_cast<const float4*>(x + (p + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * 256) + lane * 2;
+      const float4 a = xp[0], c = xp[1];
+      const float4* w0 = reinterpret_cast<const float4*>(ws + (t * 2) * 256) + lane * 2;
+      const float4* w1 = reinterpret_cast<const float4*>(ws + (t * 2 + 1) * 256) + lane * 2;
+      const float4 u0 = w0[0], u1 = w0[1], v0 = w1[0], v1 = w1[1];
+      s0 += a.x * u0.x + a.y * u0.y + a.z * u0.z + a.w * u0.w + c.x * u1.x + c.y * u1.y + c.z * u1.z + c.w * u1.w;
+      s1 += a.x * v0.x + a.y * v0.y + a.z * v0.z + a.w * v0.w + c.x * v1.x + c.y * v1.y + c.z * v1.z + c.w * v1.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      float2 c = coords1[p];
+      c.x += s0 + bias.x;
+      c.y += s1 + bias.y;
+      coords1[p] = c;
+      const float2 f = make_float2(c.x - (float)xx, c.y - (float)y);
+      flow[p] = f;
+      if (hx) *reinterpret_cast<float2*>(hx + p * hx_stride + hx_off) = f;
+      if (rhx) *reinterpret_cast<float2*>(rhx + p * rhx_stride + rhx_off) = f;
+    }
+  }
+}
+
+}  // namespace sdof
+
+extern "C" {
+
+int sdof_conv7x7_c2_relu(const float* flow, const float* wT, const float* bias, float* out, int B, int h, int w, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(flow && wT && bias && out, "sdof_conv7x7_c2_relu: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h >= 1 && w >= 1, "sdof_conv7x7_c2_relu: bad sizes");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(flow) & 7) | (reinterpret_cast<uintptr_t>(wT) & 15) | (reinterpret_cast<uintptr_t>(bias) & 15) |
+                (reinterpret_cast<uintptr_t>(out) & 15)) == 0, "sdof_conv7x7_c2_relu: misaligned pointer");
+  if (B == 0) return SDOF_OK;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  SDOF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    SDOF_CUDA(cudaFuncSetAttribute(conv7x7_c2_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC7Smem));
+    attr_set[dev] = true;
+  }
+  const int tx = ceil_div(w, kC7Tile), ty = ceil_div(h, kC7Tile);
+  const int64_t tiles = (int64_t)tx * ty * B;
+  SDOF_REQUIRE(tiles < 0x7fffffffLL, "sdof_conv7x7_c2_relu: too many tiles");
+  conv7x7_c2_relu_kernel<<<(unsigned)tiles, kC7Threads, kC7Smem, as_stream(stream)>>>(reinterpret_cast<const float2*>(flow), wT, bias, out,
+                                                                                     h, w, tx, ty);
+  SDOF_LAUNCH_CHECK("conv7x7_c2_relu_kernel");
+  return SDOF_OK;
+}
+
+int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float bias_y, float* coords1, float* flow, float* hx, int hx_stride,
+                          int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(x && w2 && coords1 && flow, "sdof_flowhead2_update: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h >= 1 && w >= 1, "sdof_flowhead2_update: bad sizes");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0, "sdof_flowhead2_update: x, w2 must be 16-byte aligned");
+  SDOF_REQUIRE((hx_stride % 2 == 0) && (hx_off % 2 == 0) && (rhx_stride % 2 == 0) && (rhx_off % 2 == 0),
+               "sdof_flowhead2_update: strides/offsets must be even (float2 stores)");
+  const int64_t npix = (int64_t)B * h * w;
+  if (npix == 0) return SDOF_OK;
+  int64_t want = ceil_div64(npix, 8);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  flowhead2_update_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(
+      x, w2, make_float2(bias_x, bias_y), reinterpret_cast<float2*>(coords1), reinterpret_cast<float2*>(flow), hx, hx_stride, hx_off, rhx,
+      rhx_stride, rhx_off, B, h, w);
+  SDOF_LAUNCH_CHECK("flowhead2_update_kernel");
+  return SDOF_OK;
+}
+
+}  // extern "C"

@@ -45,64 +45,79 @@ __device__ __noinline__ unsigned cubic_u8_c3_outlined(const int16_t* __restrict_
   return cubic_u8_c3(tab, img, buf_end, Hs, Ws, fc);
 }
 
-// Persistent CTAs (one per SM, 4 groups of 256 threads); a group walks 32x32 output tiles
+// Persistent CTAs (one per SM, 8 groups of 128 threads); a group walks 32x16 output tiles
 // (warp_tiled.cuh).  `old_src_end` is the bound of the per-pixel fallback path (cubic_u8_c3).
 __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
     const int16_t* __restrict__ tab, const unsigned char* __restrict__ src, const float* __restrict__ flow,
-    unsigned char* __restrict__ dst, int B, int Hs, int Ws, int H, int W, int64_t src_bstride, float sign,
-    const unsigned char* __restrict__ src_lo, const unsigned char* __restrict__ src_hi,
+    unsigned char* __restrict__ dst, WtTiling T, int Hs, int Ws, int H, int W, int64_t src_bstride, float sign,
     const unsigned char* __restrict__ old_src_end, int dst_vec_ok) {
   extern __shared__ __align__(16) unsigned char wt_smem_raw[];
   WtSmem& S = *reinterpret_cast<WtSmem*>(wt_smem_raw);
   wt_load_table(S, tab);
   __syncthreads();
-  const int grp = threadIdx.x >> 8, gt = threadIdx.x & 255, gw = gt >> 5, lane = gt & 31;
+  const int grp = threadIdx.x / kWtGroupThreads, gt = threadIdx.x % kWtGroupThreads, gw = gt >> 5, lane = gt & 31;
   uint2* region = S.region[grp];
-  const int tilesX = (W + kWtTile - 1) / kWtTile, tilesY = (H + kWtTile - 1) / kWtTile;
-  const int64_t tiles_per_img = (int64_t)tilesX * tilesY;
-  const int64_t ntiles = tiles_per_img * B;
-  for (int64_t t = (int64_t)blockIdx.x * kWtGroups + grp; t < ntiles; t += (int64_t)gridDim.x * kWtGroups) {
-    const int b = (int)(t / tiles_per_img);
-    const int rem = (int)(t - (int64_t)b * tiles_per_img);
-    const int tyi = rem / tilesX, txi = rem - tyi * tilesX;
-    const int gx = txi * kWtTile + lane;
-    const int gy0 = tyi * kWtTile + gw * 4;
-    const int64_t row0 = ((int64_t)b * H + gy0) * W;  // flat pixel index of (b, gy0, 0)
-    // ---- A: flow -> quantised coordinates
-    float2 f[4];
+  const WtPack pk = wt_make_pack(lane);
+  const int tstride = gridDim.x * kWtGroups;
+  const float2* flow2 = reinterpret_cast<const float2*>(flow);
+  int t = blockIdx.x * kWtGroups + grp;
+  if (t >= T.ntiles) return;  // group-uniform: the group's named barrier is never used by a partial group
+  // Pixels of this thread in tile (b, tyi, txi): column min(tx0 + lane, W-1), rows min(gy0 + k, H-1).  The flow of
+  // the NEXT tile is loaded before this tile's barriers and arithmetic (register double buffer), so the largest
+  // HBM stream (8 of the 14 bytes per pixel) is always in flight.
+  int b, tyi, txi;
+  wt_tile_coords(T, t, b, tyi, txi);
+  float2 f[4];
+  {
+    const int gx = min(txi * kWtTile + lane, W - 1);
+    const float2* fp = flow2 + (int64_t)b * H * W + gx;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      f[k] = make_float2(0.f, 0.f);
-      if (gx < W && gy0 + k < H) f[k] = __ldcs(reinterpret_cast<const float2*>(flow) + row0 + (int64_t)k * W + gx);
-    }
+    for (int k = 0; k < 4; ++k) f[k] = __ldcs(fp + (unsigned)(min(tyi * kWtTileH + gw * 4 + k, H - 1) * W));
+  }
+  for (;;) {
+    const int tx0 = txi * kWtTile, gy0 = tyi * kWtTileH + gw * 4;
+    const int gx = min(tx0 + lane, W - 1);
+    // ---- A: flow -> quantised coordinates
     WtPixels px;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const FixedCoord fc = fixed_coord(map_coord(gx, f[k].x, sign), map_coord(gy0 + k, f[k].y, sign));
+      const FixedCoord fc = wt_fixed_coord(map_coord(gx, f[k].x, sign), map_coord(min(gy0 + k, H - 1), f[k].y, sign));
       px.sx[k] = fc.sx;
       px.sy[k] = fc.sy;
-      px.fid[k] = (gx < W && gy0 + k < H) ? fc.fidx : -1;
+      px.fid[k] = fc.fidx;
+    }
+    const unsigned char* img = src + b * src_bstride;
+    unsigned char* orow = dst + (((int64_t)b * H + gy0) * W + tx0) * 3;
+    const int t_next = t + tstride;
+    int bn = b, tyn = tyi, txn = txi;
+    if (t_next < T.ntiles) {
+      wt_tile_coords(T, t_next, bn, tyn, txn);
+      const int gxn = min(txn * kWtTile + lane, W - 1);
+      const float2* fp = flow2 + (int64_t)bn * H * W + gxn;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) f[k] = __ldcs(fp + (unsigned)(min(tyn * kWtTileH + gw * 4 + k, H - 1) * W));
     }
     const WtRegion R = wt_bbox(S, grp, gw, lane, px);
     // ---- B: stage the source rectangle
-    const unsigned char* img = src + b * src_bstride;
-    wt_stage(region, R, img, Hs, Ws, src_lo, src_hi, gt, grp);
+    wt_stage(region, R, img, Hs, Ws, gt, grp);
     // ---- C: taps from shared memory, packed row stores
-    const bool seg_full = dst_vec_ok && (txi * kWtTile + kWtTile <= W);
+    const bool seg_full = dst_vec_ok && (tx0 + kWtTile <= W);
+    const bool lane_valid = tx0 + lane < W;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (gy0 + k >= H) break;  // warp-uniform
-      unsigned v = 0;
-      if (px.fid[k] >= 0) {
-        if (R.staged) {
-          v = wt_pixel(S, region, R, px.sx[k], px.sy[k], px.fid[k]);
-        } else {
-          v = cubic_u8_c3_outlined(tab, img, old_src_end, Hs, Ws, px.sx[k], px.sy[k], px.fid[k]);
-        }
-      }
-      unsigned char* o = dst + (row0 + (int64_t)k * W + txi * kWtTile) * 3;
-      wt_store_row(o, v, lane, seg_full, px.fid[k] >= 0);
+      unsigned v;
+      if (R.staged)
+        v = wt_pixel(S, region, R, px.sx[k], px.sy[k], px.fid[k]);
+      else
+        v = cubic_u8_c3_outlined(tab, img, old_src_end, Hs, Ws, px.sx[k], px.sy[k], px.fid[k]);
+      wt_store_row(orow + (unsigned)(k * W * 3), v, lane, pk, seg_full, lane_valid);
     }
+    if (t_next >= T.ntiles) break;
+    t = t_next;
+    b = bn;
+    tyi = tyn;
+    txi = txn;
   }
 }
 
@@ -236,12 +251,14 @@ int sdof_warp_cubic_u8(const uint8_t* src, const float* flow, int B, int src_bat
   if (B == 0) return SDOF_OK;
   CubicTables tabs;
   if ((rc = get_cubic_tables(&tabs))) return rc;
+  // sources larger than kWtMaxDim (or > 2^31 output bytes per image) take the generic kernel (same results)
+  if (Hs > kWtMaxDim || Ws > kWtMaxDim || (int64_t)H * W * 3 >= 0x7fffffffLL)
+    return launch_generic<unsigned char, true>("sdof_warp_cubic_u8", src, flow, B, src_batched, Hs, Ws, C, H, W, sign, dst, stream);
   const int64_t img_bytes = (int64_t)Hs * Ws * 3;
   const int64_t bstride = src_batched ? img_bytes : 0;
-  const uint8_t* src_hi = src + (src_batched ? (int64_t)B : 1) * img_bytes;
   // per-pixel fallback path: its word loads assume a 4-byte aligned source; otherwise it takes the tap loop
   const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 3) == 0;
-  const uint8_t* old_src_end = src_aligned ? src_hi : src;
+  const uint8_t* old_src_end = src_aligned ? src + (src_batched ? (int64_t)B : 1) * img_bytes : src;
   // packed 96-byte row stores need every 32-pixel segment word-aligned
   const int dst_vec = (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (W & 3) == 0;
   static bool attr_set[64] = {};
@@ -252,11 +269,13 @@ int sdof_warp_cubic_u8(const uint8_t* src, const float* flow, int B, int src_bat
                                    (int)sizeof(WtSmem)));
     attr_set[dev] = true;
   }
-  const int64_t ntiles = (int64_t)ceil_div(W, kWtTile) * ceil_div(H, kWtTile) * B;
+  const int64_t ntiles = (int64_t)ceil_div(W, kWtTile) * ceil_div(H, kWtTileH) * B;
+  SDOF_REQUIRE(ntiles < 0x7fffffffLL, "sdof_warp_cubic_u8: too many tiles (B*H*W too large for one launch)");
+  const WtTiling T = wt_make_tiling(B, H, W);
   const int64_t want = ceil_div64(ntiles, kWtGroups);
   const int grid = (int)(want < sm_count() ? want : sm_count());
   warp_cubic_u8c3_tiled_kernel<<<grid, kWtThreads, sizeof(WtSmem), as_stream(stream)>>>(
-      tabs.i16, src, flow, dst, B, Hs, Ws, H, W, bstride, sign, src, src_hi, old_src_end, dst_vec);
+      tabs.i16, src, flow, dst, T, Hs, Ws, H, W, bstride, sign, old_src_end, dst_vec);
   SDOF_LAUNCH_CHECK("warp_cubic_u8c3_tiled_kernel");
   return SDOF_OK;
 }

@@ -30,11 +30,15 @@ class RaftEngine:
     def __init__(self, checkpoint: str | None = None, iters: int = 20, small: bool = False,
                  corr_precision: str = 'fp16', alternate_corr: bool = False, mixed_precision: bool = False,
                  channels_last: bool = False, use_cuda_graph: bool = False, device=None, seed: int = 0,
-                 fast: bool | None = None):
+                 fast: bool | None = None, cudnn_benchmark: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.iters = iters
+        if cudnn_benchmark:
+            # let cuDNN time its engines once per convolution shape (during the first call / the graph warm-up):
+            # its heuristics pick slow kernels for several of RAFT's small-batch shapes
+            torch.backends.cudnn.benchmark = True
         self.args = SimpleNamespace(small=small, mixed_precision=mixed_precision, alternate_corr=alternate_corr,
                                     corr_precision=corr_precision)
         model = RAFT(self.args)

@@ -401,3 +401,69 @@ def instnorm_relu(x: torch.Tensor, relu: bool = True, eps: float = 1e-5, inplace
     check(load().sdof_instnorm_relu_nchw(ptr(x), ptr(y), N * C, H * W, float(eps), int(relu), stream_ptr(x.device)),
           'sdof_instnorm_relu_nchw')
     return y
+
+
+def _nhwc_dims(x: torch.Tensor):
+    """x: 4-D tensor [N,C,H,W] stored channels-last (dense NHWC)."""
+    require_cuda_cl(x, 'x')
+    N, C, H, W = x.shape
+    return N, C, H * W
+
+
+def require_cuda_cl(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != f32 or t.dim() != 4:
+        raise RuntimeError(f'{name} must be a 4-D fp32 CUDA tensor')
+    if not t.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError(f'{name} must be dense channels_last (NHWC)')
+
+
+def instnorm_nhwc(x: torch.Tensor, stats: torch.Tensor, relu: bool = True, residual: torch.Tensor | None = None,
+                  eps: float = 1e-5) -> torch.Tensor:
+    """In-place InstanceNorm2d(no affine) (+ReLU) (+ `relu(residual + .)`) on a channels-last [N,C,H,W] tensor.
+    stats: zeroed fp64 scratch with at least N*C*2 elements (consumed by this call)."""
+    N, C, hw = _nhwc_dims(x)
+    if residual is not None:
+        require_cuda_cl(residual, 'residual')
+        if residual.shape != x.shape:
+            raise RuntimeError('residual must have the shape of x')
+    if stats.dtype != torch.float64 or not stats.is_cuda or stats.numel() < N * C * 2 or not stats.is_contiguous():
+        raise RuntimeError('stats must be a contiguous fp64 CUDA tensor with >= N*C*2 elements')
+    s = stream_ptr(x.device)
+    check(load().sdof_instnorm_stats_nhwc(ptr(x), N, hw, C, ptr(stats), s), 'sdof_instnorm_stats_nhwc')
+    check(load().sdof_instnorm_apply_nhwc(ptr(x), ptr(stats), ptr(residual), ptr(x), N, hw, C, float(eps), int(relu), s),
+          'sdof_instnorm_apply_nhwc')
+    return x
+
+
+def add_relu_(y: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
+    """y = relu(a + y) in place; both dense with identical layout."""
+    if y.shape != a.shape or y.stride() != a.stride() or y.dtype != f32 or a.dtype != f32 or not y.is_cuda or not a.is_cuda:
+        raise RuntimeError('add_relu_: tensors must be fp32 CUDA tensors of identical shape and layout')
+    check(load().sdof_add_relu(ptr(a), ptr(y), ptr(y), y.numel(), stream_ptr(y.device)), 'sdof_add_relu')
+    return y
+
+
+def conv7x7_c2_relu(flow_nhwc: torch.Tensor, wT: torch.Tensor, bias: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """relu(conv7x7(flow) + bias): flow [B,h,w,2] -> [B,h,w,128]; wT = convf1.weight.permute(2,3,1,0) contiguous."""
+    require_cuda(flow_nhwc, 'flow', f32)
+    B, h, w, _ = flow_nhwc.shape
+    if tuple(wT.shape) != (7, 7, 2, 128) or not wT.is_contiguous():
+        raise RuntimeError(f'wT must be contiguous [7,7,2,128], got {tuple(wT.shape)}')
+    if out is None:
+        out = torch.empty((B, h, w, 128), dtype=f32, device=flow_nhwc.device)
+    check(load().sdof_conv7x7_c2_relu(ptr(flow_nhwc), ptr(wT), ptr(bias), ptr(out), B, h, w, stream_ptr(out.device)),
+          'sdof_conv7x7_c2_relu')
+    return out
+
+
+def flowhead2_update(x_nhwc: torch.Tensor, w2: torch.Tensor, bias, coords1: torch.Tensor, flow: torch.Tensor,
+                     hx: torch.Tensor | None, hx_off: int, rhx: torch.Tensor | None, rhx_off: int) -> None:
+    """delta = conv3x3(x) + bias; coords1 += delta; flow = coords1 - grid (into flow and the hx / rhx flow slots)."""
+    require_cuda(x_nhwc, 'x', f32)
+    B, h, w, C = x_nhwc.shape
+    if C != 256 or tuple(w2.shape) != (3, 3, 2, 256) or not w2.is_contiguous():
+        raise RuntimeError('flowhead2_update: x must be [B,h,w,256] and w2 contiguous [3,3,2,256]')
+    check(load().sdof_flowhead2_update(ptr(x_nhwc), ptr(w2), float(bias[0]), float(bias[1]), ptr(coords1), ptr(flow), ptr(hx),
+                                       hx.shape[-1] if hx is not None else 0, hx_off, ptr(rhx),
+                                       rhx.shape[-1] if rhx is not None else 0, rhx_off, B, h, w, stream_ptr(x_nhwc.device)),
+          'sdof_flowhead2_update')

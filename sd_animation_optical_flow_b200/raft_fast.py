@@ -9,9 +9,11 @@ iteration is ~25 kernels instead of ~100:
   * convz and convr (same input) are one convolution with concatenated filters;
   * the element-wise work between convolutions is four hand-written kernels (csrc/raft_glue.cu), the
     correlation lookup writes channels-last directly (csrc/corr_lookup.cu), and the convex 8x upsample
-    is one kernel producing the [B,H,W,2] flow the warp kernel consumes.
-
-The encoders (fnet, cnet) run as the regular PyTorch modules.
+    is one kernel producing the [B,H,W,2] flow the warp kernel consumes;
+  * the two convolutions cuDNN serves badly (7x7 on the 2-channel flow; 3x3 down to 2 channels) are
+    hand-written fp32 kernels, the second fused with the coords/flow update;
+  * the encoders run channels-last as well (FastEncoder), the context encoder on a side stream next to
+    the feature encoder, and the flow branch of the motion encoder next to the correlation branch.
 """
 from __future__ import annotations
 
@@ -45,9 +47,17 @@ def _fold_bn(conv, bn):
 
 
 class FastEncoder:
-    """Inference forward of raft.Encoder (basic model; RAFT/core/extractor.py:118-192) with the normalisation
-    collapsed: BatchNorm (cnet) folded into the conv weights with the ReLU fused by cuDNN, InstanceNorm (fnet)
-    + ReLU as ONE kernel per layer (csrc/raft_glue.cu) instead of four."""
+    """Inference forward of raft.Encoder (basic model; RAFT/core/extractor.py:118-192), channels-last end to end:
+    cuDNN's tensor-core convolutions take and produce NHWC, so none of the NCHW<->NHWC transposes eager PyTorch
+    wraps around each convolution run (0.86 ms of the round-1 5.9 ms step).  Normalisation is collapsed:
+
+      * fnet (InstanceNorm): bias-free convolutions (a per-channel constant cancels in the norm), then
+        `instnorm_stats_nhwc` + `instnorm_apply_nhwc` (csrc/raft_glue.cu); the apply kernel of a unit's second
+        convolution also does the residual tail `relu(x + y)` (extractor.py:49-58);
+      * cnet (BatchNorm): folded into the conv weights, ReLU fused by cuDNN, residual tail = `add_relu`.
+    """
+
+    N_NORMS = 15   # stem + 6 units x 2 + 2 downsample projections
 
     def __init__(self, enc):
         self.kind = enc.norm_fn
@@ -59,18 +69,29 @@ class FastEncoder:
             for u in layer:
                 ds = self._layer(u.downsample[0], u.downsample[1]) if u.downsample is not None else None
                 self.units.append((self._layer(u.conv1, u.norm1), self._layer(u.conv2, u.norm2), ds))
-        self.out = (enc.conv2.weight.detach(), enc.conv2.bias.detach(), enc.conv2.stride, enc.conv2.padding)
+        self.out = (enc.conv2.weight.detach().contiguous(memory_format=CL), enc.conv2.bias.detach(), enc.conv2.stride,
+                    enc.conv2.padding)
         self._fused_ok = None
+        self._max_c = max(l[0].shape[0] for l in [self.stem] + [x for u in self.units for x in u if x is not None])
 
     def _layer(self, conv, norm):
         w, b = _fold_bn(conv, norm)
-        return (w, b, conv.stride, conv.padding)
+        return (w.contiguous(memory_format=CL), b, conv.stride, conv.padding)
 
-    def _cnr(self, x, layer, relu: bool):
+    @staticmethod
+    def _cl(y):
+        return y if y.is_contiguous(memory_format=CL) else y.contiguous(memory_format=CL)
+
+    def _conv_norm(self, x, layer, relu: bool, residual=None):
+        """relu?(norm(conv(x))), then relu(residual + .) when a residual is given."""
         w, b, stride, pad = layer
         if self.kind == 'instance':
-            return ops.instnorm_relu(F.conv2d(x, w, b, stride=stride, padding=pad), relu=relu)
+            y = self._cl(F.conv2d(x, w, None, stride=stride, padding=pad))
+            stats = self._stats[self._slot]
+            self._slot += 1
+            return ops.instnorm_nhwc(y, stats, relu=relu, residual=residual)
         if relu:
+            y = None
             if self._fused_ok is not False:
                 try:
                     y = torch.cudnn_convolution_relu(x, w, b, tuple(stride), tuple(pad), (1, 1), 1)
@@ -78,22 +99,33 @@ class FastEncoder:
                         ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=pad))
                         self._fused_ok = bool(torch.allclose(y, ref, atol=1e-3, rtol=1e-3))
                         if not self._fused_ok:
-                            return ref
-                    return y
+                            y = ref
                 except RuntimeError:
                     self._fused_ok = False
-            return F.relu_(F.conv2d(x, w, b, stride=stride, padding=pad))
-        return F.conv2d(x, w, b, stride=stride, padding=pad)
+                    y = None
+            if y is None:
+                y = F.relu_(F.conv2d(x, w, b, stride=stride, padding=pad))
+        else:
+            y = F.conv2d(x, w, b, stride=stride, padding=pad)
+        y = self._cl(y)
+        if residual is not None:
+            ops.add_relu_(y, residual)
+        return y
 
     def __call__(self, x):
-        x = self._cnr(x, self.stem, True)
+        x = x.contiguous(memory_format=CL)
+        if self.kind == 'instance':
+            # one zeroed fp64 scratch for the statistics of every norm layer of this pass
+            self._stats = torch.zeros((self.N_NORMS, x.shape[0] * self._max_c * 2), dtype=torch.float64, device=x.device)
+            self._slot = 0
+        x = self._conv_norm(x, self.stem, True)
         for c1, c2, ds in self.units:
-            y = self._cnr(self._cnr(x, c1, True), c2, True)
+            y = self._conv_norm(x, c1, True)
             if ds is not None:
-                x = self._cnr(x, ds, False)
-            x = torch.relu_(x + y)
+                x = self._conv_norm(x, ds, False)
+            x = self._conv_norm(y, c2, True, residual=x)
         w, b, stride, pad = self.out
-        return F.conv2d(x, w, b, stride=stride, padding=pad)
+        return self._cl(F.conv2d(x, w, b, stride=stride, padding=pad))
 
 
 class FastRaft:
@@ -115,9 +147,13 @@ class FastRaft:
             self.zr.append((wzr, bzr, cz.padding))
             self.q.append(_w(cq))
         self.fh1, self.fh2 = _w(fh.conv1), _w(fh.conv2)
+        self.convf1_t = e.convf1.weight.detach().permute(2, 3, 1, 0).contiguous()      # [7,7,2,128] for conv7x7_c2_relu
+        self.fh2_t = fh.conv2.weight.detach().permute(2, 3, 0, 1).contiguous()         # [3,3,2,256] for flowhead2_update
         self._fh2_bias = tuple(float(v) for v in fh.conv2.bias.detach().cpu().tolist())
         self.mask0, self.mask2 = _w(ub.mask[0]), _w(ub.mask[2])
         self.hidden = model.hidden_dim
+        self.cdim = model.context_dim
+        self._side = {}
         self._fused_relu_ok = None
         self.fnet = FastEncoder(model.fnet)
         self.cnet = FastEncoder(model.cnet)
@@ -153,42 +189,68 @@ class FastRaft:
             y = y.contiguous(memory_format=CL)
         return y.permute(0, 2, 3, 1)
 
+    def _side_stream(self, dev):
+        st = self._side.get(dev)
+        if st is None:
+            st = self._side[dev] = torch.cuda.Stream(device=dev)
+        return st
+
     @torch.no_grad()
     def forward(self, image1: torch.Tensor, image2: torch.Tensor, iters: int = 20):
-        """image1/2: [B,3,H,W] float 0..255 (H, W multiples of 8).  Returns (flow_low [B,h,w,2], flow_up [B,H,W,2])."""
-        m = self.model
+        """image1/2: [B,3,H,W] float 0..255 (H, W multiples of 8).  Returns (flow_low [B,h,w,2], flow_up [B,H,W,2]).
+
+        Two independent chains run on a side stream (fork/join with events, so a CUDA-graph capture records them as
+        parallel branches): the context encoder next to the feature encoder + correlation pyramid, and in every
+        iteration the flow branch of the motion encoder (convf1, convf2) next to lookup -> convc1 -> convc2.  Every
+        buffer that crosses the streams is allocated before the fork on the main stream; the side stream's own
+        temporaries are allocated and freed in stream order on that stream."""
+        B, _, Hh, Ww = image1.shape
+        h, w = Hh // 8, Ww // 8
+        hd = self.hidden
+        dev = image1.device
+        cdim = self.cdim                                                  # context ("inp") channels
+        xc = cdim + 128                                                   # x = [inp | motion(126) | flow(2)]
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
         im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
-        n = im1.shape[0]
-        fmaps = self.fnet(torch.cat([im1, im2], 0))
-        pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps[:n]), _to_nhwc(fmaps[n:]), 4, self.corr_precision)
-        cnet = self.cnet(im1)
-        B, _, h, w = cnet.shape
-        hd = self.hidden
-        dev = cnet.device
-        cn = cnet.permute(0, 2, 3, 1)
-        H = torch.tanh(cn[..., :hd]).contiguous()                       # hidden state, dense [B,h,w,128]
-        inp = torch.relu(cn[..., hd:])
-        xc = inp.shape[-1] + 128                                          # x = [inp | motion(126) | flow(2)]
+        H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128]
         HX = torch.empty((B, h, w, hd + xc), device=dev)                 # [h | x]        (update.py:47)
         RHX = torch.empty_like(HX)                                        # [r*h | x]      (update.py:50)
-        HX[..., :hd] = H
-        HX[..., hd:hd + inp.shape[-1]] = inp
-        RHX[..., hd:hd + inp.shape[-1]] = inp
-        mo = hd + inp.shape[-1]                                           # motion-feature slot
+        CF = torch.empty((B, h, w, 256), device=dev)                      # [cor(192) | flo(64)]  (update.py:94)
+        corr = torch.empty((B, h, w, 4 * 81), device=dev)
+        flow = torch.empty((B, h, w, 2), device=dev)
+        mo = hd + cdim                                                    # motion-feature slot
         fo = mo + 126                                                     # flow slot
         ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing='ij')
         coords1 = torch.stack([xs, ys], -1).float()[None].repeat(B, 1, 1, 1).contiguous()
-        flow = torch.empty((B, h, w, 2), device=dev)
         ops.flow_update(None, coords1, flow, HX, fo, RHX, fo)             # flow = 0 into every slot
-        CF = torch.empty((B, h, w, 256), device=dev)                      # [cor(192) | flo(64)]  (update.py:94)
-        corr = torch.empty((B, h, w, 4 * 81), device=dev)
+
+        side.wait_stream(main)
+        with torch.cuda.stream(side):                                     # ---- context encoder branch
+            cn = self.cnet(im1).permute(0, 2, 3, 1)
+            torch.tanh(cn[..., :hd], out=H)
+            HX[..., :hd] = H
+            inp = torch.relu(cn[..., hd:])
+            HX[..., hd:hd + cdim] = inp
+            RHX[..., hd:hd + cdim] = inp
+            del cn, inp
+        fmaps = self.fnet(torch.cat([im1, im2], 0))                       # ---- feature encoder + all-pairs volume
+        pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps[:B]), _to_nhwc(fmaps[B:]), 4, self.corr_precision)
+        del fmaps
+        main.wait_stream(side)
+
         for _ in range(iters):
-            ops.corr_lookup_nhwc(pyr, coords1, 4, corr)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):                                 # flow branch (update.py:93-94)
+                f1 = ops.conv7x7_c2_relu(flow, self.convf1_t, self.convf1[1])
+                f2 = self._conv(f1, self.convf2)
+                ops.relu_scatter(f2, CF, 192, bias=self.convf2[1])
+                del f1, f2
+            ops.corr_lookup_nhwc(pyr, coords1, 4, corr)                   # correlation branch (update.py:91-92)
             c2 = self._conv(self._conv_relu(corr, self.convc1), self.convc2)
             ops.relu_scatter(c2, CF, 0, bias=self.convc2[1])
-            f2 = self._conv(self._conv_relu(flow, self.convf1), self.convf2)
-            ops.relu_scatter(f2, CF, 192, bias=self.convf2[1])
+            main.wait_stream(side)
             mot = self._conv(CF, self.conv)                               # 126 (+2 zero) channels
             ops.relu_scatter(mot, HX, mo, RHX, mo, c_valid=126, bias=self.conv[1])
             for p in (0, 1):                                              # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
@@ -196,7 +258,6 @@ class FastRaft:
                 ops.gru_rh(zr, H, RHX, bias_zr=self.zr[p][1])
                 q = self._conv(RHX, self.q[p])
                 ops.gru_update(zr, q, H, HX, bias_zr=self.zr[p][1], bias_q=self.q[p][1])
-            delta = self._conv(self._conv_relu(H, self.fh1), self.fh2)
-            ops.flow_update(delta.contiguous(), coords1, flow, HX, fo, RHX, fo, delta_bias=self._fh2_bias)
+            ops.flowhead2_update(self._conv_relu(H, self.fh1), self.fh2_t, self._fh2_bias, coords1, flow, HX, fo, RHX, fo)
         mask = self._conv(self._conv_relu(H, self.mask0), self.mask2)
         return flow, ops.convex_upsample(mask.contiguous(), flow, 0.25, mask_bias=self.mask2[1])

@@ -78,6 +78,60 @@ def test_instnorm_relu_kernel(cuda):
         assert torch.allclose(ops.instnorm_relu(x, relu=True, inplace=False), torch.relu(ref), atol=2e-5, rtol=1e-5)
 
 
+def test_instnorm_nhwc_kernels(cuda):
+    """channels-last InstanceNorm (+ReLU, + residual tail) vs F.instance_norm; tolerance 2e-5 abs (fp32 summation order)."""
+    from sd_animation_optical_flow_b200 import ops
+    CL = torch.channels_last
+    g = torch.Generator(device=cuda).manual_seed(5)
+    for shape in ((2, 64, 37, 41), (1, 96, 48, 32), (2, 128, 12, 8), (3, 8, 5, 3)):
+        N, C = shape[:2]
+        x = (torch.randn(shape, generator=g, device=cuda) * 3 + 1.5).contiguous(memory_format=CL)
+        res = torch.randn(shape, generator=g, device=cuda).contiguous(memory_format=CL)
+        ref = torch.nn.functional.instance_norm(x, eps=1e-5)
+        stats = lambda: torch.zeros((N * C * 2,), dtype=torch.float64, device=cuda)
+        y = ops.instnorm_nhwc(x.clone(memory_format=torch.preserve_format), stats(), relu=False)
+        assert y.is_contiguous(memory_format=CL) and torch.allclose(y, ref, atol=2e-5, rtol=1e-5)
+        y = ops.instnorm_nhwc(x.clone(memory_format=torch.preserve_format), stats(), relu=True)
+        assert torch.allclose(y, torch.relu(ref), atol=2e-5, rtol=1e-5)
+        y = ops.instnorm_nhwc(x.clone(memory_format=torch.preserve_format), stats(), relu=True, residual=res)
+        assert torch.allclose(y, torch.relu(res + torch.relu(ref)), atol=2e-5, rtol=1e-5)
+        z = ops.add_relu_(x.clone(memory_format=torch.preserve_format), res)
+        assert torch.equal(z, torch.relu(x + res))
+    with pytest.raises(RuntimeError):
+        ops.instnorm_nhwc(torch.randn((1, 8, 4, 4), device=cuda), torch.zeros(16, dtype=torch.float64, device=cuda))  # NCHW
+
+
+def test_small_conv_kernels(cuda):
+    """conv7x7_c2_relu (convf1) and flowhead2_update (flow_head.conv2 + coords update) vs F.conv2d in fp32.
+    Tolerance 2e-5 abs relative to unit-scale activations (fp32 FMA, different summation order)."""
+    import torch.nn.functional as F
+    from sd_animation_optical_flow_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(6)
+    for (B, h, w) in ((1, 96, 64), (2, 13, 21), (1, 8, 8)):
+        flow = torch.randn((B, h, w, 2), generator=g, device=cuda) * 4
+        wt = torch.randn((128, 2, 7, 7), generator=g, device=cuda) * 0.1
+        bias = torch.randn((128,), generator=g, device=cuda)
+        ref = F.relu(F.conv2d(flow.permute(0, 3, 1, 2), wt, bias, padding=3)).permute(0, 2, 3, 1)
+        out = ops.conv7x7_c2_relu(flow, wt.permute(2, 3, 1, 0).contiguous(), bias)
+        assert out.shape == ref.shape
+        assert float((out - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+        x = torch.relu(torch.randn((B, h, w, 256), generator=g, device=cuda))
+        w2 = torch.randn((2, 256, 3, 3), generator=g, device=cuda) * 0.05
+        b2 = (0.3, -0.7)
+        delta = F.conv2d(x.permute(0, 3, 1, 2), w2, torch.tensor(b2, device=cuda), padding=1).permute(0, 2, 3, 1)
+        ys, xs = torch.meshgrid(torch.arange(h, device=cuda), torch.arange(w, device=cuda), indexing='ij')
+        grid = torch.stack([xs, ys], -1).float()[None].repeat(B, 1, 1, 1)
+        coords1 = (grid + torch.randn((B, h, w, 2), generator=g, device=cuda)).contiguous()
+        want_c = coords1 + delta
+        fl = torch.empty((B, h, w, 2), device=cuda)
+        hx = torch.zeros((B, h, w, 12), device=cuda)
+        rhx = torch.zeros((B, h, w, 12), device=cuda)
+        ops.flowhead2_update(x, w2.permute(2, 3, 0, 1).contiguous(), b2, coords1, fl, hx, 10, rhx, 6)
+        assert float((coords1 - want_c).abs().max()) <= 5e-5
+        assert float((fl - (want_c - grid)).abs().max()) <= 5e-5
+        assert torch.equal(hx[..., 10:12], fl) and torch.equal(rhx[..., 6:8], fl) and float(hx[..., :10].abs().max()) == 0
+
+
 def test_convex_upsample_kernel(cuda):
     from sd_animation_optical_flow_b200 import ops
     from sd_animation_optical_flow_b200.raft import convex_upsample
@@ -123,7 +177,9 @@ def test_cuda_graph_replay_equals_eager(cuda):
     f1 = graphed.estimate_flow(a, b)
     f2 = graphed.estimate_flow(b, a)      # replay with new inputs
     f3 = graphed.estimate_flow(a, b)
-    assert torch.allclose(f0, f1, atol=1e-4) and torch.allclose(f1, f3, atol=0) and not torch.allclose(f1, f2, atol=1e-2)
+    # replays are bit-identical except for the order of the fp64 atomics behind the instance-norm statistics
+    # (1e-16 relative, below fp32 resolution except on a rounding boundary)
+    assert torch.allclose(f0, f1, atol=1e-4) and torch.allclose(f1, f3, atol=1e-5) and not torch.allclose(f1, f2, atol=1e-2)
 
 
 def test_batched_pairs_equal_single_pairs(cuda):
