@@ -188,7 +188,9 @@ def run_ours(args):
     d2 = torch.from_numpy(f2).to(dev)[None]
     dsty = torch.from_numpy(sty).to(dev)[None]
     eng = RaftEngine(checkpoint=None, iters=ITERS, corr_precision=args.corr_precision, use_cuda_graph=not args.no_graph,
-                     mixed_precision=args.mixed_precision, channels_last=args.channels_last, device=dev, seed=0)
+                     mixed_precision=args.mixed_precision, channels_last=args.channels_last, device=dev, seed=0,
+                     cudnn_benchmark=not args.no_cudnn_benchmark,
+                     fast_options=dict(side_streams=not args.no_side_streams, own_convf1=not args.cudnn_convf1, own_fh2=not args.cudnn_fh2))
 
     def step():
         flow = eng.estimate_flow(d1, d2)                 # [1,768,512,2]
@@ -223,6 +225,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     value = world * args.steps / dt
+    if args.quick:
+        if rank == 0:
+            sampler_stats = clocks
+            print(json.dumps({'quick': True, 'value': value, 'ms_per_step': dt / args.steps * 1e3, 'launches_per_step': launches_per_step,
+                              'clocks': sampler_stats, 'argv': sys.argv[1:]}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e: the reference-facing numpy API with HOST buffers (H2D / D2H inside the timed region)
     algo = ofgen.RAFT_2.__new__(ofgen.RAFT_2)
@@ -342,6 +352,11 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--mixed-precision', action='store_true')
     ap.add_argument('--channels-last', action='store_true')
+    ap.add_argument('--no-cudnn-benchmark', action='store_true')
+    ap.add_argument('--no-side-streams', action='store_true')
+    ap.add_argument('--cudnn-convf1', action='store_true')
+    ap.add_argument('--cudnn-fh2', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='step timing only: skip e2e, roofline and CPU legs')
     ap.add_argument('--cpu-budget-s', type=float, default=10.0)
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -257,11 +257,11 @@ int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stre
  *   sdof_flowhead2_update: FlowHead.conv2 (update.py:10,14) + the coords update of RAFT.forward (raft.py:128-131):
  *                          delta = conv3x3(x[B,h,w,256], pad 1) + bias; coords1 += delta; flow = coords1 - grid, written to
  *                          `flow` and the flow slots of hx / rhx like sdof_flow_update; w2 = weight[2,256,3,3] permuted
- *                          to [3,3,2,256].  fp32 FMA accumulation. */
+ *                          to [3,3,2,256]; scratch = B*h*w*18 floats (per-pixel tap products).  fp32 FMA accumulation. */
 int sdof_conv7x7_c2_relu(const float* flow, const float* wT, const float* bias, float* out, int B, int h, int w, sdof_stream_t stream);
 int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float bias_y, float* coords1, float* flow, float* hx,
                           int hx_stride, int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w,
-                          sdof_stream_t stream);
+                          float* scratch, sdof_stream_t stream);
 
 /* ---------------------------------------------------------------- diagnostics */
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */

@@ -54,7 +54,7 @@ SIGNATURES = {
     'sdof_instnorm_apply_nhwc': (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_float, c_int, _P]),
     'sdof_add_relu': (c_int, [_P, _P, _P, c_int64, _P]),
     'sdof_conv7x7_c2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
-    'sdof_flowhead2_update': (c_int, [_P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    'sdof_flowhead2_update': (c_int, [_P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     'sdof_alt_corr_forward': (c_int, [_P, _P, _P] + [c_int] * 8 + [_P, _P]),
     'sdof_alt_corr_level': (c_int, [_P, _P, _P] + [c_int] * 7 + [c_float, c_float, c_int, c_int, _P, _P]),
     'sdof_avgpool2_nhwc': (c_int, [_P] + [c_int] * 4 + [_P, _P]),

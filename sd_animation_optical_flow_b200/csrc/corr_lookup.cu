@@ -70,18 +70,23 @@ __device__ __forceinline__ void flush_stage(const float* __restrict__ stage, int
   }
 }
 
-template <int R_T, int L_T>
-__global__ void __launch_bounds__(kLookupThreads) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
-                                                                     int N1, int r_rt, float* __restrict__ out, int nhwc) {
+// PX = source pixels (= warps) per CTA.  The planar output needs PX = 32 (full 128-byte lines through the stage
+// tile); the channels-last output has no stage, so it runs with 8-warp CTAs: 768 CTAs at 96x64 instead of 192
+// 1024-thread CTAs that fill the 148 SMs 1.3 times.
+constexpr int kLookupPxNhwc = 8;
+
+template <int R_T, int L_T, int PX>
+__global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
+                                                              int N1, int r_rt, float* __restrict__ out, int nhwc) {
   extern __shared__ __align__(16) float smem[];
   const int r = R_T ? R_T : r_rt;
   const int L = L_T ? L_T : lv.levels;
   const int D = 2 * r + 1, T1 = D + 1, T = T1 * T1, DD = D * D;
-  float* stage = smem;                           // [L*DD][kStagePitch]
-  float* win_all = smem + L * DD * kStagePitch;  // [32 warps][L][T]
+  float* stage = smem;                                                    // [L*DD][kStagePitch]   (planar only)
+  float* win_all = smem + (PX == kLookupPx ? L * DD * kStagePitch : 0);   // [PX warps][L][T]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * kLookupPx;
+  const int p0 = blockIdx.x * PX;
   const int p = p0 + warp;
   float* win = win_all + warp * L * T;
   if (p < N1) {
@@ -270,21 +275,30 @@ static int corr_lookup_impl(const char* name, const float* pyramid, const float*
     lv.wp[l] = lay.wp[ll];
   }
   const int D = 2 * radius + 1, T = (D + 1) * (D + 1), DD = D * D;
-  const size_t smem = ((size_t)levels * DD * kStagePitch + (size_t)kLookupPx * levels * T) * sizeof(float);
+  const int px = nhwc ? kLookupPxNhwc : kLookupPx;
+  const size_t smem = ((nhwc ? 0 : (size_t)levels * DD * kStagePitch) + (size_t)px * levels * T) * sizeof(float);
   SDOF_REQUIRE(smem <= 200 * 1024, "%s: levels=%d radius=%d need %zu bytes of shared memory", name, levels, radius, smem);
-  dim3 grid(ceil_div(N1, kLookupPx), B);
+  dim3 grid(ceil_div(N1, px), B);
   cudaStream_t st = as_stream(stream);
-#define SDOF_LOOKUP_LAUNCH(RT, LT)                                                                                      \
-  do {                                                                                                                  \
-    SDOF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    corr_lookup_kernel<RT, LT><<<grid, kLookupThreads, smem, st>>>(lv, coords, N1, radius, out, nhwc);                  \
+#define SDOF_LOOKUP_LAUNCH(RT, LT, PX)                                                                                       \
+  do {                                                                                                                       \
+    SDOF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT, LT, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    corr_lookup_kernel<RT, LT, PX><<<grid, PX * 32, smem, st>>>(lv, coords, N1, radius, out, nhwc);                          \
+  } while (0)
+#define SDOF_LOOKUP_DISPATCH(RT, LT)             \
+  do {                                           \
+    if (nhwc)                                    \
+      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPxNhwc); \
+    else                                         \
+      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPx);     \
   } while (0)
   if (radius == 4 && levels == 4)
-    SDOF_LOOKUP_LAUNCH(4, 4);
+    SDOF_LOOKUP_DISPATCH(4, 4);
   else if (radius == 3 && levels == 4)
-    SDOF_LOOKUP_LAUNCH(3, 4);
+    SDOF_LOOKUP_DISPATCH(3, 4);
   else
-    SDOF_LOOKUP_LAUNCH(0, 0);
+    SDOF_LOOKUP_DISPATCH(0, 0);
+#undef SDOF_LOOKUP_DISPATCH
 #undef SDOF_LOOKUP_LAUNCH
   SDOF_LAUNCH_CHECK("corr_lookup_kernel");
   return SDOF_OK;

@@ -459,8 +459,8 @@ int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stre
 //             followed by the flow_update kernel.
 // Both are tiny and fp32 CUDA-core work here (closer to the fp32 reference than cuDNN's TF32):
 //   conv7x7_c2_relu_kernel     : out = relu(conv(flow) + bias), NHWC, register tile 4 px x 8 channels per thread
-//   flowhead2_update_kernel    : delta = conv3x3(x) + bias (warp per pixel, lanes split the 256 channels), then
-//                                the flow_update step in the same kernel
+//   flowhead2_{taps,gather_update}_kernel : delta = conv3x3(x) + bias as per-pixel tap products followed by a
+//                                9-neighbour gather fused with the flow_update step (see below)
 namespace sdof {
 
 constexpr int kC7Tile = 8;                 // 8x8 output pixels per CTA
@@ -532,48 +532,99 @@ __global__ void __launch_bounds__(kC7Threads) conv7x7_c2_relu_kernel(const float
   }
 }
 
-// x [B,h,w,256] (already activated), w2 [9][2][256] (tap row-major, output, input channel), warp per pixel.
-__global__ void __launch_bounds__(256) flowhead2_update_kernel(const float* __restrict__ x, const float* __restrict__ w2, float2 bias,
-                                                               float2* __restrict__ coords1, float2* __restrict__ flow,
-                                                               float* __restrict__ hx, int hx_stride, int hx_off,
-                                                               float* __restrict__ rhx, int rhx_stride, int rhx_off,
-                                                               int B, int h, int w) {
-  __shared__ __align__(16) float ws[9 * 2 * 256];
-  for (int i = threadIdx.x; i < 9 * 2 * 256 / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
+// Transposing butterfly: every lane holds 32 partial values v[0..31]; after 31 shuffles lane L holds the sum over
+// all lanes of v[L].
+__device__ __forceinline__ float warp_reduce_transpose32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// FlowHead.conv2 as "taps first": a 3x3 convolution with 2 output channels reads each 1 KB input pixel nine
+// times when done output-stationary (55 MB of L2 traffic at 96x64, 16 us measured).  Instead
+//   taps kernel  : y[p][tap][co] = <x[p, :], w[tap][co][:]>   (18 dot products per pixel, x read ONCE;
+//                  a warp owns 2 pixels, lanes split the 256 channels, weights from shared memory are reused
+//                  across the pixels, two transposing butterflies reduce the 36 partials)
+//   gather kernel: delta[p][co] = bias[co] + sum_tap y[p + off(tap)][tap][co] (zero padding), then the
+//                  coords / flow update of RAFT.forward (raft.py:128-131).
+constexpr int kFhPx = 2;                           // pixels per warp
+constexpr int kFhGroups = (kFhPx * 18 + 31) / 32;  // butterflies per warp
+
+__global__ void __launch_bounds__(256) flowhead2_taps_kernel(const float* __restrict__ x, const float* __restrict__ w2,
+                                                             float* __restrict__ y, int64_t npix) {
+  __shared__ __align__(16) float ws[18 * 256];
+  for (int i = threadIdx.x; i < 18 * 256 / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t npix = (int64_t)B * h * w;
-  for (int64_t p = (int64_t)blockIdx.x * 8 + wib; p < npix; p += (int64_t)gridDim.x * 8) {
+  const int64_t ngroups = (npix + kFhPx - 1) / kFhPx;
+  for (int64_t g = (int64_t)blockIdx.x * 8 + wib; g < ngroups; g += (int64_t)gridDim.x * 8) {
+    const int64_t p0 = g * kFhPx;
+    float4 xa[kFhPx], xb[kFhPx];
+#pragma unroll
+    for (int i = 0; i < kFhPx; ++i) {
+      const int64_t p = p0 + i < npix ? p0 + i : npix - 1;
+      const float4* xp = reinterpret_cast<const float4*>(x + p * 256) + lane * 2;
+      xa[i] = xp[0];
+      xb[i] = xp[1];
+    }
+    float v[kFhGroups][32];
+#pragma unroll
+    for (int q = 0; q < kFhGroups; ++q)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[q][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+      const float4* wp = reinterpret_cast<const float4*>(ws + j * 256) + lane * 2;
+      const float4 u0 = wp[0], u1 = wp[1];
+#pragma unroll
+      for (int i = 0; i < kFhPx; ++i) {
+        const int idx = i * 18 + j;
+        v[idx >> 5][idx & 31] = xa[i].x * u0.x + xa[i].y * u0.y + xa[i].z * u0.z + xa[i].w * u0.w + xb[i].x * u1.x + xb[i].y * u1.y +
+                                xb[i].z * u1.z + xb[i].w * u1.w;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kFhGroups; ++q) {
+      const float tot = warp_reduce_transpose32(v[q], lane);
+      const int idx = q * 32 + lane;  // = pixel * 18 + j
+      if (idx < kFhPx * 18 && p0 + idx / 18 < npix) y[p0 * 18 + idx] = tot;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) flowhead2_gather_update_kernel(const float* __restrict__ y, float2 bias, float2* __restrict__ coords1,
+                                                                      float2* __restrict__ flow, float* __restrict__ hx, int hx_stride,
+                                                                      int hx_off, float* __restrict__ rhx, int rhx_stride, int rhx_off,
+                                                                      int64_t npix, int h, int w) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
     const int rem = (int)(p % ((int64_t)h * w));
-    const int y = rem / w, xx = rem - y * w;
-    float s0 = 0.f, s1 = 0.f;
+    const int yy = rem / w, xx = rem - yy * w;
+    float s0 = bias.x, s1 = bias.y;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xq = xx + t % 3 - 1;
-      if ((unsigned)yy >= (unsigned)h || (unsigned)xq >= (unsigned)w) continue;  // warp-uniform (zero padding)
-      const float4* xp = reinterpret_cast<const float4*>(x + (p + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * 256) + lane * 2;
-      const float4 a = xp[0], c = xp[1];
-      const float4* w0 = reinterpret_cast<const float4*>(ws + (t * 2) * 256) + lane * 2;
-      const float4* w1 = reinterpret_cast<const float4*>(ws + (t * 2 + 1) * 256) + lane * 2;
-      const float4 u0 = w0[0], u1 = w0[1], v0 = w1[0], v1 = w1[1];
-      s0 += a.x * u0.x + a.y * u0.y + a.z * u0.z + a.w * u0.w + c.x * u1.x + c.y * u1.y + c.z * u1.z + c.w * u1.w;
-      s1 += a.x * v0.x + a.y * v0.y + a.z * v0.z + a.w * v0.w + c.x * v1.x + c.y * v1.y + c.z * v1.z + c.w * v1.w;
+      const int ny = yy + t / 3 - 1, nx = xx + t % 3 - 1;
+      if ((unsigned)ny < (unsigned)h && (unsigned)nx < (unsigned)w) {
+        const float2 q = *reinterpret_cast<const float2*>(y + (p + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * 18 + t * 2);
+        s0 += q.x;
+        s1 += q.y;
+      }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    }
-    if (lane == 0) {
-      float2 c = coords1[p];
-      c.x += s0 + bias.x;
-      c.y += s1 + bias.y;
-      coords1[p] = c;
-      const float2 f = make_float2(c.x - (float)xx, c.y - (float)y);
-      flow[p] = f;
-      if (hx) *reinterpret_cast<float2*>(hx + p * hx_stride + hx_off) = f;
-      if (rhx) *reinterpret_cast<float2*>(rhx + p * rhx_stride + rhx_off) = f;
-    }
+    float2 c = coords1[p];
+    c.x += s0;
+    c.y += s1;
+    coords1[p] = c;
+    const float2 f = make_float2(c.x - (float)xx, c.y - (float)yy);
+    flow[p] = f;
+    if (hx) *reinterpret_cast<float2*>(hx + p * hx_stride + hx_off) = f;
+    if (rhx) *reinterpret_cast<float2*>(rhx + p * rhx_stride + rhx_off) = f;
   }
 }
 
@@ -605,21 +656,24 @@ int sdof_conv7x7_c2_relu(const float* flow, const float* wT, const float* bias, 
 }
 
 int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float bias_y, float* coords1, float* flow, float* hx, int hx_stride,
-                          int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w, sdof_stream_t stream) {
+                          int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w, float* scratch, sdof_stream_t stream) {
   using namespace sdof;
-  SDOF_REQUIRE(x && w2 && coords1 && flow, "sdof_flowhead2_update: NULL pointer");
+  SDOF_REQUIRE(x && w2 && coords1 && flow && scratch, "sdof_flowhead2_update: NULL pointer");
   SDOF_REQUIRE(B >= 0 && h >= 1 && w >= 1, "sdof_flowhead2_update: bad sizes");
-  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0, "sdof_flowhead2_update: x, w2 must be 16-byte aligned");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 7) == 0,
+               "sdof_flowhead2_update: x, w2 must be 16-byte aligned, scratch 8-byte aligned");
   SDOF_REQUIRE((hx_stride % 2 == 0) && (hx_off % 2 == 0) && (rhx_stride % 2 == 0) && (rhx_off % 2 == 0),
                "sdof_flowhead2_update: strides/offsets must be even (float2 stores)");
   const int64_t npix = (int64_t)B * h * w;
   if (npix == 0) return SDOF_OK;
-  int64_t want = ceil_div64(npix, 8);
-  const int64_t cap = (int64_t)sm_count() * 4;
-  flowhead2_update_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(
-      x, w2, make_float2(bias_x, bias_y), reinterpret_cast<float2*>(coords1), reinterpret_cast<float2*>(flow), hx, hx_stride, hx_off, rhx,
-      rhx_stride, rhx_off, B, h, w);
-  SDOF_LAUNCH_CHECK("flowhead2_update_kernel");
+  const int64_t want = ceil_div64(ceil_div64(npix, kFhPx), 8);
+  const int64_t cap = (int64_t)sm_count() * 2;
+  flowhead2_taps_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(x, w2, scratch, npix);
+  SDOF_LAUNCH_CHECK("flowhead2_taps_kernel");
+  flowhead2_gather_update_kernel<<<grid_for(npix, 256, 8), 256, 0, as_stream(stream)>>>(
+      scratch, make_float2(bias_x, bias_y), reinterpret_cast<float2*>(coords1), reinterpret_cast<float2*>(flow), hx, hx_stride, hx_off, rhx,
+      rhx_stride, rhx_off, npix, h, w);
+  SDOF_LAUNCH_CHECK("flowhead2_gather_update_kernel");
   return SDOF_OK;
 }
 

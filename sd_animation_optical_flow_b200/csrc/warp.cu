@@ -33,18 +33,6 @@ int get_cubic_tables(CubicTables* out) {
 }
 
 // ---------------------------------------------------------------- cubic, u8, C = 3
-// per-pixel global-memory path for tiles whose source rectangle does not fit shared memory; kept out of
-// line so the staged path's register allocation is not shaped by it
-__device__ __noinline__ unsigned cubic_u8_c3_outlined(const int16_t* __restrict__ tab, const unsigned char* __restrict__ img,
-                                                      const unsigned char* __restrict__ buf_end, int Hs, int Ws, int sx,
-                                                      int sy, int fidx) {
-  FixedCoord fc;
-  fc.sx = sx;
-  fc.sy = sy;
-  fc.fidx = fidx;
-  return cubic_u8_c3(tab, img, buf_end, Hs, Ws, fc);
-}
-
 // Persistent CTAs (one per SM, 8 groups of 128 threads); a group walks 32x16 output tiles
 // (warp_tiled.cuh).  `old_src_end` is the bound of the per-pixel fallback path (cubic_u8_c3).
 __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
@@ -97,7 +85,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
 #pragma unroll
       for (int k = 0; k < 4; ++k) f[k] = __ldcs(fp + (unsigned)(min(tyn * kWtTileH + gw * 4 + k, H - 1) * W));
     }
-    const WtRegion R = wt_bbox(S, grp, gw, lane, px);
+    const WtRegion R = wt_bbox(S, kWtRegionCap, grp, gw, lane, px);
     // ---- B: stage the source rectangle
     wt_stage(region, R, img, Hs, Ws, gt, grp);
     // ---- C: taps from shared memory, packed row stores

@@ -35,15 +35,17 @@ constexpr int kWtGroupThreads = 32 * kWtGroupWarps;
 constexpr int kWtThreads = kWtGroups * kWtGroupThreads;
 constexpr int kWtTile = 32;             // tile width
 constexpr int kWtTileH = 4 * kWtGroupWarps;
-constexpr int kWtRegionCap = 3968;      // 8-byte entries per group (31 KB): e.g. 62 x 62 source pixels
+constexpr int kWtRegionCap = 3968;      // 8-byte entries per group (31 KB): e.g. 62 x 62 source pixels (plain warp kernel)
 constexpr int kWtMaxDim = 32766;        // largest source width / height of the tiled kernel (see wt_fixed_coord)
 
-struct WtSmem {
+template <int CAP>
+struct WtSmemT {
   uint4 tabA[1024];                     // weight rows ky = 0,1 of every (fy,fx)
   uint4 tabB[1024];                     // weight rows ky = 2,3
   int red[kWtGroups][kWtGroupWarps][4];  // per-warp bounding boxes
-  uint2 region[kWtGroups][kWtRegionCap];
+  uint2 region[kWtGroups][CAP];
 };
+using WtSmem = WtSmemT<kWtRegionCap>;
 
 // n / d for 0 <= n < 2^31 as one multiply-high and a shift (host-built; mul == 0 means d == 1).
 struct WtDiv {
@@ -85,7 +87,8 @@ __device__ __forceinline__ void wt_group_barrier(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kWtGroupThreads) : "memory");
 }
 
-__device__ __forceinline__ void wt_load_table(WtSmem& S, const int16_t* __restrict__ tab) {
+template <class SMEM>
+__device__ __forceinline__ void wt_load_table(SMEM& S, const int16_t* __restrict__ tab) {
   const uint4* t4 = reinterpret_cast<const uint4*>(tab);
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
     const uint4 v = __ldg(t4 + i);
@@ -127,7 +130,8 @@ struct WtRegion {
 
 // Phase A (second half): bounding box of the group's taps -> region geometry.  Contains the
 // group barrier that also orders the previous tile's reads of `region` before this tile's writes.
-__device__ __forceinline__ WtRegion wt_bbox(WtSmem& S, int grp, int gw, int lane, const WtPixels& px) {
+template <class SMEM>
+__device__ __forceinline__ WtRegion wt_bbox(SMEM& S, int cap, int grp, int gw, int lane, const WtPixels& px) {
   int mnx = __vimin3_s32(px.sx[0], px.sx[1], min(px.sx[2], px.sx[3]));
   int mxx = __vimax3_s32(px.sx[0], px.sx[1], max(px.sx[2], px.sx[3]));
   int mny = __vimin3_s32(px.sy[0], px.sy[1], min(px.sy[2], px.sy[3]));
@@ -154,7 +158,7 @@ __device__ __forceinline__ WtRegion wt_bbox(WtSmem& S, int grp, int gw, int lane
   R.ngr = (ew + 3) >> 2;
   R.pitch = 4 * R.ngr + 2;
   R.rows = eh;
-  R.staged = ew <= 2048 && eh <= 2048 && R.pitch * eh <= kWtRegionCap;
+  R.staged = ew <= 2048 && eh <= 2048 && R.pitch * eh <= cap;
   return R;
 }
 
@@ -220,7 +224,8 @@ __device__ __forceinline__ void wt_stage(uint2* __restrict__ region, const WtReg
 }
 
 // Phase C: one pixel from the staged region; returns the 3 channels in the low 24 bits.
-__device__ __forceinline__ unsigned wt_pixel(const WtSmem& S, const uint2* __restrict__ region, const WtRegion& R,
+template <class SMEM>
+__device__ __forceinline__ unsigned wt_pixel(const SMEM& S, const uint2* __restrict__ region, const WtRegion& R,
                                              int sx, int sy, int fid) {
   const uint2* e = region + (sy - R.ry0) * R.pitch + (sx - R.rx0);
   const uint4 wa = S.tabA[fid];
@@ -240,6 +245,18 @@ __device__ __forceinline__ unsigned wt_pixel(const WtSmem& S, const uint2* __res
     a2 = dp2a_lo_s16u8(whi[ky], e1.y, a2);
   }
   return (unsigned)cast_q15_u8(a0) | ((unsigned)cast_q15_u8(a1) << 8) | ((unsigned)cast_q15_u8(a2) << 16);
+}
+
+// per-pixel global-memory path for tiles whose source rectangle does not fit shared memory; kept out of
+// line so the staged path's register allocation is not shaped by it
+static __device__ __noinline__ unsigned cubic_u8_c3_outlined(const int16_t* __restrict__ tab, const unsigned char* __restrict__ img,
+                                                      const unsigned char* __restrict__ buf_end, int Hs, int Ws, int sx,
+                                                      int sy, int fidx) {
+  FixedCoord fc;
+  fc.sx = sx;
+  fc.sy = sy;
+  fc.fidx = fidx;
+  return cubic_u8_c3(tab, img, buf_end, Hs, Ws, fc);
 }
 
 // Lane constants of the row packer: word j of a 96-byte row segment starts in pixel j + j/3 at channel j % 3.

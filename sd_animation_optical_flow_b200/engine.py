@@ -30,7 +30,7 @@ class RaftEngine:
     def __init__(self, checkpoint: str | None = None, iters: int = 20, small: bool = False,
                  corr_precision: str = 'fp16', alternate_corr: bool = False, mixed_precision: bool = False,
                  channels_last: bool = False, use_cuda_graph: bool = False, device=None, seed: int = 0,
-                 fast: bool | None = None, cudnn_benchmark: bool = True):
+                 fast: bool | None = None, cudnn_benchmark: bool = True, fast_options: dict | None = None):
         if not torch.cuda.is_available():
             raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
@@ -57,16 +57,17 @@ class RaftEngine:
         if fast is None:
             fast = not small and not alternate_corr and not mixed_precision and not channels_last
         self.fast = None
+        self.fast_options = dict(fast_options or {})
         if fast:
             from .raft_fast import FastRaft
-            self.fast = FastRaft(self.model, corr_precision)
+            self.fast = FastRaft(self.model, corr_precision, **self.fast_options)
 
     def load_checkpoint(self, path: str):
         self.model.load_state_dict(torch.load(path, map_location='cpu'))
         self._graphs.clear()
         if self.fast is not None:
             from .raft_fast import FastRaft
-            self.fast = FastRaft(self.model, self.args.corr_precision)
+            self.fast = FastRaft(self.model, self.args.corr_precision, **self.fast_options)
         return self
 
     def to(self, device):
@@ -75,7 +76,7 @@ class RaftEngine:
         self._graphs.clear()
         if self.fast is not None:
             from .raft_fast import FastRaft
-            self.fast = FastRaft(self.model, self.args.corr_precision)
+            self.fast = FastRaft(self.model, self.args.corr_precision, **self.fast_options)
         return self
 
     # ---------------------------------------------------------------- core

@@ -457,13 +457,19 @@ def conv7x7_c2_relu(flow_nhwc: torch.Tensor, wT: torch.Tensor, bias: torch.Tenso
 
 
 def flowhead2_update(x_nhwc: torch.Tensor, w2: torch.Tensor, bias, coords1: torch.Tensor, flow: torch.Tensor,
-                     hx: torch.Tensor | None, hx_off: int, rhx: torch.Tensor | None, rhx_off: int) -> None:
+                     hx: torch.Tensor | None, hx_off: int, rhx: torch.Tensor | None, rhx_off: int,
+                     scratch: torch.Tensor | None = None) -> None:
     """delta = conv3x3(x) + bias; coords1 += delta; flow = coords1 - grid (into flow and the hx / rhx flow slots)."""
     require_cuda(x_nhwc, 'x', f32)
     B, h, w, C = x_nhwc.shape
     if C != 256 or tuple(w2.shape) != (3, 3, 2, 256) or not w2.is_contiguous():
         raise RuntimeError('flowhead2_update: x must be [B,h,w,256] and w2 contiguous [3,3,2,256]')
+    if scratch is None:
+        scratch = torch.empty((B * h * w * 18,), dtype=f32, device=x_nhwc.device)
+    elif scratch.numel() < B * h * w * 18 or scratch.dtype != f32 or not scratch.is_cuda:
+        raise RuntimeError('flowhead2_update: scratch must be an fp32 CUDA tensor with >= B*h*w*18 elements')
     check(load().sdof_flowhead2_update(ptr(x_nhwc), ptr(w2), float(bias[0]), float(bias[1]), ptr(coords1), ptr(flow), ptr(hx),
                                        hx.shape[-1] if hx is not None else 0, hx_off, ptr(rhx),
-                                       rhx.shape[-1] if rhx is not None else 0, rhx_off, B, h, w, stream_ptr(x_nhwc.device)),
+                                       rhx.shape[-1] if rhx is not None else 0, rhx_off, B, h, w, ptr(scratch),
+                                       stream_ptr(x_nhwc.device)),
           'sdof_flowhead2_update')

@@ -129,7 +129,11 @@ class FastEncoder:
 
 
 class FastRaft:
-    def __init__(self, model, corr_precision: str = 'fp16'):
+    def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
+                 own_fh2: bool = True):
+        """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
+        convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical."""
+        self.side_streams, self.own_convf1, self.own_fh2 = side_streams, own_convf1, own_fh2
         if model.small:
             raise ValueError('FastRaft implements the basic RAFT model (the one the ofgen scripts use)')
         self.model = model
@@ -211,7 +215,7 @@ class FastRaft:
         cdim = self.cdim                                                  # context ("inp") channels
         xc = cdim + 128                                                   # x = [inp | motion(126) | flow(2)]
         main = torch.cuda.current_stream(dev)
-        side = self._side_stream(dev)
+        side = self._side_stream(dev) if self.side_streams else main
         im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128]
@@ -220,6 +224,7 @@ class FastRaft:
         CF = torch.empty((B, h, w, 256), device=dev)                      # [cor(192) | flo(64)]  (update.py:94)
         corr = torch.empty((B, h, w, 4 * 81), device=dev)
         flow = torch.empty((B, h, w, 2), device=dev)
+        fh_scratch = torch.empty((B * h * w * 18,), device=dev)          # tap products of the flow head's second conv
         mo = hd + cdim                                                    # motion-feature slot
         fo = mo + 126                                                     # flow slot
         ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing='ij')
@@ -243,7 +248,7 @@ class FastRaft:
         for _ in range(iters):
             side.wait_stream(main)
             with torch.cuda.stream(side):                                 # flow branch (update.py:93-94)
-                f1 = ops.conv7x7_c2_relu(flow, self.convf1_t, self.convf1[1])
+                f1 = ops.conv7x7_c2_relu(flow, self.convf1_t, self.convf1[1]) if self.own_convf1 else self._conv_relu(flow, self.convf1)
                 f2 = self._conv(f1, self.convf2)
                 ops.relu_scatter(f2, CF, 192, bias=self.convf2[1])
                 del f1, f2
@@ -258,6 +263,11 @@ class FastRaft:
                 ops.gru_rh(zr, H, RHX, bias_zr=self.zr[p][1])
                 q = self._conv(RHX, self.q[p])
                 ops.gru_update(zr, q, H, HX, bias_zr=self.zr[p][1], bias_q=self.q[p][1])
-            ops.flowhead2_update(self._conv_relu(H, self.fh1), self.fh2_t, self._fh2_bias, coords1, flow, HX, fo, RHX, fo)
+            if self.own_fh2:
+                ops.flowhead2_update(self._conv_relu(H, self.fh1), self.fh2_t, self._fh2_bias, coords1, flow, HX, fo, RHX, fo,
+                                     scratch=fh_scratch)
+            else:
+                delta = self._conv(self._conv_relu(H, self.fh1), self.fh2)
+                ops.flow_update(delta.contiguous(), coords1, flow, HX, fo, RHX, fo, delta_bias=self._fh2_bias)
         mask = self._conv(self._conv_relu(H, self.mask0), self.mask2)
         return flow, ops.convex_upsample(mask.contiguous(), flow, 0.25, mask_bias=self.mask2[1])
