@@ -263,6 +263,22 @@ int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float b
                           int hx_stride, int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w,
                           float* scratch, sdof_stream_t stream);
 
+/* ---------------------------------------------------------------- after the path: mask blur, composite, latent mask
+ * What GuidedLDM.img2img_inpaint does to the warped frame and the inpainting mask before Stable Diffusion runs
+ * (guided_ldm_inpainting.py:290-309), bit-exact to Pillow (the library the reference calls there):
+ *   sdof_mask_blur_composite : blurred = mask.filter(ImageFilter.GaussianBlur(mask_blur))            (:292-293)
+ *                              out = Image.composite(reference, image, blurred)                        (:298)
+ *                              mask, blurred u8 [B,H,W]; image, reference, out u8 [B,H,W,C] (NULL out = blur only).
+ *   sdof_resize_bicubic_u8   : Image.resize((ow, oh)) (default BICUBIC, antialiased) of u8 [B,H,W] -> dst u8 [B,oh,ow]
+ *                              and/or latmask f32 [B,4,oh,ow] = around(dst / 255) tiled over the 4 latent channels
+ *                              (:304-308).  workspace: sdof_resize_bicubic_workspace_bytes() device bytes, 16-byte aligned.
+ *                              Synchronises the stream once (coefficient tables are built on the host like Pillow's). */
+int sdof_mask_blur_composite(const uint8_t* mask, const uint8_t* image, const uint8_t* reference, int B, int H, int W, int C,
+                             float mask_blur, uint8_t* blurred, uint8_t* out, sdof_stream_t stream);
+int64_t sdof_resize_bicubic_workspace_bytes(int B, int H, int W, int oh, int ow);
+int sdof_resize_bicubic_u8(const uint8_t* src, int B, int H, int W, int oh, int ow, uint8_t* dst, float* latmask, void* workspace,
+                           int64_t workspace_bytes, sdof_stream_t stream);
+
 /* ---------------------------------------------------------------- diagnostics */
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t sdof_launch_count(void);

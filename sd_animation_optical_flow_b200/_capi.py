@@ -74,6 +74,9 @@ SIGNATURES = {
     'sdof_greedy_workspace_bytes': (c_int64, [c_int] * 3),
     'sdof_greedy_composite': (c_int, [_P, _P] + [c_int] * 3 + [c_float, _P, _P, _P, _P, _P]),
     'sdof_confidence_sums': (c_int, [_P, c_int, c_int64, _P, _P]),
+    'sdof_mask_blur_composite': (c_int, [_P, _P, _P] + [c_int] * 4 + [c_float, _P, _P, _P]),
+    'sdof_resize_bicubic_workspace_bytes': (c_int64, [c_int] * 5),
+    'sdof_resize_bicubic_u8': (c_int, [_P] + [c_int] * 5 + [_P, _P, _P, c_int64, _P]),
     'sdof_warp_mask_composite': (c_int, [_P, _P, _P, _P] + [c_int] * 4 + [c_float, c_int, _P, _P, _P]),
 }
 

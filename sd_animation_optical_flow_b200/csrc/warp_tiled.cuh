@@ -164,7 +164,7 @@ __device__ __forceinline__ WtRegion wt_bbox(SMEM& S, int cap, int grp, int gw, i
 
 // 15 bytes of pixels xs..xs+4 of one source row (a = address of pixel xs, possibly outside the row), 0 outside
 // [0, Ws).  Out of line: it runs only at image borders and must not shape the main path's registers.
-__device__ __noinline__ uint4 wt_stage_bytes(const unsigned char* __restrict__ a, int xs, int Ws) {
+static __device__ __noinline__ uint4 wt_stage_bytes(const unsigned char* __restrict__ a, int xs, int Ws) {
   unsigned r[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int n = 0; n < 15; ++n) {

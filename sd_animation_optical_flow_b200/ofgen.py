@@ -30,7 +30,7 @@ import torch
 
 from . import ops
 from .engine import RaftEngine
-from .pdcnet_of import _device, _h2d
+from .pdcnet_of import _d2h, _device, _h2d
 from .pdcnet_of import warp_frame as warp_frame_pdcnet  # noqa: F401  (re-export under the scripts' alias)
 
 
@@ -39,7 +39,7 @@ def warp_frame(frame: np.ndarray, flow: np.ndarray, device=None) -> np.ndarray:
     """ofgen.warp_frame: map = grid - flow, cv2.remap INTER_CUBIC, border 0.  `flow` is not modified."""
     dev = _device(device)
     out = ops.warp(_h2d(frame, dev), _h2d(np.asarray(flow, dtype=np.float32), dev), mode='cv2_cubic', sign=-1.0)
-    return out.cpu().numpy()
+    return _d2h(out)
 
 
 # ----------------------------------------------------------------------------- F0
@@ -69,7 +69,7 @@ class RAFT_2:
         dev = self.engine.device
         a = _h2d(img1, dev)[None].flip(-1).contiguous()  # BGR -> RGB
         b = _h2d(img2, dev)[None].flip(-1).contiguous()
-        return self.engine.estimate_flow(a, b, unpad=False)[0].cpu().numpy()
+        return _d2h(self.engine.estimate_flow(a, b, unpad=False)[0])
 
 
 def create_of_algo(model_path: str | None = 'RAFT/models/raft-things.pth', **kw):
@@ -88,7 +88,7 @@ def of_calc_pdcnet(frame1: np.ndarray, frame2: np.ndarray, algo, device=None):
     """ofgen_pixel_inpaint.py:105-118: (flow, confidence, travel distance, log_confidence)."""
     flow, confidence, log_confidence = algo.calc(frame1, frame2)
     dev = _device(device)
-    v = ops.travel_distance(_h2d(flow, dev)[None], _h2d(confidence, dev)[None], 0.9)[0].cpu().numpy()
+    v = _d2h(ops.travel_distance(_h2d(flow, dev)[None], _h2d(confidence, dev)[None], 0.9)[0])
     return flow, confidence, v, log_confidence
 
 
@@ -99,7 +99,7 @@ def generate_mask(cum_confidence: np.ndarray, log_confidence: np.ndarray, thres:
     dev = _device(device)
     conf_d = _h2d(np.asarray(cum_confidence, dtype=np.float32), dev)[None]
     logc_d = _h2d(np.asarray(log_confidence, dtype=np.float32), dev)[None].clone()
-    mask = ops.generate_mask(conf_d, logc_d, thres, 7)[0].cpu().numpy()
+    mask = _d2h(ops.generate_mask(conf_d, logc_d, thres, 7)[0])
     log_confidence[...] = logc_d[0].cpu().numpy()
     return mask, log_confidence
 
@@ -118,7 +118,7 @@ def confidence_to_mask(confidence, flow, dist, mask_aux, device=None):
     mask[low | far] = 255
     ptd[far] = 0
     mask_aux.pixel_travel_dist = ptd.cpu().numpy()
-    return ops.dilate_ellipse(mask[None].contiguous(), 15)[0].cpu().numpy()
+    return _d2h(ops.dilate_ellipse(mask[None].contiguous(), 15)[0])
 
 
 def mix_propagated_ai_frame(raw_ai_frame, warped_propagated_ai_frame, mask, propagated_pixel_weight=1.0, device=None):
@@ -127,7 +127,7 @@ def mix_propagated_ai_frame(raw_ai_frame, warped_propagated_ai_frame, mask, prop
     dev = _device(device)
     out = ops.mix_propagated(_h2d(raw_ai_frame, dev)[None], _h2d(warped_propagated_ai_frame, dev)[None],
                              _h2d(mask, dev)[None], propagated_pixel_weight)
-    return out[0].cpu().numpy()
+    return _d2h(out[0])
 
 
 def merge_images(base_image, second_image, mask, method='naive', device=None):
@@ -135,18 +135,18 @@ def merge_images(base_image, second_image, mask, method='naive', device=None):
         raise NotImplementedError("only method='naive' is on the hot path (the 'poisson' branch calls cv2.seamlessClone)")
     dev = _device(device)
     out = ops.merge_select(_h2d(base_image, dev)[None], _h2d(second_image, dev)[None], _h2d(mask, dev)[None])
-    return out[0].cpu().numpy()
+    return _d2h(out[0])
 
 
 def expand_mask(mask: np.ndarray, ori_image: np.ndarray, device=None) -> np.ndarray:
     dev = _device(device)
-    return ops.expand_mask(_h2d(mask, dev)[None], _h2d(ori_image, dev)[None], 7)[0].cpu().numpy()
+    return _d2h(ops.expand_mask(_h2d(mask, dev)[None], _h2d(ori_image, dev)[None], 7)[0])
 
 
 def invert_and_dilate(mask: np.ndarray, device=None) -> np.ndarray:
     """mask2 = dilate(255 - mask, ellipse 7x7) (ofgen_keyframe_inpaint.py:772-774)."""
     dev = _device(device)
-    return ops.dilate_ellipse(_h2d(mask, dev)[None], 7, invert=True)[0].cpu().numpy()
+    return _d2h(ops.dilate_ellipse(_h2d(mask, dev)[None], 7, invert=True)[0])
 
 
 def composite_references(flow_mat: np.ndarray, ai_frames, thres: float = 0.5, device=None):
@@ -160,7 +160,7 @@ def composite_references(flow_mat: np.ndarray, ai_frames, thres: float = 0.5, de
     frames = _h2d(np.stack([np.asarray(f) for f in ai_frames]), dev)
     ret, mask, order = ops.greedy_composite(fm, frames, thres)
     flow_mat[...] = fm.cpu().numpy().reshape(flow_mat.shape)
-    return ret.cpu().numpy(), mask.cpu().numpy(), [int(i) for i in order.cpu().tolist()]
+    return _d2h(ret), _d2h(mask), [int(i) for i in order.cpu().tolist()]
 
 
 # ----------------------------------------------------------------------------- A1 / A2

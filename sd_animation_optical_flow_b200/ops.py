@@ -473,3 +473,39 @@ def flowhead2_update(x_nhwc: torch.Tensor, w2: torch.Tensor, bias, coords1: torc
                                        rhx.shape[-1] if rhx is not None else 0, rhx_off, B, h, w, ptr(scratch),
                                        stream_ptr(x_nhwc.device)),
           'sdof_flowhead2_update')
+
+
+# --------------------------------------------------------------------------- after the path (guided_ldm_inpainting.py:290-309)
+def mask_blur_composite(mask: torch.Tensor, image: torch.Tensor | None, reference: torch.Tensor | None, mask_blur: float):
+    """blurred = GaussianBlur(mask_blur)(mask); out = Image.composite(reference, image, blurred), bit-exact to Pillow.
+    mask u8 [B,H,W]; image, reference u8 [B,H,W,C] or both None (blur only).  Returns (out or None, blurred)."""
+    require_cuda(mask, 'mask', u8)
+    B, H, W = mask.shape
+    out, C = None, 1
+    if image is not None or reference is not None:
+        require_cuda(image, 'image', u8)
+        require_cuda(reference, 'reference', u8)
+        if image.shape != reference.shape or tuple(image.shape[:3]) != (B, H, W):
+            raise RuntimeError('image and reference must both be [B,H,W,C] matching the mask')
+        C = image.shape[3]
+        out = torch.empty_like(image)
+    blurred = torch.empty_like(mask)
+    check(load().sdof_mask_blur_composite(ptr(mask), ptr(image), ptr(reference), B, H, W, C, float(mask_blur), ptr(blurred), ptr(out),
+                                          stream_ptr(mask.device)), 'sdof_mask_blur_composite')
+    return out, blurred
+
+
+def resize_bicubic_u8(src: torch.Tensor, oh: int, ow: int, want_latmask: bool = False):
+    """Image.resize((ow, oh)) (BICUBIC) of u8 [B,H,W], bit-exact to Pillow.  Returns dst u8 [B,oh,ow] and, with
+    want_latmask, also f32 [B,4,oh,ow] = around(dst / 255) tiled over 4 channels (guided_ldm_inpainting.py:304-308)."""
+    require_cuda(src, 'src', u8)
+    B, H, W = src.shape
+    nbytes = int(load().sdof_resize_bicubic_workspace_bytes(B, H, W, oh, ow))
+    if nbytes < 0:
+        raise RuntimeError('resize_bicubic_u8: bad sizes')
+    ws = torch.empty((nbytes,), dtype=u8, device=src.device)
+    dst = torch.empty((B, oh, ow), dtype=u8, device=src.device)
+    lat = torch.empty((B, 4, oh, ow), dtype=f32, device=src.device) if want_latmask else None
+    check(load().sdof_resize_bicubic_u8(ptr(src), B, H, W, oh, ow, ptr(dst), ptr(lat), ptr(ws), nbytes, stream_ptr(src.device)),
+          'sdof_resize_bicubic_u8')
+    return (dst, lat) if want_latmask else dst

@@ -31,13 +31,24 @@ def _h2d(a: np.ndarray, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
 
 
+def _d2h(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> fresh host array.  The copy lands in pinned memory (PyTorch's caching host allocator recycles
+    the blocks), which avoids the driver's staged pageable copy: 3 MB of flow per 768x512 pair otherwise costs more
+    than the warp kernel."""
+    t = t.contiguous()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out.numpy()
+
+
 def warp_frame(frame: np.ndarray, flow: np.ndarray, device=None) -> np.ndarray:
     """out[y,x] = cubic(frame, x + flow[y,x,0], y + flow[y,x,1]), constant border 0.
     frame uint8/float32 [H,W] or [H,W,C]; flow float32 [H,W,2]; `flow` is not modified."""
     dev = _device(device)
     fl = _h2d(np.asarray(flow, dtype=np.float32), dev)
     out = ops.warp(_h2d(frame, dev), fl, mode='cv2_cubic', sign=1.0)
-    return out.cpu().numpy()
+    return _d2h(out)
 
 
 def warp_frame_latent(latent: torch.Tensor, flow: np.ndarray, device=None) -> torch.Tensor:
@@ -53,7 +64,8 @@ def warp_frame_latent(latent: torch.Tensor, flow: np.ndarray, device=None) -> to
     if big.ndim == 2:
         big = big[:, :, None]
     warped = ops.warp(_h2d(big.astype(np.float32), dev), _h2d(np.asarray(flow, dtype=np.float32), dev),
-                      mode='cv2_cubic', sign=1.0).cpu().numpy()
+                      mode='cv2_cubic', sign=1.0)
+    warped = _d2h(warped)
     small = cv2.resize(warped, (lw, lh), interpolation=cv2.INTER_CUBIC)
     if small.ndim == 2:
         small = small[:, :, None]
@@ -124,7 +136,7 @@ class PDCNetPlus:
         f2 = _h2d(frame2, dev)[None].flip(-1)
         flow, wm = self._estimate(f1.contiguous(), f2.contiguous())
         conf, logc = ops.confidence_softmax(wm.to(dev))
-        return flow[0].cpu().numpy(), conf[0].cpu().numpy(), logc[0].cpu().numpy()
+        return _d2h(flow[0]), _d2h(conf[0]), _d2h(logc[0])
 
     @torch.no_grad()
     def calc_batch(self, src: torch.Tensor, tgt: torch.Tensor):
@@ -132,7 +144,7 @@ class PDCNetPlus:
         as host arrays, so `ret[si,ti,:,:,0:2] = flow[i]` works as written at
         ofgen_keyframe_inpaint.py:594-599 (the method is called there but missing from the reference)."""
         flow, conf = self.calc_batch_device(src, tgt)
-        return flow.cpu().numpy(), conf.cpu().numpy()
+        return _d2h(flow), _d2h(conf)
 
     @torch.no_grad()
     def calc_batch_device(self, src: torch.Tensor, tgt: torch.Tensor):
