@@ -263,6 +263,19 @@ int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float b
                           int hx_stride, int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w,
                           float* scratch, sdof_stream_t stream);
 
+/* ---------------------------------------------------------------- before the path: key-frame detector
+ * frame_generator's edge-change detector (ofgen_pixel_inpaint.py:127-176, 300-312), bit-exact to OpenCV:
+ *   sdof_detect_edges   : edges = cv2.dilate(cv2.Canny(V(frame), low, high), ones(k,k)) with V = max(B,G,R) (8-bit HSV
+ *                         value channel).  low < 0 or high < 0 selects the reference's rule
+ *                         low, high = int(max(0, (1-1/3)*median(V))), int(min(255, (1+1/3)*median(V))) (:158-161).
+ *                         frame_bgr u8 [H,W,3], edges u8 [H,W] (0/255).  Synchronises the stream (hysteresis runs to a
+ *                         global fixed point; the host relaunches while any tile changed).
+ *   sdof_abs_diff_sum_u8: sum |a - b| over n bytes into *sum (device, 8 bytes): mean_pixel_distance (:132-139) = sum / n. */
+int64_t sdof_detect_edges_workspace_bytes(int H, int W);
+int sdof_detect_edges(const uint8_t* frame_bgr, int H, int W, int dilate_k, int low, int high, uint8_t* edges, void* workspace,
+                      int64_t workspace_bytes, sdof_stream_t stream);
+int sdof_abs_diff_sum_u8(const uint8_t* a, const uint8_t* b, int64_t n, unsigned long long* sum, sdof_stream_t stream);
+
 /* ---------------------------------------------------------------- after the path: mask blur, composite, latent mask
  * What GuidedLDM.img2img_inpaint does to the warped frame and the inpainting mask before Stable Diffusion runs
  * (guided_ldm_inpainting.py:290-309), bit-exact to Pillow (the library the reference calls there):

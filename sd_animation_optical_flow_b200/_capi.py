@@ -74,6 +74,9 @@ SIGNATURES = {
     'sdof_greedy_workspace_bytes': (c_int64, [c_int] * 3),
     'sdof_greedy_composite': (c_int, [_P, _P] + [c_int] * 3 + [c_float, _P, _P, _P, _P, _P]),
     'sdof_confidence_sums': (c_int, [_P, c_int, c_int64, _P, _P]),
+    'sdof_detect_edges_workspace_bytes': (c_int64, [c_int, c_int]),
+    'sdof_detect_edges': (c_int, [_P] + [c_int] * 5 + [_P, _P, c_int64, _P]),
+    'sdof_abs_diff_sum_u8': (c_int, [_P, _P, c_int64, _P, _P]),
     'sdof_mask_blur_composite': (c_int, [_P, _P, _P] + [c_int] * 4 + [c_float, _P, _P, _P]),
     'sdof_resize_bicubic_workspace_bytes': (c_int64, [c_int] * 5),
     'sdof_resize_bicubic_u8': (c_int, [_P] + [c_int] * 5 + [_P, _P, _P, c_int64, _P]),

@@ -91,15 +91,19 @@ __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
     // ---- C: taps from shared memory, packed row stores
     const bool seg_full = dst_vec_ok && (tx0 + kWtTile <= W);
     const bool lane_valid = tx0 + lane < W;
+    // all four pixels first (independent LDS -> dp2a chains the scheduler can interleave), then the row stores
+    unsigned v[4];
+    if (R.staged) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = wt_pixel(S, region, R, px.sx[k], px.sy[k], px.fid[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = cubic_u8_c3_outlined(tab, img, old_src_end, Hs, Ws, px.sx[k], px.sy[k], px.fid[k]);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (gy0 + k >= H) break;  // warp-uniform
-      unsigned v;
-      if (R.staged)
-        v = wt_pixel(S, region, R, px.sx[k], px.sy[k], px.fid[k]);
-      else
-        v = cubic_u8_c3_outlined(tab, img, old_src_end, Hs, Ws, px.sx[k], px.sy[k], px.fid[k]);
-      wt_store_row(orow + (unsigned)(k * W * 3), v, lane, pk, seg_full, lane_valid);
+      wt_store_row(orow + (unsigned)(k * W * 3), v[k], lane, pk, seg_full, lane_valid);
     }
     if (t_next >= T.ntiles) break;
     t = t_next;

@@ -260,3 +260,64 @@ def keyframe_conv_pick(flow_mat: np.ndarray, device=None) -> int:
     dev = _device(device)
     sums = ops.confidence_sums(_h2d(np.asarray(flow_mat, dtype=np.float32), dev))
     return int(torch.argmax(sums).item())
+
+
+# ----------------------------------------------------------------------------- key-frame detector (before the path)
+def estimated_kernel_size(frame_width: int, frame_height: int) -> int:
+    """ofgen_pixel_inpaint.py:142-147."""
+    import math
+    size = 4 + round(math.sqrt(frame_width * frame_height) / 192)
+    if size % 2 == 0:
+        size += 1
+    return size
+
+
+def detect_edges_device(frame_bgr: torch.Tensor) -> torch.Tensor:
+    """detect_edges for a CUDA uint8 [H,W,3] frame -> CUDA uint8 [H,W] edge map (stays on the device)."""
+    H, W, _ = frame_bgr.shape
+    return ops.detect_edges(frame_bgr, estimated_kernel_size(W, H))
+
+
+def detect_edges(frame: np.ndarray, device=None) -> np.ndarray:
+    """ofgen_pixel_inpaint.py:150-176: HSV value channel -> median-thresholded Canny -> k x k dilation."""
+    return _d2h(detect_edges_device(_h2d(frame, _device(device))))
+
+
+def mean_pixel_distance(left, right, device=None) -> float:
+    """ofgen_pixel_inpaint.py:132-139 (from PySceneDetect): mean |left - right| of two 2-D 8-bit images."""
+    if isinstance(left, np.ndarray):
+        dev = _device(device)
+        left, right = _h2d(left, dev), _h2d(right, dev)
+    assert left.dim() == 2 and right.dim() == 2
+    assert left.shape == right.shape
+    return ops.abs_diff_sum(left.contiguous(), right.contiguous()) / float(left.shape[0] * left.shape[1])
+
+
+class KeyFrameSelector:
+    """The decision logic of frame_generator (ofgen_pixel_inpaint.py:272-313) without the video IO: feed the resized
+    frames in order, `push(frame)` answers whether the frame starts a new key-frame segment.  Edge maps stay on the
+    device; only the scalar distance comes back."""
+
+    def __init__(self, fps: float = 30.0, th: float = 8.5, min_gap: int = -1, max_gap: int = -1, device=None):
+        self.th = th
+        self.min_gap = int(10 * fps / 30) if min_gap == -1 else int(max(1, min_gap) * fps / 30)
+        self.max_gap = int(300 * fps / 30) if max_gap == -1 else int(max(10, max_gap) * fps / 30)
+        self.gap = 0
+        self.key_edges = None
+        self.device = _device(device)
+
+    def push(self, frame, frames_advanced: int = 1) -> bool:
+        """frame: BGR uint8 [H,W,3] (numpy or CUDA tensor); frames_advanced = source frames consumed since the last
+        push (`keep_every`), which is what the reference's `gap` counts (:293-297)."""
+        self.gap += frames_advanced
+        f = frame if isinstance(frame, torch.Tensor) else _h2d(frame, self.device)
+        edges = detect_edges_device(f)
+        if self.key_edges is None:
+            self.key_edges = edges
+            return True
+        delta = mean_pixel_distance(edges, self.key_edges)
+        if self.th * (self.max_gap - self.gap) / self.max_gap < delta:
+            self.key_edges = edges
+            self.gap = 0
+            return True
+        return False

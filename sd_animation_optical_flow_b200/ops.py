@@ -509,3 +509,30 @@ def resize_bicubic_u8(src: torch.Tensor, oh: int, ow: int, want_latmask: bool = 
     check(load().sdof_resize_bicubic_u8(ptr(src), B, H, W, oh, ow, ptr(dst), ptr(lat), ptr(ws), nbytes, stream_ptr(src.device)),
           'sdof_resize_bicubic_u8')
     return (dst, lat) if want_latmask else dst
+
+
+# --------------------------------------------------------------------------- before the path (ofgen_pixel_inpaint.py:127-176)
+def detect_edges(frame_bgr: torch.Tensor, dilate_k: int, low: int = -1, high: int = -1) -> torch.Tensor:
+    """cv2.dilate(cv2.Canny(V(frame), low, high), ones(k,k)); low/high < 0 = the reference's median rule.
+    frame_bgr u8 [H,W,3] -> u8 [H,W] in {0,255}, bit-exact to OpenCV."""
+    require_cuda(frame_bgr, 'frame', u8)
+    if frame_bgr.dim() != 3 or frame_bgr.shape[2] != 3:
+        raise RuntimeError(f'frame must be [H,W,3], got {tuple(frame_bgr.shape)}')
+    H, W, _ = frame_bgr.shape
+    nbytes = int(load().sdof_detect_edges_workspace_bytes(H, W))
+    ws = torch.empty((nbytes,), dtype=u8, device=frame_bgr.device)
+    edges = torch.empty((H, W), dtype=u8, device=frame_bgr.device)
+    check(load().sdof_detect_edges(ptr(frame_bgr), H, W, int(dilate_k), int(low), int(high), ptr(edges), ptr(ws), nbytes,
+                                   stream_ptr(frame_bgr.device)), 'sdof_detect_edges')
+    return edges
+
+
+def abs_diff_sum(a: torch.Tensor, b: torch.Tensor) -> int:
+    """sum |a - b| over two u8 tensors of the same shape (exact integer)."""
+    require_cuda(a, 'a', u8)
+    require_cuda(b, 'b', u8)
+    if a.shape != b.shape:
+        raise RuntimeError('abs_diff_sum: shapes differ')
+    out = torch.empty((1,), dtype=torch.int64, device=a.device)
+    check(load().sdof_abs_diff_sum_u8(ptr(a), ptr(b), a.numel(), ptr(out), stream_ptr(a.device)), 'sdof_abs_diff_sum_u8')
+    return int(out.item())
