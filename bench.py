@@ -298,6 +298,9 @@ def run_ours(args):
     coords = coords_grid(1, H // 8, W // 8, dev) + 2 * torch.randn((1, 2, H // 8, W // 8), generator=g, device=dev)
     look_out = torch.empty((1, 324, H // 8, W // 8), device=dev)
     t_look = time_op(lambda: ops.corr_lookup(pyr, coords, 4, out=look_out), 50, torch)
+    coords_nhwc = coords.permute(0, 2, 3, 1).contiguous()
+    look_nhwc = torch.empty((1, H // 8, W // 8, 324), device=dev)
+    t_look_nhwc = time_op(lambda: ops.corr_lookup_nhwc(pyr, coords_nhwc, 4, look_nhwc), 50, torch)
     # flows as the path produces them: smooth fields (camera / object motion): per frame a random translation of a few
     # pixels plus a low-frequency deformation (1/64-resolution Gaussian field of 4 px, bicubic-upsampled: |grad| ~ 0.1)
     flow32 = (torch.nn.functional.interpolate(torch.randn((32, 2, H // 64, W // 64), generator=g, device=dev) * 4, scale_factor=64,
@@ -320,11 +323,14 @@ def run_ours(args):
     extra = [
         {'kernel': corr_kernel, 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
          'frac': tf / peaks['bf16_tflops'], 'note': f'{args.corr_precision} MMA (2*N^2*C flops of level 0) vs measured bf16 burst peak; the kernel is HBM-store-bound'},
-        {'kernel': 'corr_lookup_kernel', 'bound': 'hbm', 'achieved': 2896.0 * n1 / t_look / 1e9, 'peak': hbm, 'unit': 'GB/s',
-         'frac': 2896.0 * n1 / t_look / 1e9 / hbm, 'us_per_launch': t_look * 1e6},
+        {'kernel': 'corr_lookup_kernel<4,4,32> (planar output, the corr_fn protocol)', 'bound': 'hbm', 'achieved': 2896.0 * n1 / t_look / 1e9,
+         'peak': hbm, 'unit': 'GB/s', 'frac': 2896.0 * n1 / t_look / 1e9 / hbm, 'us_per_launch': t_look * 1e6},
+        {'kernel': 'corr_lookup_kernel<4,4,8> (channels-last output, the one in the step)', 'bound': 'hbm',
+         'achieved': 2896.0 * n1 / t_look_nhwc / 1e9, 'peak': hbm, 'unit': 'GB/s', 'frac': 2896.0 * n1 / t_look_nhwc / 1e9 / hbm,
+         'us_per_launch': t_look_nhwc * 1e6},
         {'kernel': 'warp_cubic_u8c3_tiled_kernel, 32 frames, smooth flow (translation + low-frequency deformation)', 'bound': 'hbm', 'achieved': 14.0 * 32 * H * W / t_warp / 1e9, 'peak': hbm,
          'unit': 'GB/s', 'frac': 14.0 * 32 * H * W / t_warp / 1e9 / hbm, 'us_per_launch': t_warp * 1e6},
-        {'kernel': 'warp_mask_composite_tiled_kernel, 32 frames, same flows, N(0,3) logits, thres 0.95, 7x7 ellipse', 'bound': 'hbm', 'achieved': 26.0 * 32 * H * W / t_fused / 1e9, 'peak': hbm,
+        {'kernel': 'warp_mask_composite_kernel, 32 frames, same flows, N(0,3) logits, thres 0.95, 7x7 ellipse', 'bound': 'hbm', 'achieved': 26.0 * 32 * H * W / t_fused / 1e9, 'peak': hbm,
          'unit': 'GB/s', 'frac': 26.0 * 32 * H * W / t_fused / 1e9 / hbm, 'us_per_launch': t_fused * 1e6},
     ]
 

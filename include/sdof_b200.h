@@ -251,6 +251,11 @@ int sdof_instnorm_stats_nhwc(const float* x, int N, int64_t hw, int C, double* s
 int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* residual, float* y, int N, int64_t hw, int C,
                              float eps, int relu, sdof_stream_t stream);
 int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stream_t stream);
+/* Input side of RAFT_2.calc / RAFT.forward (ofgen.py:72-76, RAFT/core/raft.py:89-90, utils/utils.py:7-19) in one pass:
+ * img u8 [B,H,W,3] -> out f32 [B,Hp,Wp,3] (NHWC) = 2*(x/255)-1 of the replicate-padded frame; pixel (y,x) of out reads
+ * img at (clamp(y-top), clamp(x-left)). */
+int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, float* out,
+                               sdof_stream_t stream);
 /* The two convolutions of the update block that are too small / too thin for a tensor-core library kernel:
  *   sdof_conv7x7_c2_relu : BasicMotionEncoder.convf1 (RAFT/core/update.py:85,93): out[B,h,w,128] =
  *                          relu(conv7x7(flow[B,h,w,2], pad 3) + bias); wT = weight[128,2,7,7] permuted to [7,7,2,128].

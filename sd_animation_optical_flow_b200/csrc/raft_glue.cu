@@ -678,3 +678,38 @@ int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float b
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Input side of RAFT_2.calc / RAFT.forward (ofgen.py:72-76, raft.py:89-90) in one pass: uint8 HWC frame ->
+// replicate-padded (InputPadder, utils/utils.py:7-19), normalised 2*(x/255)-1 fp32 NHWC image that the channels-last
+// encoder convolutions consume directly.  Replaces permute + float + pad + contiguous + div + mul + sub + the
+// NCHW -> NHWC copy (about a dozen ATen launches per pair).
+namespace sdof {
+__global__ void __launch_bounds__(256) normalize_pad_u8_nhwc_kernel(const unsigned char* __restrict__ img, int B, int H, int W, int top, int left,
+                                                                    int Hp, int Wp, float* __restrict__ out) {
+  const int64_t total = (int64_t)B * Hp * Wp;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(p % Wp);
+    const int y = (int)((p / Wp) % Hp);
+    const int b = (int)(p / ((int64_t)Wp * Hp));
+    const int sy = min(max(y - top, 0), H - 1), sx = min(max(x - left, 0), W - 1);
+    const unsigned char* q = img + (((int64_t)b * H + sy) * W + sx) * 3;
+    float* o = out + p * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn((float)q[c], 255.0f)), 1.0f);
+  }
+}
+}  // namespace sdof
+
+extern "C" int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, float* out,
+                                          sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(img && out, "sdof_normalize_pad_u8_nhwc: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && H >= 1 && W >= 1 && top >= 0 && left >= 0 && Hp >= H + top && Wp >= W + left,
+               "sdof_normalize_pad_u8_nhwc: bad sizes H=%d W=%d top=%d left=%d Hp=%d Wp=%d", H, W, top, left, Hp, Wp);
+  const int64_t total = (int64_t)B * Hp * Wp;
+  if (total == 0) return SDOF_OK;
+  normalize_pad_u8_nhwc_kernel<<<grid_for(total, 256, 8), 256, 0, as_stream(stream)>>>(img, B, H, W, top, left, Hp, Wp, out);
+  SDOF_LAUNCH_CHECK("normalize_pad_u8_nhwc_kernel");
+  return SDOF_OK;
+}

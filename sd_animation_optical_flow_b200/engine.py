@@ -115,6 +115,39 @@ class RaftEngine:
         g.replay()
         return out.clone()  # the graph's output buffer is overwritten by the next replay
 
+    # ---------------------------------------------------------------- uint8 fast path
+    @torch.no_grad()
+    def _forward_u8(self, a: torch.Tensor, b: torch.Tensor, pad) -> torch.Tensor:
+        """uint8 RGB [B,H,W,3] x2 -> padded-size flow [B,Hp,Wp,2]: one kernel normalises + pads each frame straight into
+        the channels-last layout the encoders consume (csrc/raft_glue.cu::normalize_pad_u8_nhwc_kernel)."""
+        im1 = ops.normalize_pad_u8(a, pad)
+        im2 = ops.normalize_pad_u8(b, pad)
+        _, flow_up = self.fast.forward(im1, im2, self.iters, normalized=True)
+        return flow_up
+
+    @torch.no_grad()
+    def _forward_u8_graphed(self, a: torch.Tensor, b: torch.Tensor, pad) -> torch.Tensor:
+        key = ('u8', tuple(a.shape), self.iters)
+        ent = self._graphs.get(key)
+        if ent is None:
+            s1, s2 = a.clone(), b.clone()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up: cuDNN autotune, table uploads, allocator
+                    self._forward_u8(s1, s2, pad)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward_u8(s1, s2, pad)
+            ent = (g, s1, s2, out)
+            self._graphs[key] = ent
+        g, s1, s2, out = ent
+        s1.copy_(a)
+        s2.copy_(b)
+        g.replay()
+        return out  # overwritten by the next replay: estimate_flow copies (unpad / contiguous) before returning
+
     @torch.no_grad()
     def estimate_flow(self, img1: torch.Tensor, img2: torch.Tensor, unpad: bool = True) -> torch.Tensor:
         """img1, img2: RGB uint8 (or float 0..255) CUDA tensors [B,H,W,3].  Returns flow of img1 -> img2
@@ -125,6 +158,15 @@ class RaftEngine:
             raise RuntimeError(f'images must both be [B,H,W,3], got {tuple(img1.shape)} and {tuple(img2.shape)}')
         if not img1.is_cuda or not img2.is_cuda:
             raise RuntimeError('estimate_flow takes CUDA tensors; use ofgen.RAFT_2.calc for numpy frames')
+        if self.fast is not None and img1.dtype == torch.uint8 and img2.dtype == torch.uint8:
+            B, H, W, _ = img1.shape
+            pad = InputPadder((H, W))._pad
+            fwd = self._forward_u8_graphed if self.use_cuda_graph else self._forward_u8
+            flow_up = fwd(img1.contiguous(), img2.contiguous(), pad)
+            if unpad and any(pad):
+                Hp, Wp = flow_up.shape[1:3]
+                return flow_up[:, pad[2]:Hp - pad[3], pad[0]:Wp - pad[1]].contiguous()
+            return flow_up.clone() if self.use_cuda_graph else flow_up
         im1 = img1.permute(0, 3, 1, 2).float()
         im2 = img2.permute(0, 3, 1, 2).float()
         padder = InputPadder(im1.shape)

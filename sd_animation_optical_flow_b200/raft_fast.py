@@ -200,8 +200,9 @@ class FastRaft:
         return st
 
     @torch.no_grad()
-    def forward(self, image1: torch.Tensor, image2: torch.Tensor, iters: int = 20):
-        """image1/2: [B,3,H,W] float 0..255 (H, W multiples of 8).  Returns (flow_low [B,h,w,2], flow_up [B,H,W,2]).
+    def forward(self, image1: torch.Tensor, image2: torch.Tensor, iters: int = 20, normalized: bool = False):
+        """image1/2: [B,3,H,W] float 0..255 (H, W multiples of 8), or with normalized=True already 2*(x/255)-1 (any memory
+        format; ops.normalize_pad_u8 hands over channels-last).  Returns (flow_low [B,h,w,2], flow_up [B,H,W,2]).
 
         Two independent chains run on a side stream (fork/join with events, so a CUDA-graph capture records them as
         parallel branches): the context encoder next to the feature encoder + correlation pyramid, and in every
@@ -216,8 +217,11 @@ class FastRaft:
         xc = cdim + 128                                                   # x = [inp | motion(126) | flow(2)]
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.side_streams else main
-        im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
-        im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        if normalized:
+            im1, im2 = image1, image2
+        else:
+            im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+            im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128]
         HX = torch.empty((B, h, w, hd + xc), device=dev)                 # [h | x]        (update.py:47)
         RHX = torch.empty_like(HX)                                        # [r*h | x]      (update.py:50)

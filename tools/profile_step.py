@@ -32,13 +32,31 @@ else:
     f1 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
     f2 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
     coords = coords_grid(1, 96, 64, dev) + 2 * torch.randn((1, 2, 96, 64), generator=g, device=dev)
+    coords_nhwc = coords.permute(0, 2, 3, 1).contiguous()
+    look_nhwc = torch.empty((1, 96, 64, 324), device=dev)
     src = torch.randint(0, 256, (32, 768, 512, 3), dtype=torch.uint8, device=dev)
-    flow = torch.nn.functional.interpolate(torch.randn((32, 2, 96, 64), generator=g, device=dev) * 6, scale_factor=8, mode='bilinear',
-                                           align_corners=False).permute(0, 2, 3, 1).contiguous()
+    # the flows bench.py uses: translation + low-frequency deformation
+    flow = (torch.nn.functional.interpolate(torch.randn((32, 2, 12, 8), generator=g, device=dev) * 4, scale_factor=64, mode='bicubic',
+                                            align_corners=False)
+            + 6 * torch.randn((32, 2, 1, 1), generator=g, device=dev)).permute(0, 2, 3, 1).contiguous()
     wm = torch.randn((32, 2, 768, 512), generator=g, device=dev) * 3
+    act = torch.randn((2, 64, 384, 256), generator=g, device=dev).contiguous(memory_format=torch.channels_last)   # fnet layer-1 size
+    lowflow = torch.randn((1, 96, 64, 2), generator=g, device=dev)
+    w7 = torch.randn((7, 7, 2, 128), generator=g, device=dev)
+    b7 = torch.randn((128,), generator=g, device=dev)
+    x256 = torch.relu(torch.randn((1, 96, 64, 256), generator=g, device=dev))
+    w2 = torch.randn((3, 3, 2, 256), generator=g, device=dev) * 0.05
+    c1 = coords_nhwc.clone()
+    fl = torch.empty((1, 96, 64, 2), device=dev)
+    mask = (torch.rand((32, 768, 512), generator=g, device=dev) < 0.3).to(torch.uint8) * 255
     for _ in range(3):
         pyr = ops.corr_volume_pyramid(f1, f2, 4, prec)
         ops.corr_lookup(pyr, coords, 4)
+        ops.corr_lookup_nhwc(pyr, coords_nhwc, 4, look_nhwc)
         ops.warp(src, flow)
         ops.warp_mask_composite(src[:1], src, flow, wm, 0.95, 7)
+        ops.instnorm_nhwc(act, torch.zeros((2 * 64 * 2,), dtype=torch.float64, device=dev))
+        ops.conv7x7_c2_relu(lowflow, w7, b7)
+        ops.flowhead2_update(x256, w2, (0.1, 0.2), c1, fl, None, 0, None, 0)
+        ops.mask_blur_composite(mask, src, src.flip(0), 4.0)
     torch.cuda.synchronize()
