@@ -346,6 +346,32 @@ def run_ours(args):
     batched = {'pairs_per_step': P, 'ms_per_step': t_b * 1e3, 'value': P / t_b, 'unit': UNIT, 'n_gpus': 1,
                'note': 'device-resident, one GPU (rank 0), CUDA graph' if not args.no_graph else 'device-resident, one GPU (rank 0)'}
 
+    # ---- configs[2] in miniature: a 32-frame clip against its key frame, all on the device: flow + confidence (RAFT has
+    # no confidence head: forward-backward consistency, i.e. two flow passes per pair) -> 7x7-dilated
+    # low-confidence mask -> cubic warp of the stylised key frame composited over the frame, 8 pairs per call
+    from sd_animation_optical_flow_b200 import pdcnet_of
+    from sd_animation_optical_flow_b200.engine import RaftFlowConfidence
+    from tests import golden_inputs as gi
+    algo3 = pdcnet_of.PDCNetPlus(network=RaftFlowConfidence(eng))
+    canvas = gi.texture(H + 64, W + 64, 4242)
+    clip = torch.from_numpy(np.stack([canvas[(3 * i) % 48:(3 * i) % 48 + H, (5 * i) % 56:(5 * i) % 56 + W] for i in range(32)])).to(dev)
+    key8, sty8 = clip[:1].expand(P, -1, -1, -1).contiguous(), dsty
+
+    def clip_pass():
+        outs = []
+        for i0 in range(1, 32, P):
+            tgt = clip[i0:i0 + P]
+            if tgt.shape[0] < P:                                    # keep one graph shape: pad the last call
+                tgt = torch.cat([tgt, clip[-1:].expand(P - tgt.shape[0], -1, -1, -1)], 0)
+            flow_c, wm_c = algo3._estimate(key8, tgt.contiguous())
+            outs.append(ops.warp_mask_composite(sty8, tgt.contiguous(), flow_c, wm_c, 0.95, 7))
+        return outs
+
+    t_clip = time_op(clip_pass, 2, torch)
+    clip_leg = {'workload': 'configs[2] shape: 32-frame 768x512 clip vs its key frame: flow + forward-backward confidence + dilated mask + composite',
+                'pairs': 31, 'pairs_per_call': P, 'ms_per_clip': t_clip * 1e3, 'value': 31 / t_clip, 'unit': UNIT, 'n_gpus': 1,
+                'note': 'two RAFT passes per pair (confidence by forward-backward consistency); device-resident'}
+
     cpu = cpu_baseline_leg(args.cpu_budget_s) if args.cpu_budget_s > 0 else None
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -355,7 +381,7 @@ def run_ours(args):
                        'conv_precision': 'bf16 autocast' if args.mixed_precision else 'cuDNN fp32 (TF32 allowed, torch default)',
                        'cuda_graph': not args.no_graph, 'pairs_per_step_per_gpu': 1, 'parallelism': f'pairs x{world}, no collective',
                        'l2': 'per-step working set (200.5 MB pyramid rewritten every step + activations) exceeds the 126 MB L2; no explicit flush'},
-            'roofline': roofline, 'roofline_extra': extra, 'batched': batched, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
+            'roofline': roofline, 'roofline_extra': extra, 'batched': batched, 'clip': clip_leg, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
             'gpu_launches': int(launches),
             'gpu_launches_note': f'{launches_per_step} libsdof_b200 kernels per step (counted on an eager step) x {args.steps} steps'
                                  + ('; CUDA-graph replays re-run the captured launches' if not args.no_graph else '')}

@@ -47,26 +47,41 @@ constexpr int kBlurThreads = 256;
 
 // One extended-box pass along x (kVert = false) or y (kVert = true) over the rectangle [x0,x1) x [y0,y1) of the
 // staged region (region coordinates; gx0/gy0 = image coordinates of region (0,0); pitch = region row pitch).
+// A thread owns a run of kBoxRun outputs along the pass direction and slides the box sum: two shared-memory loads per
+// output instead of 2*radius+3.  Lanes map to consecutive rows (horizontal pass) / columns (vertical pass).
+constexpr int kBoxRun = 16;
+
 template <bool kVert>
 __device__ __forceinline__ void box_pass(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int pitch,
                                          int x0, int x1, int y0, int y1, int gx0, int gy0, int W, int H, BoxParams bp) {
-  const int w = x1 - x0, n = w * (y1 - y0);
   const int r = bp.radius;
-  for (int i = threadIdx.x; i < n; i += kBlurThreads) {
-    const int ry = y0 + i / w, rx = x0 + i % w;
-    unsigned acc = 0, far;
-    if (kVert) {
-      const int gy = gy0 + ry;
-      for (int d = -r; d <= r; ++d) acc += in[(min(max(gy + d, 0), H - 1) - gy0) * pitch + rx];
-      far = (unsigned)in[(min(max(gy - r - 1, 0), H - 1) - gy0) * pitch + rx] + in[(min(max(gy + r + 1, 0), H - 1) - gy0) * pitch + rx];
-    } else {
-      const int gx = gx0 + rx;
-      const unsigned char* row = in + ry * pitch - gx0;
-      for (int d = -r; d <= r; ++d) acc += row[min(max(gx + d, 0), W - 1)];
-      far = (unsigned)row[min(max(gx - r - 1, 0), W - 1)] + row[min(max(gx + r + 1, 0), W - 1)];
+  // along = pass direction, across = the other one
+  const int a0 = kVert ? y0 : x0, a1 = kVert ? y1 : x1;
+  const int c0 = kVert ? x0 : y0, c1 = kVert ? x1 : y1;
+  const int ga0 = kVert ? gy0 : gx0;            // image coordinate of region 0 along the pass
+  const int gmax = (kVert ? H : W) - 1;
+  const int step = kVert ? pitch : 1;           // byte step along the pass
+  const int nacross = c1 - c0;
+  const int nruns = (a1 - a0 + kBoxRun - 1) / kBoxRun;
+  for (int i = threadIdx.x; i < nacross * nruns; i += kBlurThreads) {
+    const int run = i / nacross, c = c0 + (i - run * nacross);
+    const int s0 = a0 + run * kBoxRun, s1 = min(s0 + kBoxRun, a1);
+    // line(k) = value at IMAGE coordinate k along the pass (clamped = edge replication), on this thread's row / column
+    const unsigned char* base = in + (kVert ? c : c * pitch) - ga0 * step;
+#define SDOF_LINE(k) ((unsigned)base[min(max((k), 0), gmax) * step])
+    int g = ga0 + s0;
+    unsigned acc = 0;
+    for (int d = -r; d <= r; ++d) acc += SDOF_LINE(g + d);
+    unsigned left = SDOF_LINE(g - r - 1);
+    unsigned char* o = out + (kVert ? s0 * pitch + c : c * pitch + s0);
+    for (int sidx = s0; sidx < s1; ++sidx, ++g, o += step) {
+      const unsigned right = SDOF_LINE(g + r + 1);
+      const unsigned bulk = acc * bp.ww + (left + right) * bp.fw;  // UINT32 arithmetic as in Pillow
+      *o = (unsigned char)((bulk + (1u << 23)) >> 24);
+      left = SDOF_LINE(g - r);
+      acc += right - left;
     }
-    const unsigned bulk = acc * bp.ww + far * bp.fw;  // UINT32 arithmetic as in Pillow
-    out[ry * pitch + rx] = (unsigned char)((bulk + (1u << 23)) >> 24);
+#undef SDOF_LINE
   }
 }
 
@@ -78,7 +93,7 @@ __device__ __forceinline__ unsigned div255(unsigned a) {
 // mask [B,H,W]; image, reference, out [B,H,W,C] (image/reference/out may be NULL: blur only); blurred [B,H,W].
 __global__ void __launch_bounds__(kBlurThreads) blur_composite_kernel(const unsigned char* __restrict__ mask, const unsigned char* __restrict__ image,
                                                                       const unsigned char* __restrict__ reference, int H, int W, int C,
-                                                                      BoxParams bp, int passes, int TW, int TH, int pitch,
+                                                                      BoxParams bp, int passes, int TW, int TH, int pitch, int vec_ok,
                                                                       unsigned char* __restrict__ blurred, unsigned char* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char bl_smem[];
   const int halo = passes * (bp.radius + 1);
@@ -90,9 +105,9 @@ __global__ void __launch_bounds__(kBlurThreads) blur_composite_kernel(const unsi
   unsigned char* buf0 = bl_smem;
   unsigned char* buf1 = bl_smem + (size_t)pitch * (TH + 2 * halo);
   const unsigned char* mb = mask + (int64_t)b * H * W;
-  for (int i = threadIdx.x; i < rw * rh; i += kBlurThreads) {
-    const int ry = i / rw, rx = i - ry * rw;
-    buf0[ry * pitch + rx] = mb[(int64_t)(gy0 + ry) * W + gx0 + rx];
+  for (int ry = threadIdx.x >> 5; ry < rh; ry += kBlurThreads / 32) {  // a warp per staged row: coalesced byte loads
+    const unsigned char* srow = mb + (int64_t)(gy0 + ry) * W + gx0;
+    for (int rx = threadIdx.x & 31; rx < rw; rx += 32) buf0[ry * pitch + rx] = srow[rx];
   }
   __syncthreads();
   unsigned char* cur = buf0;
@@ -118,6 +133,34 @@ __global__ void __launch_bounds__(kBlurThreads) blur_composite_kernel(const unsi
   // write the blurred tile and composite
   const int ox = tx0 - gx0, oy = ty0 - gy0;
   const int tw = min(TW, W - tx0), th = min(TH, H - ty0);
+  if (vec_ok && C == 3 && (tw & 3) == 0) {
+    // 4 pixels per thread: 12 image + 12 reference bytes as aligned words (W % 4 == 0, TW % 4 == 0, aligned pointers)
+    const int tw4 = tw >> 2;
+    for (int i = threadIdx.x; i < tw4 * th; i += kBlurThreads) {
+      const int ly = i / tw4, lx = (i - ly * tw4) * 4;
+      const unsigned char* mrow = cur + (oy + ly) * pitch + ox + lx;
+      const unsigned m[4] = {mrow[0], mrow[1], mrow[2], mrow[3]};
+      const int64_t p = ((int64_t)b * H + ty0 + ly) * W + tx0 + lx;
+      if (blurred) *reinterpret_cast<unsigned*>(blurred + p) = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+      if (out) {
+        const unsigned* iw = reinterpret_cast<const unsigned*>(image + p * 3);
+        const unsigned* rw_ = reinterpret_cast<const unsigned*>(reference + p * 3);
+        unsigned* ow = reinterpret_cast<unsigned*>(out + p * 3);
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const unsigned iv = __ldcs(iw + w), rv = __ldcs(rw_ + w);
+          unsigned res = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned mm = m[(w * 4 + k) / 3];
+            res |= div255(((iv >> (8 * k)) & 0xff) * (255u - mm) + ((rv >> (8 * k)) & 0xff) * mm) << (8 * k);
+          }
+          __stcs(ow + w, res);
+        }
+      }
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < tw * th; i += kBlurThreads) {
     const int ly = i / tw, lx = i - ly * tw;
     const unsigned m = cur[(oy + ly) * pitch + ox + lx];
@@ -249,7 +292,10 @@ int sdof_mask_blur_composite(const uint8_t* mask, const uint8_t* image, const ui
   SDOF_REQUIRE(smem <= 220 * 1024, "sdof_mask_blur_composite: mask_blur %.2f needs %zu bytes of shared memory", mask_blur, smem);
   SDOF_CUDA(cudaFuncSetAttribute(blur_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(W, TW), ceil_div(H, TH), B);
-  blur_composite_kernel<<<grid, kBlurThreads, smem, as_stream(stream)>>>(mask, image, reference, H, W, C, bp, passes, TW, TH, pitch, blurred, out);
+  const int vec_ok = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(reference) |
+                                       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(blurred)) & 3) == 0;
+  blur_composite_kernel<<<grid, kBlurThreads, smem, as_stream(stream)>>>(mask, image, reference, H, W, C, bp, passes, TW, TH, pitch, vec_ok,
+                                                                        blurred, out);
   SDOF_LAUNCH_CHECK("blur_composite_kernel");
   return SDOF_OK;
 }

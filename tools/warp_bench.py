@@ -49,3 +49,19 @@ for (B, H, W) in ((32, 768, 512), (1, 768, 512), (16, 720, 1280)):
             print(f'warp_mask_composite B={B:2d} {H}x{W} flow={name:8s} {t * 1e6:8.1f} us  {gbs:7.1f} GB/s  {gbs / HBM * 100:5.1f}% of HBM peak')
     t = timeit(lambda: ops.warp(src, flow, 'bilinear'))
     print(f'warp_bilinear_u8  B={B:2d} {H}x{W} {t * 1e6:8.1f} us')
+
+# after-the-path step: mask blur + composite (11 B/pixel) and the latent-mask resize
+B, H, W = 32, 768, 512
+src = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev)
+ref = src.flip(0).contiguous()
+mask = ((torch.rand((B, H // 16, W // 16), generator=g, device=dev) < 0.3).to(torch.uint8) * 255).repeat_interleave(16, 1).repeat_interleave(16, 2).contiguous()
+for blur in (4.0, 12.0):
+    t = timeit(lambda: ops.mask_blur_composite(mask, src, ref, blur))
+    gbs = 11.0 * B * H * W / t / 1e9
+    print(f'blur_composite    B={B:2d} {H}x{W} mask_blur={blur:4.1f} {t * 1e6:8.1f} us  {gbs:7.1f} GB/s  {gbs / HBM * 100:5.1f}% of HBM peak')
+t = timeit(lambda: ops.resize_bicubic_u8(mask, H // 8, W // 8, want_latmask=True), 5)
+print(f'resize_bicubic_u8 B={B:2d} {H}x{W} -> {H // 8}x{W // 8} {t * 1e6:8.1f} us (includes the host-built coefficient tables and one stream sync)')
+frame = src[0].contiguous()
+from sd_animation_optical_flow_b200 import ofgen  # noqa: E402
+t = timeit(lambda: ofgen.detect_edges_device(frame), 5)
+print(f'detect_edges      768x512 {t * 1e6:8.1f} us per frame (V + histogram + thresholds + Canny + hysteresis relaunches + dilation)')
