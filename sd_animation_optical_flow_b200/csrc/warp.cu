@@ -100,10 +100,22 @@ __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = cubic_u8_c3_outlined(tab, img, old_src_end, Hs, Ws, px.sx[k], px.sy[k], px.fid[k]);
     }
+    if (seg_full && gy0 + 4 <= H) {
+      // common case, straight-line: 4 full rows, each 24 words (W % 4 == 0, so a row is W*3/4 words)
+      unsigned* op = reinterpret_cast<unsigned*>(orow) + lane;
+      const unsigned row_words = (unsigned)(W * 3) >> 2;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (gy0 + k >= H) break;  // warp-uniform
-      wt_store_row(orow + (unsigned)(k * W * 3), v[k], lane, pk, seg_full, lane_valid);
+      for (int k = 0; k < 4; ++k) {
+        const unsigned a = __shfl_sync(0xffffffffu, v[k], pk.p);
+        const unsigned b2 = __shfl_sync(0xffffffffu, v[k], pk.p + 1);
+        if (lane < 24) __stcs(op + k * row_words, (a >> pk.sh) | (b2 << (24u - pk.sh)));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (gy0 + k >= H) break;  // warp-uniform
+        wt_store_row(orow + (unsigned)(k * W * 3), v[k], lane, pk, seg_full, lane_valid);
+      }
     }
     if (t_next >= T.ntiles) break;
     t = t_next;

@@ -191,3 +191,27 @@ def test_batched_pairs_equal_single_pairs(cuda):
     both = eng.estimate_flow(a, b)
     one = eng.estimate_flow(a[1:], b[1:])
     assert float((both[1:] - one).abs().max()) <= 2e-3
+
+
+def test_config5_size_fast_path_equals_module_forward(cuda):
+    """720x1280 (90x160 features, N = 14400: partial correlation tiles, odd pooled sizes 45x80 / 22x40 / 11x20) through
+    the uint8 fast path with a CUDA graph vs the plain module forward; tolerance as above (EPE <= 2e-3 mean)."""
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    f1, f2 = gi.shifted_pair(720, 1280, 77, dx=5, dy=-2)
+    a = torch.from_numpy(f1).to(cuda)[None]
+    b = torch.from_numpy(f2).to(cuda)[None]
+    fast = RaftEngine(checkpoint=None, iters=6, seed=1, device=cuda, corr_precision='3xtf32', use_cuda_graph=True)
+    slow = RaftEngine(checkpoint=None, iters=6, seed=1, device=cuda, corr_precision='3xtf32', fast=False)
+    ff = fast.estimate_flow(a, b)
+    fs = slow.estimate_flow(a, b)
+    assert ff.shape == fs.shape == (1, 720, 1280, 2)
+    d = (ff - fs).norm(dim=-1)
+    print(f'720x1280 fast vs module: EPE mean {float(d.mean()):.2e} max {float(d.max()):.2e}')
+    assert float(d.mean()) <= 2e-3 and float(d.max()) <= 5e-2
+    assert torch.allclose(fast.estimate_flow(a, b), ff, atol=1e-5)     # graph replay
+    # a frame size that needs padding (InputPadder) through the fused normalise+pad kernel
+    g1, g2 = gi.shifted_pair(250, 333, 78)
+    c, d2 = torch.from_numpy(g1).to(cuda)[None], torch.from_numpy(g2).to(cuda)[None]
+    e = (fast.estimate_flow(c, d2) - slow.estimate_flow(c, d2)).norm(dim=-1)
+    assert fast.estimate_flow(c, d2).shape == (1, 250, 333, 2) and float(e.mean()) <= 2e-3
+    assert fast.estimate_flow(c, d2, unpad=False).shape == (1, 256, 336, 2)
