@@ -102,6 +102,7 @@ class ClockSampler:
 
 def cpu_baseline_leg(budget_s: float):
     from oracle import farneback_baseline as fb
+    fb.use_all_host_threads()
     f1, f2, sty = synthetic_pair(0)
     bgr = lambda a: a[:, :, ::-1].copy()
     rate, n, times = fb.time_pairs(bgr(f1), bgr(f2), bgr(sty), budget_s=budget_s)
@@ -118,6 +119,7 @@ def run_reference(args):
     if int(os.environ.get('RANK', '0')) != 0:
         return
     from oracle import farneback_baseline as fb
+    fb.use_all_host_threads()
     f1, f2, sty = synthetic_pair(0)
     bgr = lambda a: a[:, :, ::-1].copy()
     a, b, c = bgr(f1), bgr(f2), bgr(sty)
@@ -315,8 +317,8 @@ def run_ours(args):
     corr_gbs = (in_bytes + out_bytes) / t_corr / 1e9
     roofline = {'kernel': corr_kernel + ', 1 pair, N=6144, C=256, 4 levels', 'us_per_op_with_prepass': t_corr_op * 1e6, 'bound': 'hbm',
                 'achieved': corr_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': corr_gbs / hbm,
-                'traffic': 151629824 if args.corr_precision == 'fp16' else None,
-                'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_kernels_ncu_summary.txt); below the algorithmic bytes because part of the 200 MB pyramid is still dirty in the 126 MB L2 when the kernel ends',
+                'traffic': 152921088 if args.corr_precision == 'fp16' else None,
+                'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1b_kernels_ncu_summary.txt: 8.84 MB read + 144.08 MB written); below the algorithmic bytes because part of the 200 MB pyramid is still dirty in the 126 MB L2 when the kernel ends',
                 'peak_source': peaks['source'], 'us_per_launch': t_corr * 1e6,
                 'algorithmic_bytes': in_bytes + out_bytes}
     tf = corr_flops / t_corr / 1e12

@@ -252,9 +252,10 @@ int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* r
                              float eps, int relu, sdof_stream_t stream);
 int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stream_t stream);
 /* Input side of RAFT_2.calc / RAFT.forward (ofgen.py:72-76, RAFT/core/raft.py:89-90, utils/utils.py:7-19) in one pass:
- * img u8 [B,H,W,3] -> out f32 [B,Hp,Wp,3] (NHWC) = 2*(x/255)-1 of the replicate-padded frame; pixel (y,x) of out reads
- * img at (clamp(y-top), clamp(x-left)). */
-int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, float* out,
+ * img u8 [B,H,W,3] -> out f32 [B,Hp,Wp,Cout] (NHWC) = 2*(x/255)-1 of the replicate-padded frame; pixel (y,x) of out reads
+ * img at (clamp(y-top), clamp(x-left)).  Cout = 3, or 4 with a zero fourth channel (lets cuDNN run the 7x7 stem
+ * convolution on tensor cores with a zero-padded filter). */
+int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, int Cout, float* out,
                                sdof_stream_t stream);
 /* The two convolutions of the update block that are too small / too thin for a tensor-core library kernel:
  *   sdof_conv7x7_c2_relu : BasicMotionEncoder.convf1 (RAFT/core/update.py:85,93): out[B,h,w,128] =

@@ -38,6 +38,16 @@ def flow_and_warp(frame1_bgr, frame2_bgr, stylised_bgr):
     return flow, grid_sample_warp(stylised_bgr, flow)
 
 
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host thread it can."""
+    import cv2
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    cv2.setNumThreads(n)
+    return n
+
+
 def host_info():
     import cv2
     import torch

@@ -120,8 +120,8 @@ class RaftEngine:
     def _forward_u8(self, a: torch.Tensor, b: torch.Tensor, pad) -> torch.Tensor:
         """uint8 RGB [B,H,W,3] x2 -> padded-size flow [B,Hp,Wp,2]: one kernel normalises + pads each frame straight into
         the channels-last layout the encoders consume (csrc/raft_glue.cu::normalize_pad_u8_nhwc_kernel)."""
-        im1 = ops.normalize_pad_u8(a, pad)
-        im2 = ops.normalize_pad_u8(b, pad)
+        im1 = ops.normalize_pad_u8(a, pad, channels=4)
+        im2 = ops.normalize_pad_u8(b, pad, channels=4)
         _, flow_up = self.fast.forward(im1, im2, self.iters, normalized=True)
         return flow_up
 

@@ -64,6 +64,10 @@ class FastEncoder:
         if self.kind not in ('instance', 'batch', 'none'):
             raise ValueError(f'unsupported norm {self.kind}')
         self.stem = self._layer(enc.conv1, enc.norm1)
+        # 3 -> 4 input channels (zero filter plane): cuDNN's tensor-core NHWC kernels need C % 4 == 0; with 3 channels the
+        # 7x7 stem runs on a CUDA-core engine (266 us per pair in the round-1 launch list)
+        w, b, st, pd = self.stem
+        self.stem = (torch.cat([w, w.new_zeros((w.shape[0], 1, *w.shape[2:]))], 1).contiguous(memory_format=CL), b, st, pd)
         self.units = []
         for layer in (enc.layer1, enc.layer2, enc.layer3):
             for u in layer:
@@ -113,6 +117,8 @@ class FastEncoder:
         return y
 
     def __call__(self, x):
+        if x.shape[1] == 3:   # callers on the fast path already hand over 4 channels (ops.normalize_pad_u8(.., channels=4))
+            x = F.pad(x, (0, 0, 0, 0, 0, 1))
         x = x.contiguous(memory_format=CL)
         if self.kind == 'instance':
             # one zeroed fp64 scratch for the statistics of every norm layer of this pass
