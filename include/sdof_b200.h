@@ -295,6 +295,12 @@ int sdof_abs_diff_sum_u8(const uint8_t* a, const uint8_t* b, int64_t n, unsigned
 int sdof_mask_blur_composite(const uint8_t* mask, const uint8_t* image, const uint8_t* reference, int B, int H, int W, int C,
                              float mask_blur, uint8_t* blurred, uint8_t* out, sdof_stream_t stream);
 int64_t sdof_resize_bicubic_workspace_bytes(int B, int H, int W, int oh, int ow);
+/* Host-side tables behind the two calls above (no GPU needed; pinned against Pillow by the CPU tests):
+ *   sdof_box_blur_params: out3 = {radius, ww, fw} of the extended box for GaussianBlur(mask_blur) (BoxBlur.c);
+ *   sdof_resample_table : per output pixel bounds[2*i] = first input pixel, bounds[2*i+1] = tap count, and
+ *                         coeffs[i*ksize + k] = 22-bit coefficients (Resample.c::precompute_coeffs + normalize_coeffs_8bpc). */
+int sdof_box_blur_params(float mask_blur, int32_t* out3);
+int sdof_resample_table(int in_size, int out_size, int32_t* ksize, int32_t* bounds, int32_t* coeffs, int64_t coeffs_cap);
 int sdof_resize_bicubic_u8(const uint8_t* src, int B, int H, int W, int oh, int ow, uint8_t* dst, float* latmask, void* workspace,
                            int64_t workspace_bytes, sdof_stream_t stream);
 

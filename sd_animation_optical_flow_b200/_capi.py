@@ -80,6 +80,8 @@ SIGNATURES = {
     'sdof_abs_diff_sum_u8': (c_int, [_P, _P, c_int64, _P, _P]),
     'sdof_mask_blur_composite': (c_int, [_P, _P, _P] + [c_int] * 4 + [c_float, _P, _P, _P]),
     'sdof_resize_bicubic_workspace_bytes': (c_int64, [c_int] * 5),
+    'sdof_box_blur_params': (c_int, [c_float, POINTER(c_int32)]),
+    'sdof_resample_table': (c_int, [c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int64]),
     'sdof_resize_bicubic_u8': (c_int, [_P] + [c_int] * 5 + [_P, _P, _P, c_int64, _P]),
     'sdof_warp_mask_composite': (c_int, [_P, _P, _P, _P] + [c_int] * 4 + [c_float, c_int, _P, _P, _P]),
 }

@@ -300,6 +300,28 @@ int sdof_mask_blur_composite(const uint8_t* mask, const uint8_t* image, const ui
   return SDOF_OK;
 }
 
+// Host-side tables, exported so the CPU test-suite can pin them against Pillow's without a GPU.
+int sdof_box_blur_params(float mask_blur, int32_t* out3) {
+  using namespace sdof;
+  SDOF_REQUIRE(out3 && mask_blur >= 0.f, "sdof_box_blur_params: bad arguments");
+  const BoxParams bp = gaussian_box_params(mask_blur, 3);
+  out3[0] = bp.radius;
+  out3[1] = (int32_t)bp.ww;
+  out3[2] = (int32_t)bp.fw;
+  return SDOF_OK;
+}
+
+int sdof_resample_table(int in_size, int out_size, int32_t* ksize, int32_t* bounds, int32_t* coeffs, int64_t coeffs_cap) {
+  using namespace sdof;
+  SDOF_REQUIRE(in_size >= 1 && out_size >= 1 && ksize && bounds && coeffs, "sdof_resample_table: bad arguments");
+  const ResampleTable t = precompute_coeffs(in_size, out_size);
+  SDOF_REQUIRE((int64_t)t.coeffs.size() <= coeffs_cap, "sdof_resample_table: coeffs_cap %lld < %zu", (long long)coeffs_cap, t.coeffs.size());
+  *ksize = t.ksize;
+  for (size_t i = 0; i < t.bounds.size(); ++i) bounds[i] = t.bounds[i];
+  for (size_t i = 0; i < t.coeffs.size(); ++i) coeffs[i] = t.coeffs[i];
+  return SDOF_OK;
+}
+
 int64_t sdof_resize_bicubic_workspace_bytes(int B, int H, int W, int oh, int ow) {
   if (B < 0 || H < 1 || W < 1 || oh < 1 || ow < 1) return -1;
   const sdof::ResampleTable th = sdof::precompute_coeffs(W, ow), tv = sdof::precompute_coeffs(H, oh);

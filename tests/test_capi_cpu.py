@@ -119,3 +119,28 @@ def test_product_never_imports_oracle():
             if fn.endswith('.py'):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f'{fn} imports the oracle'
+
+
+def test_blur_and_resample_host_tables_match_the_oracle(lib):
+    """The host-side tables of csrc/blur.cu (Pillow's box-blur weights and resample coefficients) against the oracle's,
+    which tests/test_oracle_blur.py pins against Pillow itself.  No GPU needed."""
+    import ctypes
+
+    import numpy as np
+
+    from oracle import blur_oracle as bo
+    out3 = (ctypes.c_int32 * 3)()
+    for r in (0.0, 0.1, 0.5, 1, 2, 3.3, 4, 5.5, 8, 12, 30, 64):
+        assert lib.sdof_box_blur_params(float(r), out3) == 0
+        want = bo.box_weights(bo.gaussian_box_radius(r))
+        assert tuple(np.uint32(v) for v in out3) == tuple(np.uint32(v) for v in want), (r, list(out3), want)
+    for (n_in, n_out) in ((768, 96), (512, 64), (1280, 160), (720, 90), (100, 12), (60, 7), (16, 16), (40, 80), (9, 1)):
+        bounds, coeffs = bo.resample_coeffs(n_in, n_out)
+        kmax = 64 * max(1, -(-n_in // n_out)) + 8
+        b = (ctypes.c_int32 * (2 * n_out))()
+        c = (ctypes.c_int32 * (n_out * kmax))()
+        ks = ctypes.c_int32()
+        assert lib.sdof_resample_table(n_in, n_out, ctypes.byref(ks), b, c, n_out * kmax) == 0
+        for i in range(n_out):
+            assert b[2 * i] == bounds[i] and b[2 * i + 1] == len(coeffs[i]), (n_in, n_out, i)
+            assert list(c[i * ks.value:i * ks.value + len(coeffs[i])]) == [int(v) for v in coeffs[i]], (n_in, n_out, i)
