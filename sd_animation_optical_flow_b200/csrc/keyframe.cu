@@ -12,7 +12,7 @@
 //                          and the two thresholds in the reference's double arithmetic
 //   canny_nms_kernel     : 3x3 Sobel (replicated border), L1 magnitude, non-maximum suppression with OpenCV's
 //                          fixed-point tangent test (TG22 = 13573, shift 15); state 2 = strong, 0 = candidate, 1 = no edge
-//   canny_hysteresis_kernel : candidates 8-connected to a strong pixel become strong; a CTA iterates its 32x32 tile
+//   canny_hysteresis_kernel : candidates 8-connected to a strong pixel become strong; a CTA iterates its 32x32 tile (Jacobi sweeps)
 //                          (+1 halo) to a local fixed point in shared memory; the host relaunches until no tile changes
 //   edges_dilate_kernel  : 255 where strong, then the k x k rectangular dilation
 //   abs_diff_sum_kernel  : integer sum of |a - b| (mean_pixel_distance numerator)
@@ -129,18 +129,25 @@ __global__ void __launch_bounds__(256) canny_hysteresis_kernel(unsigned char* __
   __syncthreads();
   bool any = false;
   for (;;) {
-    int ch = 0;
-    for (int i = threadIdx.x; i < kCnT * kCnT; i += blockDim.x) {
+    // Jacobi sweep: all reads of this sweep happen before any write (no shared-memory race), 4 pixels per thread
+    bool upd[kCnT * kCnT / 256];
+#pragma unroll
+    for (int k = 0; k < kCnT * kCnT / 256; ++k) {
+      const int i = threadIdx.x + k * 256;
       const int ly = i / kCnT + 1, lx = i % kCnT + 1;
-      if (s[ly][lx] == 0) {
-        const bool strong = s[ly - 1][lx - 1] == 2 || s[ly - 1][lx] == 2 || s[ly - 1][lx + 1] == 2 || s[ly][lx - 1] == 2 ||
-                            s[ly][lx + 1] == 2 || s[ly + 1][lx - 1] == 2 || s[ly + 1][lx] == 2 || s[ly + 1][lx + 1] == 2;
-        if (strong) {
-          s[ly][lx] = 2;  // monotone 0 -> 2: a concurrent reader seeing either value stays correct
-          ch = 1;
-        }
-      }
+      upd[k] = s[ly][lx] == 0 &&
+               (s[ly - 1][lx - 1] == 2 || s[ly - 1][lx] == 2 || s[ly - 1][lx + 1] == 2 || s[ly][lx - 1] == 2 ||
+                s[ly][lx + 1] == 2 || s[ly + 1][lx - 1] == 2 || s[ly + 1][lx] == 2 || s[ly + 1][lx + 1] == 2);
     }
+    __syncthreads();
+    int ch = 0;
+#pragma unroll
+    for (int k = 0; k < kCnT * kCnT / 256; ++k)
+      if (upd[k]) {
+        const int i = threadIdx.x + k * 256;
+        s[i / kCnT + 1][i % kCnT + 1] = 2;
+        ch = 1;
+      }
     if (!__syncthreads_or(ch)) break;
     any = true;
   }
