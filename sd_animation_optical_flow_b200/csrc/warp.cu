@@ -33,7 +33,7 @@ int get_cubic_tables(CubicTables* out) {
 }
 
 // ---------------------------------------------------------------- cubic, u8, C = 3
-// Persistent CTAs (one per SM, 8 groups of 128 threads); a group walks 32x16 output tiles
+// Persistent CTAs (one per SM, 3 groups of 256 threads); a group walks 32x32 output tiles
 // (warp_tiled.cuh).  `old_src_end` is the bound of the per-pixel fallback path (cubic_u8_c3).
 __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
     const int16_t* __restrict__ tab, const unsigned char* __restrict__ src, const float* __restrict__ flow,

@@ -3,7 +3,7 @@
 // The per-pixel gather of cv2.remap (16 taps x 3 interleaved channels at an arbitrary byte
 // alignment + a 32-byte weight row) is LSU/issue-bound when every tap comes from global memory
 // (round-1 ncu: L1TEX 66-82 %, 330 instructions per pixel, 11 % of the HBM roofline).  Here a
-// 128-thread GROUP owns a 32x16 output tile:
+// 256-thread GROUP owns a 32x32 output tile:
 //
 //   A. every lane loads the flow of its 4 pixels (lane = x, 4 rows per warp; the NEXT tile's flow is
 //      prefetched into registers), quantises the sampling coordinates exactly like OpenCV (1/32 px)
@@ -19,9 +19,10 @@
 //      conflict-free), and a warp packs its 32 pixels x 3 bytes into 24 words with two shuffles
 //      for one coalesced 96-byte store.
 //
-// Eight groups share one CTA (one CTA per SM, persistent over tiles) so the weight table is
+// Three groups share one CTA (one CTA per SM, persistent over tiles) so the weight table is
 // loaded into shared memory once per SM and the groups' load phases overlap each other's
-// arithmetic (a group with 4 groups of 256 threads measured latency-bound: 6 us per tile).  A tile whose bounding box does not fit the group's region (non-smooth flow,
+// arithmetic.  Measured group shapes (32 frames 768x512, zero / smooth / sheared flow, us): 12 x 64 threads
+// 122/156/208, 6 x 128: 108/145/175, 4 x 256 (64 registers): 116/152/177, 3 x 256: 104/141/164, 2 x 384: 123/159/181.  A tile whose bounding box does not fit the group's region (non-smooth flow,
 // NaN / far out-of-image samples) falls back to the per-pixel global-memory path (warp.cuh).
 #pragma once
 
@@ -29,13 +30,13 @@
 
 namespace sdof {
 
-constexpr int kWtGroups = 6;            // independent groups per CTA (named barriers 1..6); 768 threads leave 85 registers per thread
-constexpr int kWtGroupWarps = 4;        // warp w owns tile rows 4w..4w+3, lane = x
+constexpr int kWtGroups = 3;            // independent groups per CTA (named barriers 1..3); 768 threads leave 85 registers per thread
+constexpr int kWtGroupWarps = 8;        // warp w owns tile rows 4w..4w+3, lane = x
 constexpr int kWtGroupThreads = 32 * kWtGroupWarps;
 constexpr int kWtThreads = kWtGroups * kWtGroupThreads;
 constexpr int kWtTile = 32;             // tile width
 constexpr int kWtTileH = 4 * kWtGroupWarps;
-constexpr int kWtRegionCap = 3968;      // 8-byte entries per group (31 KB): e.g. 62 x 62 source pixels (plain warp kernel)
+constexpr int kWtRegionCap = 7936;      // 8-byte entries per group (62 KB): e.g. 88 x 88 source pixels (plain warp kernel)
 constexpr int kWtMaxDim = 32766;        // largest source width / height of the tiled kernel (see wt_fixed_coord)
 
 template <int CAP>
