@@ -254,9 +254,10 @@ int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stre
 /* Input side of RAFT_2.calc / RAFT.forward (ofgen.py:72-76, RAFT/core/raft.py:89-90, utils/utils.py:7-19) in one pass:
  * img u8 [B,H,W,3] -> out f32 [B,Hp,Wp,Cout] (NHWC) = 2*(x/255)-1 of the replicate-padded frame; pixel (y,x) of out reads
  * img at (clamp(y-top), clamp(x-left)).  Cout = 3, or 4 with a zero fourth channel (lets cuDNN run the 7x7 stem
- * convolution on tensor cores with a zero-padded filter). */
-int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, int Cout, float* out,
-                               sdof_stream_t stream);
+ * convolution on tensor cores with a zero-padded filter).  swap_rb != 0 reads BGR frames as RGB (the `[:, :, ::-1]` of
+ * RAFT_2.calc, ofgen.py:72-73). */
+int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, int Cout, int swap_rb,
+                               float* out, sdof_stream_t stream);
 /* The two convolutions of the update block that are too small / too thin for a tensor-core library kernel:
  *   sdof_conv7x7_c2_relu : BasicMotionEncoder.convf1 (RAFT/core/update.py:85,93): out[B,h,w,128] =
  *                          relu(conv7x7(flow[B,h,w,2], pad 3) + bias); wT = weight[128,2,7,7] permuted to [7,7,2,128].

@@ -53,7 +53,7 @@ SIGNATURES = {
     'sdof_instnorm_stats_nhwc': (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     'sdof_instnorm_apply_nhwc': (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_float, c_int, _P]),
     'sdof_add_relu': (c_int, [_P, _P, _P, c_int64, _P]),
-    'sdof_normalize_pad_u8_nhwc': (c_int, [_P] + [c_int] * 8 + [_P, _P]),
+    'sdof_normalize_pad_u8_nhwc': (c_int, [_P] + [c_int] * 9 + [_P, _P]),
     'sdof_conv7x7_c2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     'sdof_flowhead2_update': (c_int, [_P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     'sdof_alt_corr_forward': (c_int, [_P, _P, _P] + [c_int] * 8 + [_P, _P]),

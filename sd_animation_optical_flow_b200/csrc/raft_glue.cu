@@ -700,7 +700,7 @@ namespace sdof {
 // Cout = 3, or 4 with a zero fourth channel: cuDNN only runs its tensor-core implicit GEMM on NHWC inputs whose channel
 // count is a multiple of 4 (the 3-channel stem convolution otherwise falls back to a CUDA-core engine, 266 us per pair).
 __global__ void __launch_bounds__(256) normalize_pad_u8_nhwc_kernel(const unsigned char* __restrict__ img, int B, int H, int W, int top, int left,
-                                                                    int Hp, int Wp, int Cout, float* __restrict__ out) {
+                                                                    int Hp, int Wp, int Cout, int swap_rb, float* __restrict__ out) {
   const int64_t total = (int64_t)B * Hp * Wp;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(p % Wp);
@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(256) normalize_pad_u8_nhwc_kernel(const unsign
     const unsigned char* q = img + (((int64_t)b * H + sy) * W + sx) * 3;
     float v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn((float)q[c], 255.0f)), 1.0f);
+    for (int c = 0; c < 3; ++c) v[c] = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn((float)q[swap_rb ? 2 - c : c], 255.0f)), 1.0f);
     if (Cout == 4) {
       reinterpret_cast<float4*>(out)[p] = make_float4(v[0], v[1], v[2], 0.f);
     } else {
@@ -721,8 +721,8 @@ __global__ void __launch_bounds__(256) normalize_pad_u8_nhwc_kernel(const unsign
 }
 }  // namespace sdof
 
-extern "C" int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, int Cout, float* out,
-                                          sdof_stream_t stream) {
+extern "C" int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int W, int top, int left, int Hp, int Wp, int Cout, int swap_rb,
+                                          float* out, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(img && out, "sdof_normalize_pad_u8_nhwc: NULL pointer");
   SDOF_REQUIRE(B >= 0 && H >= 1 && W >= 1 && top >= 0 && left >= 0 && Hp >= H + top && Wp >= W + left,
@@ -731,7 +731,7 @@ extern "C" int sdof_normalize_pad_u8_nhwc(const uint8_t* img, int B, int H, int 
                "sdof_normalize_pad_u8_nhwc: Cout must be 3, or 4 with a 16-byte aligned output");
   const int64_t total = (int64_t)B * Hp * Wp;
   if (total == 0) return SDOF_OK;
-  normalize_pad_u8_nhwc_kernel<<<grid_for(total, 256, 8), 256, 0, as_stream(stream)>>>(img, B, H, W, top, left, Hp, Wp, Cout, out);
+  normalize_pad_u8_nhwc_kernel<<<grid_for(total, 256, 8), 256, 0, as_stream(stream)>>>(img, B, H, W, top, left, Hp, Wp, Cout, swap_rb, out);
   SDOF_LAUNCH_CHECK("normalize_pad_u8_nhwc_kernel");
   return SDOF_OK;
 }

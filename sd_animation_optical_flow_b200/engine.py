@@ -117,17 +117,17 @@ class RaftEngine:
 
     # ---------------------------------------------------------------- uint8 fast path
     @torch.no_grad()
-    def _forward_u8(self, a: torch.Tensor, b: torch.Tensor, pad) -> torch.Tensor:
+    def _forward_u8(self, a: torch.Tensor, b: torch.Tensor, pad, bgr: bool = False) -> torch.Tensor:
         """uint8 RGB [B,H,W,3] x2 -> padded-size flow [B,Hp,Wp,2]: one kernel normalises + pads each frame straight into
         the channels-last layout the encoders consume (csrc/raft_glue.cu::normalize_pad_u8_nhwc_kernel)."""
-        im1 = ops.normalize_pad_u8(a, pad, channels=4)
-        im2 = ops.normalize_pad_u8(b, pad, channels=4)
+        im1 = ops.normalize_pad_u8(a, pad, channels=4, bgr=bgr)
+        im2 = ops.normalize_pad_u8(b, pad, channels=4, bgr=bgr)
         _, flow_up = self.fast.forward(im1, im2, self.iters, normalized=True)
         return flow_up
 
     @torch.no_grad()
-    def _forward_u8_graphed(self, a: torch.Tensor, b: torch.Tensor, pad) -> torch.Tensor:
-        key = ('u8', tuple(a.shape), self.iters)
+    def _forward_u8_graphed(self, a: torch.Tensor, b: torch.Tensor, pad, bgr: bool = False) -> torch.Tensor:
+        key = ('u8', tuple(a.shape), self.iters, bool(bgr))
         ent = self._graphs.get(key)
         if ent is None:
             s1, s2 = a.clone(), b.clone()
@@ -135,11 +135,11 @@ class RaftEngine:
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up: cuDNN autotune, table uploads, allocator
-                    self._forward_u8(s1, s2, pad)
+                    self._forward_u8(s1, s2, pad, bgr)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                out = self._forward_u8(s1, s2, pad)
+                out = self._forward_u8(s1, s2, pad, bgr)
             ent = (g, s1, s2, out)
             self._graphs[key] = ent
         g, s1, s2, out = ent
@@ -149,8 +149,8 @@ class RaftEngine:
         return out  # overwritten by the next replay: estimate_flow copies (unpad / contiguous) before returning
 
     @torch.no_grad()
-    def estimate_flow(self, img1: torch.Tensor, img2: torch.Tensor, unpad: bool = True) -> torch.Tensor:
-        """img1, img2: RGB uint8 (or float 0..255) CUDA tensors [B,H,W,3].  Returns flow of img1 -> img2
+    def estimate_flow(self, img1: torch.Tensor, img2: torch.Tensor, unpad: bool = True, bgr: bool = False) -> torch.Tensor:
+        """img1, img2: RGB (bgr=True: BGR) uint8 (or float 0..255) CUDA tensors [B,H,W,3].  Returns flow of img1 -> img2
         on img1's grid, [B,H,W,2] fp32 (x, y pixels).  Images are replicate-padded to a multiple of 8
         like the reference (utils/utils.py:7-19); unpad=False reproduces RAFT_2.calc, which returns
         the padded-size flow (ofgen.py:75-78)."""
@@ -162,11 +162,13 @@ class RaftEngine:
             B, H, W, _ = img1.shape
             pad = InputPadder((H, W))._pad
             fwd = self._forward_u8_graphed if self.use_cuda_graph else self._forward_u8
-            flow_up = fwd(img1.contiguous(), img2.contiguous(), pad)
+            flow_up = fwd(img1.contiguous(), img2.contiguous(), pad, bgr)
             if unpad and any(pad):
                 Hp, Wp = flow_up.shape[1:3]
                 return flow_up[:, pad[2]:Hp - pad[3], pad[0]:Wp - pad[1]].contiguous()
             return flow_up.clone() if self.use_cuda_graph else flow_up
+        if bgr:
+            img1, img2 = img1.flip(-1), img2.flip(-1)
         im1 = img1.permute(0, 3, 1, 2).float()
         im2 = img2.permute(0, 3, 1, 2).float()
         padder = InputPadder(im1.shape)

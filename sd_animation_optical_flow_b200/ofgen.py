@@ -67,9 +67,8 @@ class RAFT_2:
         """BGR uint8 [H,W,3] x2 -> flow float32 [H',W',2] on img1's grid.  Like the reference the
         result keeps the replicate-padded size H',W' (multiples of 8; ofgen.py:75-78 never unpads)."""
         dev = self.engine.device
-        a = _h2d(img1, dev)[None].flip(-1).contiguous()  # BGR -> RGB
-        b = _h2d(img2, dev)[None].flip(-1).contiguous()
-        return _d2h(self.engine.estimate_flow(a, b, unpad=False)[0])
+        a, b = _h2d(img1, dev)[None], _h2d(img2, dev)[None]
+        return _d2h(self.engine.estimate_flow(a, b, unpad=False, bgr=True)[0])   # BGR -> RGB inside the first kernel
 
 
 def create_of_algo(model_path: str | None = 'RAFT/models/raft-things.pth', **kw):

@@ -538,9 +538,9 @@ def abs_diff_sum(a: torch.Tensor, b: torch.Tensor) -> int:
     return int(out.item())
 
 
-def normalize_pad_u8(img: torch.Tensor, pad, channels: int = 3) -> torch.Tensor:
+def normalize_pad_u8(img: torch.Tensor, pad, channels: int = 3, bgr: bool = False) -> torch.Tensor:
     """u8 [B,H,W,3] -> channels-last fp32 [B,channels,Hp,Wp] = 2*(x/255)-1 of the replicate-padded frame (channels = 4
-    appends a zero channel).  pad = (left, right, top, bottom) as in F.pad / InputPadder."""
+    appends a zero channel; bgr=True reads BGR frames as RGB).  pad = (left, right, top, bottom) as in F.pad / InputPadder."""
     require_cuda(img, 'img', u8)
     B, H, W, C = img.shape
     if C != 3:
@@ -548,6 +548,6 @@ def normalize_pad_u8(img: torch.Tensor, pad, channels: int = 3) -> torch.Tensor:
     left, right, top, bottom = (int(v) for v in pad)
     Hp, Wp = H + top + bottom, W + left + right
     out = torch.empty((B, Hp, Wp, channels), dtype=f32, device=img.device)
-    check(load().sdof_normalize_pad_u8_nhwc(ptr(img), B, H, W, top, left, Hp, Wp, channels, ptr(out), stream_ptr(img.device)),
+    check(load().sdof_normalize_pad_u8_nhwc(ptr(img), B, H, W, top, left, Hp, Wp, channels, int(bgr), ptr(out), stream_ptr(img.device)),
           'sdof_normalize_pad_u8_nhwc')
     return out.permute(0, 3, 1, 2)
