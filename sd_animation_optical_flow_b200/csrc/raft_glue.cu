@@ -48,15 +48,18 @@ __global__ void __launch_bounds__(256) relu_scatter_kernel(const float4* __restr
 
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+// bias_zr / bias_q: per-channel vectors (bias_map = 0) or per-pixel maps [npix][2*Hd] / [npix][Hd] (bias_map = 1): the
+// maps carry the convolution bias PLUS the contribution of the context features `inp`, which is the same in every
+// iteration and is therefore convolved once per pair instead of 20 x 6 times (raft_fast.py).
 __global__ void __launch_bounds__(256) gru_rh_kernel(const float4* __restrict__ zr, const float4* __restrict__ bias_zr,
                                                      const float4* __restrict__ h, float* __restrict__ rhx, int64_t npix,
-                                                     int Hd4, int rhx_stride) {
+                                                     int Hd4, int rhx_stride, int bias_map) {
   const int64_t total = npix * Hd4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / Hd4;
     const int c4 = (int)(i - p * Hd4);
     float4 r = zr[p * (2 * Hd4) + Hd4 + c4];
-    if (bias_zr) r = add4(r, __ldg(bias_zr + Hd4 + c4));
+    if (bias_zr) r = add4(r, __ldg(bias_zr + (bias_map ? p * (2 * Hd4) : 0) + Hd4 + c4));
     const float4 hv = h[i];
     float4 o;
     o.x = sigmoidf_(r.x) * hv.x; o.y = sigmoidf_(r.y) * hv.y; o.z = sigmoidf_(r.z) * hv.z; o.w = sigmoidf_(r.w) * hv.w;
@@ -67,15 +70,15 @@ __global__ void __launch_bounds__(256) gru_rh_kernel(const float4* __restrict__ 
 __global__ void __launch_bounds__(256) gru_update_kernel(const float4* __restrict__ zr, const float4* __restrict__ bias_zr,
                                                          const float4* __restrict__ q, const float4* __restrict__ bias_q,
                                                          float4* __restrict__ h, float* __restrict__ hx, int64_t npix,
-                                                         int Hd4, int hx_stride) {
+                                                         int Hd4, int hx_stride, int bias_map) {
   const int64_t total = npix * Hd4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / Hd4;
     const int c4 = (int)(i - p * Hd4);
     float4 z = zr[p * (2 * Hd4) + c4];
     float4 qv = q[i];
-    if (bias_zr) z = add4(z, __ldg(bias_zr + c4));
-    if (bias_q) qv = add4(qv, __ldg(bias_q + c4));
+    if (bias_zr) z = add4(z, __ldg(bias_zr + (bias_map ? p * (2 * Hd4) : 0) + c4));
+    if (bias_q) qv = add4(qv, __ldg(bias_q + (bias_map ? p * Hd4 : 0) + c4));
     const float4 hv = h[i];
     float4 o;
     float s;
@@ -238,7 +241,7 @@ int sdof_relu_scatter(const float* src, const float* bias, int64_t npix, int C, 
 }
 
 int sdof_gru_rh(const float* zr, const float* bias_zr, const float* h, float* rhx, int64_t npix, int hidden, int rhx_stride,
-                sdof_stream_t stream) {
+                int bias_map, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(zr && h && rhx, "sdof_gru_rh: NULL pointer");
   SDOF_REQUIRE(hidden > 0 && hidden % 4 == 0 && rhx_stride % 4 == 0, "sdof_gru_rh: hidden and stride must be multiples of 4");
@@ -247,13 +250,13 @@ int sdof_gru_rh(const float* zr, const float* bias_zr, const float* h, float* rh
   if (npix <= 0) return SDOF_OK;
   gru_rh_kernel<<<grid_for(npix * (hidden / 4), 256, 8), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(zr), reinterpret_cast<const float4*>(bias_zr), reinterpret_cast<const float4*>(h), rhx, npix,
-      hidden / 4, rhx_stride);
+      hidden / 4, rhx_stride, bias_map);
   SDOF_LAUNCH_CHECK("gru_rh_kernel");
   return SDOF_OK;
 }
 
 int sdof_gru_update(const float* zr, const float* bias_zr, const float* q, const float* bias_q, float* h, float* hx,
-                    int64_t npix, int hidden, int hx_stride, sdof_stream_t stream) {
+                    int64_t npix, int hidden, int hx_stride, int bias_map, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(zr && q && h && hx, "sdof_gru_update: NULL pointer");
   SDOF_REQUIRE(hidden > 0 && hidden % 4 == 0 && hx_stride % 4 == 0, "sdof_gru_update: hidden and stride must be multiples of 4");
@@ -262,7 +265,7 @@ int sdof_gru_update(const float* zr, const float* bias_zr, const float* q, const
   if (npix <= 0) return SDOF_OK;
   gru_update_kernel<<<grid_for(npix * (hidden / 4), 256, 8), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(zr), reinterpret_cast<const float4*>(bias_zr), reinterpret_cast<const float4*>(q),
-      reinterpret_cast<const float4*>(bias_q), reinterpret_cast<float4*>(h), hx, npix, hidden / 4, hx_stride);
+      reinterpret_cast<const float4*>(bias_q), reinterpret_cast<float4*>(h), hx, npix, hidden / 4, hx_stride, bias_map);
   SDOF_LAUNCH_CHECK("gru_update_kernel");
   return SDOF_OK;
 }

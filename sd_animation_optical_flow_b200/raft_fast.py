@@ -149,13 +149,22 @@ class FastRaft:
         self.convc1, self.convc2 = _w(e.convc1), _w(e.convc2)
         self.convf1, self.convf2 = _w(e.convf1), _w(e.convf2)
         self.conv = _w(e.conv, pad_out_to=128)           # 126 -> 128 filters (two zero filters) keeps rows 16-byte aligned
-        self.zr, self.q = [], []
+        # GRU input hx = [h | inp | motion | flow] (update.py:47).  `inp` (the context features) does not change over the
+        # iterations, so its share of convz/convr/convq is convolved ONCE per pair into per-pixel bias maps (exact by
+        # linearity) and the per-iteration convolutions run on [h | motion | flow] only: 256 instead of 384 input channels.
+        hd, cd = model.hidden_dim, model.context_dim
+        keep = list(range(hd)) + list(range(hd + cd, hd + cd + 128))
+        ctx = list(range(hd, hd + cd))
+        self.zr, self.q, self.zr_ctx, self.q_ctx = [], [], [], []
         for p in ('1', '2'):
             cz, cr, cq = getattr(g, 'convz' + p), getattr(g, 'convr' + p), getattr(g, 'convq' + p)
-            wzr = torch.cat([cz.weight.detach(), cr.weight.detach()], 0).contiguous(memory_format=CL)
+            wzr = torch.cat([cz.weight.detach(), cr.weight.detach()], 0)
             bzr = torch.cat([cz.bias.detach(), cr.bias.detach()], 0).contiguous()
-            self.zr.append((wzr, bzr, cz.padding))
-            self.q.append(_w(cq))
+            wq, bq = cq.weight.detach(), cq.bias.detach().contiguous()
+            self.zr.append((wzr[:, keep].contiguous(memory_format=CL), bzr, cz.padding))
+            self.q.append((wq[:, keep].contiguous(memory_format=CL), bq, cq.padding))
+            self.zr_ctx.append((wzr[:, ctx].contiguous(memory_format=CL), bzr, cz.padding))
+            self.q_ctx.append((wq[:, ctx].contiguous(memory_format=CL), bq, cq.padding))
         self.fh1, self.fh2 = _w(fh.conv1), _w(fh.conv2)
         self.convf1_t = e.convf1.weight.detach().permute(2, 3, 1, 0).contiguous()      # [7,7,2,128] for conv7x7_c2_relu
         self.fh2_t = fh.conv2.weight.detach().permute(2, 3, 0, 1).contiguous()         # [3,3,2,256] for flowhead2_update
@@ -220,7 +229,7 @@ class FastRaft:
         hd = self.hidden
         dev = image1.device
         cdim = self.cdim                                                  # context ("inp") channels
-        xc = cdim + 128                                                   # x = [inp | motion(126) | flow(2)]
+        xc = 128                                                          # per-iteration x = [motion(126) | flow(2)]; inp is folded into bias maps
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.side_streams else main
         if normalized:
@@ -229,13 +238,15 @@ class FastRaft:
             im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
             im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128]
-        HX = torch.empty((B, h, w, hd + xc), device=dev)                 # [h | x]        (update.py:47)
-        RHX = torch.empty_like(HX)                                        # [r*h | x]      (update.py:50)
+        HX = torch.empty((B, h, w, hd + xc), device=dev)                 # [h | motion | flow]      (update.py:47 minus inp)
+        RHX = torch.empty_like(HX)                                        # [r*h | motion | flow]    (update.py:50 minus inp)
+        ZRMAP = [torch.empty((B, h, w, 2 * hd), device=dev) for _ in (0, 1)]   # bias + conv(inp) of convz|convr, per GRU pass
+        QMAP = [torch.empty((B, h, w, hd), device=dev) for _ in (0, 1)]        # bias + conv(inp) of convq
         CF = torch.empty((B, h, w, 256), device=dev)                      # [cor(192) | flo(64)]  (update.py:94)
         corr = torch.empty((B, h, w, 4 * 81), device=dev)
         flow = torch.empty((B, h, w, 2), device=dev)
         fh_scratch = torch.empty((B * h * w * 18,), device=dev)          # tap products of the flow head's second conv
-        mo = hd + cdim                                                    # motion-feature slot
+        mo = hd                                                           # motion-feature slot
         fo = mo + 126                                                     # flow slot
         ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing='ij')
         coords1 = torch.stack([xs, ys], -1).float()[None].repeat(B, 1, 1, 1).contiguous()
@@ -246,9 +257,10 @@ class FastRaft:
             cn = self.cnet(im1).permute(0, 2, 3, 1)
             torch.tanh(cn[..., :hd], out=H)
             HX[..., :hd] = H
-            inp = torch.relu(cn[..., hd:])
-            HX[..., hd:hd + cdim] = inp
-            RHX[..., hd:hd + cdim] = inp
+            inp = torch.relu(cn[..., hd:]).contiguous()
+            for p in (0, 1):                                              # once per pair: the context share of the GRU convolutions
+                ZRMAP[p].copy_(self._conv(inp, self.zr_ctx[p], bias=True))
+                QMAP[p].copy_(self._conv(inp, self.q_ctx[p], bias=True))
             del cn, inp
         fmaps = self.fnet(torch.cat([im1, im2], 0))                       # ---- feature encoder + all-pairs volume
         pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps[:B]), _to_nhwc(fmaps[B:]), 4, self.corr_precision)
@@ -270,9 +282,9 @@ class FastRaft:
             ops.relu_scatter(mot, HX, mo, RHX, mo, c_valid=126, bias=self.conv[1])
             for p in (0, 1):                                              # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
                 zr = self._conv(HX, self.zr[p])
-                ops.gru_rh(zr, H, RHX, bias_zr=self.zr[p][1])
+                ops.gru_rh(zr, H, RHX, bias_zr=ZRMAP[p])
                 q = self._conv(RHX, self.q[p])
-                ops.gru_update(zr, q, H, HX, bias_zr=self.zr[p][1], bias_q=self.q[p][1])
+                ops.gru_update(zr, q, H, HX, bias_zr=ZRMAP[p], bias_q=QMAP[p])
             if self.own_fh2:
                 ops.flowhead2_update(self._conv_relu(H, self.fh1), self.fh2_t, self._fh2_bias, coords1, flow, HX, fo, RHX, fo,
                                      scratch=fh_scratch)
