@@ -229,9 +229,12 @@ int sdof_warp_mask_composite(const uint8_t* src, const uint8_t* base, const floa
 int sdof_relu_scatter(const float* src, const float* bias, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off,
                       float* dst2, int dst2_stride, int dst2_off, int C_valid, sdof_stream_t stream);
 int sdof_gru_rh(const float* zr, const float* bias_zr, const float* h, float* rhx, int64_t npix, int hidden, int rhx_stride,
-                int bias_map, sdof_stream_t stream);
+                int bias_map, int zr_channels, sdof_stream_t stream);
 int sdof_gru_update(const float* zr, const float* bias_zr, const float* q, const float* bias_q, float* h, float* hx,
-                    int64_t npix, int hidden, int hx_stride, int bias_map, sdof_stream_t stream);
+                    int64_t npix, int hidden, int hx_stride, int bias_map, int zr_channels, sdof_stream_t stream);
+/* zr_channels = 2*hidden: zr = [z | r].  zr_channels = 3*hidden: zr = [z | r | q_x], where q_x is the share of convq that
+ * does not depend on r (its [motion | flow] input channels), computed by the same convolution as z and r; gru_update adds
+ * it to q (which then only holds the convolution of r*h). */
 /* bias_map = 0: bias_zr [2*hidden], bias_q [hidden] per-channel vectors; bias_map = 1: per-pixel maps [npix][2*hidden] and
  * [npix][hidden] holding bias + the convolution of the iteration-invariant context features (computed once per pair). */
 int sdof_flow_update(const float* delta, float delta_bias_x, float delta_bias_y, float* coords1, float* flow, float* hx,

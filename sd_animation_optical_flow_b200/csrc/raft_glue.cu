@@ -53,12 +53,12 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 // iteration and is therefore convolved once per pair instead of 20 x 6 times (raft_fast.py).
 __global__ void __launch_bounds__(256) gru_rh_kernel(const float4* __restrict__ zr, const float4* __restrict__ bias_zr,
                                                      const float4* __restrict__ h, float* __restrict__ rhx, int64_t npix,
-                                                     int Hd4, int rhx_stride, int bias_map) {
+                                                     int Hd4, int rhx_stride, int bias_map, int zr_stride4) {
   const int64_t total = npix * Hd4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / Hd4;
     const int c4 = (int)(i - p * Hd4);
-    float4 r = zr[p * (2 * Hd4) + Hd4 + c4];
+    float4 r = zr[p * zr_stride4 + Hd4 + c4];
     if (bias_zr) r = add4(r, __ldg(bias_zr + (bias_map ? p * (2 * Hd4) : 0) + Hd4 + c4));
     const float4 hv = h[i];
     float4 o;
@@ -70,13 +70,14 @@ __global__ void __launch_bounds__(256) gru_rh_kernel(const float4* __restrict__ 
 __global__ void __launch_bounds__(256) gru_update_kernel(const float4* __restrict__ zr, const float4* __restrict__ bias_zr,
                                                          const float4* __restrict__ q, const float4* __restrict__ bias_q,
                                                          float4* __restrict__ h, float* __restrict__ hx, int64_t npix,
-                                                         int Hd4, int hx_stride, int bias_map) {
+                                                         int Hd4, int hx_stride, int bias_map, int zr_stride4, int q_extra) {
   const int64_t total = npix * Hd4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / Hd4;
     const int c4 = (int)(i - p * Hd4);
-    float4 z = zr[p * (2 * Hd4) + c4];
+    float4 z = zr[p * zr_stride4 + c4];
     float4 qv = q[i];
+    if (q_extra) qv = add4(qv, zr[p * zr_stride4 + 2 * Hd4 + c4]);  // share of convq computed with the z|r convolution
     if (bias_zr) z = add4(z, __ldg(bias_zr + (bias_map ? p * (2 * Hd4) : 0) + c4));
     if (bias_q) qv = add4(qv, __ldg(bias_q + (bias_map ? p * Hd4 : 0) + c4));
     const float4 hv = h[i];
@@ -241,31 +242,34 @@ int sdof_relu_scatter(const float* src, const float* bias, int64_t npix, int C, 
 }
 
 int sdof_gru_rh(const float* zr, const float* bias_zr, const float* h, float* rhx, int64_t npix, int hidden, int rhx_stride,
-                int bias_map, sdof_stream_t stream) {
+                int bias_map, int zr_channels, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(zr && h && rhx, "sdof_gru_rh: NULL pointer");
   SDOF_REQUIRE(hidden > 0 && hidden % 4 == 0 && rhx_stride % 4 == 0, "sdof_gru_rh: hidden and stride must be multiples of 4");
+  SDOF_REQUIRE(zr_channels == 2 * hidden || zr_channels == 3 * hidden, "sdof_gru_rh: zr must have 2*hidden or 3*hidden channels");
   SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(zr) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(rhx)) & 15) == 0,
                "sdof_gru_rh: pointers must be 16-byte aligned");
   if (npix <= 0) return SDOF_OK;
   gru_rh_kernel<<<grid_for(npix * (hidden / 4), 256, 8), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(zr), reinterpret_cast<const float4*>(bias_zr), reinterpret_cast<const float4*>(h), rhx, npix,
-      hidden / 4, rhx_stride, bias_map);
+      hidden / 4, rhx_stride, bias_map, zr_channels / 4);
   SDOF_LAUNCH_CHECK("gru_rh_kernel");
   return SDOF_OK;
 }
 
 int sdof_gru_update(const float* zr, const float* bias_zr, const float* q, const float* bias_q, float* h, float* hx,
-                    int64_t npix, int hidden, int hx_stride, int bias_map, sdof_stream_t stream) {
+                    int64_t npix, int hidden, int hx_stride, int bias_map, int zr_channels, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(zr && q && h && hx, "sdof_gru_update: NULL pointer");
   SDOF_REQUIRE(hidden > 0 && hidden % 4 == 0 && hx_stride % 4 == 0, "sdof_gru_update: hidden and stride must be multiples of 4");
+  SDOF_REQUIRE(zr_channels == 2 * hidden || zr_channels == 3 * hidden, "sdof_gru_update: zr must have 2*hidden or 3*hidden channels");
   SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(zr) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(h) |
                  reinterpret_cast<uintptr_t>(hx)) & 15) == 0, "sdof_gru_update: pointers must be 16-byte aligned");
   if (npix <= 0) return SDOF_OK;
   gru_update_kernel<<<grid_for(npix * (hidden / 4), 256, 8), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(zr), reinterpret_cast<const float4*>(bias_zr), reinterpret_cast<const float4*>(q),
-      reinterpret_cast<const float4*>(bias_q), reinterpret_cast<float4*>(h), hx, npix, hidden / 4, hx_stride, bias_map);
+      reinterpret_cast<const float4*>(bias_q), reinterpret_cast<float4*>(h), hx, npix, hidden / 4, hx_stride, bias_map, zr_channels / 4,
+      zr_channels == 3 * hidden);
   SDOF_LAUNCH_CHECK("gru_update_kernel");
   return SDOF_OK;
 }

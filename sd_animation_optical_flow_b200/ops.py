@@ -365,7 +365,7 @@ def _bias_is_map(bias, width: int) -> int:
 def gru_rh(zr: torch.Tensor, h: torch.Tensor, rhx: torch.Tensor, bias_zr: torch.Tensor | None = None) -> None:
     hidden = h.shape[-1]
     check(load().sdof_gru_rh(ptr(zr), ptr(bias_zr), ptr(h), ptr(rhx), h.numel() // hidden, hidden, rhx.shape[-1],
-                             _bias_is_map(bias_zr, 2 * hidden), stream_ptr(h.device)), 'sdof_gru_rh')
+                             _bias_is_map(bias_zr, 2 * hidden), zr.shape[-1], stream_ptr(h.device)), 'sdof_gru_rh')
 
 
 def gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor, hx: torch.Tensor, bias_zr: torch.Tensor | None = None,
@@ -374,7 +374,8 @@ def gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor, hx: torch.Ten
     if _bias_is_map(bias_zr, 2 * hidden) != _bias_is_map(bias_q, hidden):
         raise RuntimeError('gru_update: bias_zr and bias_q must both be vectors or both be per-pixel maps')
     check(load().sdof_gru_update(ptr(zr), ptr(bias_zr), ptr(q), ptr(bias_q), ptr(h), ptr(hx), h.numel() // hidden, hidden,
-                                 hx.shape[-1], _bias_is_map(bias_zr, 2 * hidden), stream_ptr(h.device)), 'sdof_gru_update')
+                                 hx.shape[-1], _bias_is_map(bias_zr, 2 * hidden), zr.shape[-1], stream_ptr(h.device)),
+          'sdof_gru_update')
 
 
 def flow_update(delta: torch.Tensor | None, coords1: torch.Tensor, flow: torch.Tensor, hx: torch.Tensor | None, hx_off: int,

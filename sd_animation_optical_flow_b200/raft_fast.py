@@ -161,8 +161,13 @@ class FastRaft:
             wzr = torch.cat([cz.weight.detach(), cr.weight.detach()], 0)
             bzr = torch.cat([cz.bias.detach(), cr.bias.detach()], 0).contiguous()
             wq, bq = cq.weight.detach(), cq.bias.detach().contiguous()
-            self.zr.append((wzr[:, keep].contiguous(memory_format=CL), bzr, cz.padding))
-            self.q.append((wq[:, keep].contiguous(memory_format=CL), bq, cq.padding))
+            # convq's input [r*h | x]: only the first `hd` channels depend on r.  The [motion | flow] share of convq is
+            # appended to the z|r convolution as 128 more filters (their h-channel taps are zero), so the convolution
+            # that has to wait for r shrinks to hd -> hd channels and needs no [r*h | x] concatenation any more.
+            wq_x = wq[:, keep].clone()
+            wq_x[:, :hd] = 0
+            self.zr.append((torch.cat([wzr[:, keep], wq_x], 0).contiguous(memory_format=CL), bzr, cz.padding))
+            self.q.append((wq[:, :hd].contiguous(memory_format=CL), bq, cq.padding))
             self.zr_ctx.append((wzr[:, ctx].contiguous(memory_format=CL), bzr, cz.padding))
             self.q_ctx.append((wq[:, ctx].contiguous(memory_format=CL), bq, cq.padding))
         self.fh1, self.fh2 = _w(fh.conv1), _w(fh.conv2)
@@ -239,7 +244,7 @@ class FastRaft:
             im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128]
         HX = torch.empty((B, h, w, hd + xc), device=dev)                 # [h | motion | flow]      (update.py:47 minus inp)
-        RHX = torch.empty_like(HX)                                        # [r*h | motion | flow]    (update.py:50 minus inp)
+        RH = torch.empty((B, h, w, hd), device=dev)                       # r*h                      (update.py:50)
         ZRMAP = [torch.empty((B, h, w, 2 * hd), device=dev) for _ in (0, 1)]   # bias + conv(inp) of convz|convr, per GRU pass
         QMAP = [torch.empty((B, h, w, hd), device=dev) for _ in (0, 1)]        # bias + conv(inp) of convq
         CF = torch.empty((B, h, w, 256), device=dev)                      # [cor(192) | flo(64)]  (update.py:94)
@@ -250,7 +255,7 @@ class FastRaft:
         fo = mo + 126                                                     # flow slot
         ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing='ij')
         coords1 = torch.stack([xs, ys], -1).float()[None].repeat(B, 1, 1, 1).contiguous()
-        ops.flow_update(None, coords1, flow, HX, fo, RHX, fo)             # flow = 0 into every slot
+        ops.flow_update(None, coords1, flow, HX, fo, None, 0)             # flow = 0 into every slot
 
         side.wait_stream(main)
         with torch.cuda.stream(side):                                     # ---- context encoder branch
@@ -279,17 +284,17 @@ class FastRaft:
             ops.relu_scatter(c2, CF, 0, bias=self.convc2[1])
             main.wait_stream(side)
             mot = self._conv(CF, self.conv)                               # 126 (+2 zero) channels
-            ops.relu_scatter(mot, HX, mo, RHX, mo, c_valid=126, bias=self.conv[1])
+            ops.relu_scatter(mot, HX, mo, c_valid=126, bias=self.conv[1])
             for p in (0, 1):                                              # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
-                zr = self._conv(HX, self.zr[p])
-                ops.gru_rh(zr, H, RHX, bias_zr=ZRMAP[p])
-                q = self._conv(RHX, self.q[p])
+                zr = self._conv(HX, self.zr[p])                           # [z | r | x-share of q], 3*hd channels
+                ops.gru_rh(zr, H, RH, bias_zr=ZRMAP[p])
+                q = self._conv(RH, self.q[p])                             # r*h share of q
                 ops.gru_update(zr, q, H, HX, bias_zr=ZRMAP[p], bias_q=QMAP[p])
             if self.own_fh2:
-                ops.flowhead2_update(self._conv_relu(H, self.fh1), self.fh2_t, self._fh2_bias, coords1, flow, HX, fo, RHX, fo,
+                ops.flowhead2_update(self._conv_relu(H, self.fh1), self.fh2_t, self._fh2_bias, coords1, flow, HX, fo, None, 0,
                                      scratch=fh_scratch)
             else:
                 delta = self._conv(self._conv_relu(H, self.fh1), self.fh2)
-                ops.flow_update(delta.contiguous(), coords1, flow, HX, fo, RHX, fo, delta_bias=self._fh2_bias)
+                ops.flow_update(delta.contiguous(), coords1, flow, HX, fo, None, 0, delta_bias=self._fh2_bias)
         mask = self._conv(self._conv_relu(H, self.mask0), self.mask2)
         return flow, ops.convex_upsample(mask.contiguous(), flow, 0.25, mask_bias=self.mask2[1])
