@@ -226,7 +226,7 @@ int sdof_warp_mask_composite(const uint8_t* src, const uint8_t* base, const floa
  *                  flow slots of hx / rhx (either may be NULL)                      (raft.py:126-131)
  *   convex_upsample : RAFT.upsample_flow (raft.py:72-83): mask [B,h,w,576] (times mask_scale), flow [B,h,w,2]
  *                  -> up [B,8h,8w,2]                                                                           */
-int sdof_relu_scatter(const float* src, const float* bias, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off,
+int sdof_relu_scatter(const float* src, const float* src2, const float* bias, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off,
                       float* dst2, int dst2_stride, int dst2_off, int C_valid, sdof_stream_t stream);
 int sdof_gru_rh(const float* zr, const float* bias_zr, const float* h, float* rhx, int64_t npix, int hidden, int rhx_stride,
                 int bias_map, int zr_channels, sdof_stream_t stream);

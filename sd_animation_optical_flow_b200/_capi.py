@@ -44,7 +44,7 @@ SIGNATURES = {
     'sdof_corr_pyramid_from_operands': (c_int, [c_int] * 8 + [_P, _P, c_int64, _P]),
     'sdof_corr_lookup': (c_int, [_P, _P] + [c_int] * 7 + [_P, _P]),
     'sdof_corr_lookup_nhwc': (c_int, [_P, _P] + [c_int] * 7 + [_P, _P]),
-    'sdof_relu_scatter': (c_int, [_P, _P, c_int64, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, _P]),
+    'sdof_relu_scatter': (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, _P]),
     'sdof_gru_rh': (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     'sdof_gru_update': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     'sdof_flow_update': (c_int, [_P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -6,7 +6,7 @@
 // concatenated buffers, everything between the convolutions collapses into the four element-wise
 // kernels below; the convolutions themselves stay in cuDNN (raft_fast.py).
 //
-//   relu_scatter   : dst[:, off:off+C] = relu(src)            (optionally into two buffers)
+//   relu_scatter   : dst[:, off:off+C] = relu(src (+ src2) + bias)   (optionally into two buffers)
 //   gru_rh         : rhx[:, 0:Hd] = sigmoid(zr[:, Hd:2Hd]) * h
 //   gru_update     : h' = (1 - sigmoid(z)) * h + sigmoid(z) * tanh(q)   -> h (dense) and hx[:, 0:Hd]
 //   flow_update    : coords1 += delta; flow = coords1 - grid  -> dense flow, hx / rhx flow slots
@@ -19,14 +19,18 @@ namespace sdof {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-__global__ void __launch_bounds__(256) relu_scatter_kernel(const float4* __restrict__ src, const float4* __restrict__ bias,
-                                                           int64_t npix, int C4, float* __restrict__ d1, int d1_stride, int d1_off,
+__global__ void __launch_bounds__(256) relu_scatter_kernel(const float4* __restrict__ src, const float4* __restrict__ src2,
+                                                           const float4* __restrict__ bias, int64_t npix, int C4, float* __restrict__ d1, int d1_stride, int d1_off,
                                                            float* __restrict__ d2, int d2_stride, int d2_off, int C_valid) {
   const int64_t total = npix * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / C4;
     const int c = (int)(i - p * C4) * 4;
     float4 v = src[i];
+    if (src2) {  // a convolution split over two input-channel groups (computed on two streams): sum of the partial results
+      const float4 u = src2[i];
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
     if (bias) {
       const float4 bv = __ldg(bias + (c >> 2));
       v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
@@ -227,15 +231,15 @@ int sdof_instnorm_relu_nchw(const float* x, float* y, int64_t planes, int64_t hw
 }
 
 
-int sdof_relu_scatter(const float* src, const float* bias, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off, float* dst2,
+int sdof_relu_scatter(const float* src, const float* src2, const float* bias, int64_t npix, int C, float* dst1, int dst1_stride, int dst1_off, float* dst2,
                       int dst2_stride, int dst2_off, int C_valid, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(src && dst1, "sdof_relu_scatter: NULL pointer");
   SDOF_REQUIRE(C > 0 && C % 4 == 0 && C_valid > 0 && C_valid <= C, "sdof_relu_scatter: C must be a multiple of 4, 0 < C_valid <= C");
-  SDOF_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0, "sdof_relu_scatter: src must be 16-byte aligned");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(src2)) & 15) == 0, "sdof_relu_scatter: src, src2 must be 16-byte aligned");
   if (npix <= 0) return SDOF_OK;
   relu_scatter_kernel<<<grid_for(npix * (C / 4), 256, 8), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(src), reinterpret_cast<const float4*>(bias), npix, C / 4, dst1, dst1_stride, dst1_off, dst2,
+      reinterpret_cast<const float4*>(src), reinterpret_cast<const float4*>(src2), reinterpret_cast<const float4*>(bias), npix, C / 4, dst1, dst1_stride, dst1_off, dst2,
       dst2_stride, dst2_off, C_valid);
   SDOF_LAUNCH_CHECK("relu_scatter_kernel");
   return SDOF_OK;

@@ -348,11 +348,11 @@ def corr_lookup_nhwc(pyr: CorrPyramid, coords_nhwc: torch.Tensor, radius: int, o
 
 
 def relu_scatter(src: torch.Tensor, dst1: torch.Tensor, off1: int, dst2: torch.Tensor | None = None, off2: int = 0,
-                 c_valid: int | None = None, bias: torch.Tensor | None = None) -> None:
-    """dst[..., off:off+c_valid] = relu(src[..., :c_valid] + bias) for dense channels-last buffers [..., C]."""
+                 c_valid: int | None = None, bias: torch.Tensor | None = None, src2: torch.Tensor | None = None) -> None:
+    """dst[..., off:off+c_valid] = relu(src[..., :c_valid] (+ src2) + bias) for dense channels-last buffers [..., C]."""
     C = src.shape[-1]
     npix = src.numel() // C
-    check(load().sdof_relu_scatter(ptr(src), ptr(bias), npix, C, ptr(dst1), dst1.shape[-1], off1, ptr(dst2),
+    check(load().sdof_relu_scatter(ptr(src), ptr(src2), ptr(bias), npix, C, ptr(dst1), dst1.shape[-1], off1, ptr(dst2),
                                    dst2.shape[-1] if dst2 is not None else 0, off2, C if c_valid is None else c_valid,
                                    stream_ptr(src.device)), 'sdof_relu_scatter')
 

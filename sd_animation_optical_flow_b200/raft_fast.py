@@ -5,7 +5,8 @@ iteration is ~25 kernels instead of ~100:
   * every activation of the update block lives in a dense NHWC buffer, so cuDNN's tensor-core convolutions
     run without the NCHW<->NHWC transposes eager PyTorch wraps around each of them;
   * the `torch.cat`s of update.py (hx = [h, x], [r*h, x], [cor, flo], [out, flow]) are persistent
-    concatenated buffers (HX, RHX, CF) whose channel slices are written in place by the producers;
+    concatenated buffer HX = [h | motion | flow] whose channel slices are written in place by the producers
+    (the other concatenations of update.py disappear algebraically, see FastRaft.__init__);
   * convz and convr (same input) are one convolution with concatenated filters;
   * the element-wise work between convolutions is four hand-written kernels (csrc/raft_glue.cu), the
     correlation lookup writes channels-last directly (csrc/corr_lookup.cu), and the convex 8x upsample
@@ -149,6 +150,11 @@ class FastRaft:
         self.convc1, self.convc2 = _w(e.convc1), _w(e.convc2)
         self.convf1, self.convf2 = _w(e.convf1), _w(e.convf2)
         self.conv = _w(e.conv, pad_out_to=128)           # 126 -> 128 filters (two zero filters) keeps rows 16-byte aligned
+        # the same convolution split over its two input groups [cor(192) | flo(64)] (update.py:94-95): each branch
+        # convolves its own group on its own stream and the partial results are summed by relu_scatter
+        wc = self.conv[0]
+        self.conv_cor = (wc[:, :192].contiguous(memory_format=CL), None, e.conv.padding)
+        self.conv_flo = (wc[:, 192:].contiguous(memory_format=CL), None, e.conv.padding)
         # GRU input hx = [h | inp | motion | flow] (update.py:47).  `inp` (the context features) does not change over the
         # iterations, so its share of convz/convr/convq is convolved ONCE per pair into per-pixel bias maps (exact by
         # linearity) and the per-iteration convolutions run on [h | motion | flow] only: 256 instead of 384 input channels.
@@ -247,7 +253,7 @@ class FastRaft:
         RH = torch.empty((B, h, w, hd), device=dev)                       # r*h                      (update.py:50)
         ZRMAP = [torch.empty((B, h, w, 2 * hd), device=dev) for _ in (0, 1)]   # bias + conv(inp) of convz|convr, per GRU pass
         QMAP = [torch.empty((B, h, w, hd), device=dev) for _ in (0, 1)]        # bias + conv(inp) of convq
-        CF = torch.empty((B, h, w, 256), device=dev)                      # [cor(192) | flo(64)]  (update.py:94)
+        MF = torch.empty((B, h, w, 128), device=dev)                      # flow-branch share of the motion-encoder output conv
         corr = torch.empty((B, h, w, 4 * 81), device=dev)
         flow = torch.empty((B, h, w, 2), device=dev)
         fh_scratch = torch.empty((B * h * w * 18,), device=dev)          # tap products of the flow head's second conv
@@ -276,15 +282,14 @@ class FastRaft:
             side.wait_stream(main)
             with torch.cuda.stream(side):                                 # flow branch (update.py:93-94)
                 f1 = ops.conv7x7_c2_relu(flow, self.convf1_t, self.convf1[1]) if self.own_convf1 else self._conv_relu(flow, self.convf1)
-                f2 = self._conv(f1, self.convf2)
-                ops.relu_scatter(f2, CF, 192, bias=self.convf2[1])
+                f2 = self._conv_relu(f1, self.convf2)                     # flo (64 channels)
+                MF.copy_(self._conv(f2, self.conv_flo))                   # its share of conv([cor | flo]) (update.py:95)
                 del f1, f2
             ops.corr_lookup_nhwc(pyr, coords1, 4, corr)                   # correlation branch (update.py:91-92)
-            c2 = self._conv(self._conv_relu(corr, self.convc1), self.convc2)
-            ops.relu_scatter(c2, CF, 0, bias=self.convc2[1])
+            c2 = self._conv_relu(self._conv_relu(corr, self.convc1), self.convc2)   # cor (192 channels)
+            mc = self._conv(c2, self.conv_cor)                            # 126 (+2 zero) channels, cor share
             main.wait_stream(side)
-            mot = self._conv(CF, self.conv)                               # 126 (+2 zero) channels
-            ops.relu_scatter(mot, HX, mo, c_valid=126, bias=self.conv[1])
+            ops.relu_scatter(mc, HX, mo, c_valid=126, bias=self.conv[1], src2=MF)
             for p in (0, 1):                                              # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
                 zr = self._conv(HX, self.zr[p])                           # [z | r | x-share of q], 3*hd channels
                 ops.gru_rh(zr, H, RH, bias_zr=ZRMAP[p])
