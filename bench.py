@@ -53,7 +53,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi sampling DURING the timed regions (B200_PROFILING.md recipe: -lms 200; a 50 ms period measurably
+    perturbed the host-timed e2e loop on some boxes through driver-lock contention)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -68,7 +69,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '50'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          '-lms', '200'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -247,7 +248,7 @@ def run_ours(args):
         flow = algo.calc(bgr1, bgr2)                      # H2D 2 frames, D2H flow
         return ofgen.warp_frame(bgrs, flow)               # H2D frame + flow, D2H warped frame
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
