@@ -53,8 +53,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed regions (B200_PROFILING.md recipe: -lms 200; a 50 ms period measurably
-    perturbed the host-timed e2e loop on some boxes through driver-lock contention)."""
+    """nvidia-smi sampling DURING the timed regions (B200_PROFILING.md recipe).  Started before the warm-up steps so it is
+    already polling when the timed region begins; 100 ms period (a 50 ms period perturbed the host-timed e2e loop on one
+    box through driver-lock contention)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -69,7 +70,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -199,6 +200,9 @@ def run_ours(args):
         flow = eng.estimate_flow(d1, d2)                 # [1,768,512,2]
         return ops.warp(dsty, flow, 'cv2_cubic', -1.0)   # ofgen.warp_frame: previous stylised frame at x - flow
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     # kernels of THIS library per step, counted on one eager (non-graph) step: graph replays re-run
@@ -210,9 +214,6 @@ def run_ours(args):
     launches_per_step = _capi.launch_count() - c0
     eng.use_cuda_graph = graphed
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     s.record()
