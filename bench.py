@@ -379,10 +379,14 @@ def run_ours(args):
     cpu = cpu_baseline_leg(args.cpu_budget_s) if args.cpu_budget_s > 0 else None
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': args.corr_precision, 'data': 'synthetic',
+            'dtype': 'tf32', 'data': 'synthetic',
             'config': {'workload': 'configs[1]: RAFT all-pairs correlation + warp, single 512x768 frame pair per GPU',
                        'H': H, 'W': W, 'iters': ITERS, 'weights': 'random-init (name-seeded)', 'corr_precision': args.corr_precision,
-                       'conv_precision': 'bf16 autocast' if args.mixed_precision else 'cuDNN fp32 (TF32 allowed, torch default)',
+                       'conv_precision': 'bf16 autocast' if args.mixed_precision else 'cuDNN TF32 tensor cores, fp32 accumulate (torch default = what the reference runs on this GPU)',
+                       'precision_note': 'dtype names the arithmetic of the bulk of the step (TF32 convolutions); the correlation volume uses '
+                                         f'{args.corr_precision} operands with fp32 accumulation, the thin convolutions and all glue fp32, the warp exact integer (u8). '
+                                         'Final flow vs the reference RAFT (fp32): EPE 3e-4 px mean with the fp16/tf32 volume, 1e-5 px with --corr-precision 3xtf32 '
+                                         '(tests/test_gpu_raft.py)',
                        'cuda_graph': not args.no_graph, 'pairs_per_step_per_gpu': 1, 'parallelism': f'pairs x{world}, no collective',
                        'l2': 'per-step working set (200.5 MB pyramid rewritten every step + activations) exceeds the 126 MB L2; no explicit flush'},
             'roofline': roofline, 'roofline_extra': extra, 'batched': batched, 'clip': clip_leg, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
