@@ -311,6 +311,9 @@ int sdof_resize_bicubic_u8(const uint8_t* src, int B, int H, int W, int oh, int 
                            int64_t workspace_bytes, sdof_stream_t stream);
 
 /* ---------------------------------------------------------------- diagnostics */
+/* n / d (d >= 1, n < 2^31) evaluated on the host with the multiply-high constants the tiled kernels use for their tile
+ * coordinates: lets the CPU tests pin those constants. */
+uint32_t sdof_fastdiv_u31(uint32_t n, uint32_t d);
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t sdof_launch_count(void);
 

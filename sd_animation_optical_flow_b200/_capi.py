@@ -37,6 +37,7 @@ SIGNATURES = {
     'sdof_abi_version': (c_int, []),
     'sdof_last_error': (c_char_p, []),
     'sdof_launch_count': (c_int64, []),
+    'sdof_fastdiv_u31': (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
     'sdof_corr_pyramid_layout': (c_int, [c_int64, c_int, c_int, c_int, POINTER(PyramidLayout)]),
     'sdof_corr_volume_workspace_bytes': (c_int64, [c_int] * 8),
     'sdof_corr_volume_pyramid': (c_int, [_P, _P] + [c_int] * 8 + [_P, _P, c_int64, _P]),

@@ -284,6 +284,13 @@ int sdof_warp_cubic_u8(const uint8_t* src, const float* flow, int B, int src_bat
   return SDOF_OK;
 }
 
+// Host evaluation of the multiply-high division the tiled kernels use for tile coordinates (warp_tiled.cuh::wt_make_div /
+// wt_div), exported so the CPU test-suite can check the magic numbers against n / d without a GPU.
+uint32_t sdof_fastdiv_u31(uint32_t n, uint32_t d) {
+  const sdof::WtDiv m = sdof::wt_make_div(d);
+  return m.mul ? (uint32_t)(((uint64_t)n * m.mul) >> 32) >> m.shr : n;
+}
+
 int sdof_warp_cubic_f32(const float* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
                         int W, float sign, float* dst, sdof_stream_t stream) {
   return sdof::launch_generic<float, true>("sdof_warp_cubic_f32", src, flow, B, src_batched, Hs, Ws, C, H, W, sign, dst,

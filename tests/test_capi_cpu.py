@@ -144,3 +144,17 @@ def test_blur_and_resample_host_tables_match_the_oracle(lib):
         for i in range(n_out):
             assert b[2 * i] == bounds[i] and b[2 * i + 1] == len(coeffs[i]), (n_in, n_out, i)
             assert list(c[i * ks.value:i * ks.value + len(coeffs[i])]) == [int(v) for v in coeffs[i]], (n_in, n_out, i)
+
+
+def test_tile_coordinate_division_constants(lib):
+    """warp_tiled.cuh::wt_make_div: floor(n / d) by one multiply-high and a shift must be exact for every 0 <= n < 2^31."""
+    import random
+    rnd = random.Random(0)
+    ds = list(range(1, 300)) + [2 ** k for k in range(1, 31)] + [2 ** k - 1 for k in range(2, 31)] + [2 ** k + 1 for k in range(1, 30)] + \
+        [rnd.randrange(1, 2 ** 31) for _ in range(300)]
+    for d in ds:
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, 2 ** 31 - 2, (2 ** 31 - 1) // d * d, (2 ** 31 - 1) // d * d - 1]
+        ns += [rnd.randrange(0, 2 ** 31) for _ in range(40)]
+        for n in ns:
+            if 0 <= n < 2 ** 31:
+                assert lib.sdof_fastdiv_u31(n, d) == n // d, (n, d)
