@@ -9,10 +9,11 @@ north star names, so a clip's flow -> warp -> mask -> composite never leaves the
 The convolutions run in PyTorch/cuDNN; the all-pairs correlation volume + pyramid, the
 per-iteration lookup, the warp and the mask/composite steps run in this package's sm_100a
 kernels.  The whole forward for one input shape can be captured into a CUDA graph
-(`use_cuda_graph=True`) so the ~1000 launches of a 20-iteration pass replay without host work.
+(`use_cuda_graph`, the default on the fast path) so the ~480 launches of a 20-iteration pass replay without host work.
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from types import SimpleNamespace
 
 import torch
@@ -29,8 +30,9 @@ def warp(img: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: f
 class RaftEngine:
     def __init__(self, checkpoint: str | None = None, iters: int = 20, small: bool = False,
                  corr_precision: str = 'fp16', alternate_corr: bool = False, mixed_precision: bool = False,
-                 channels_last: bool = False, use_cuda_graph: bool = False, device=None, seed: int = 0,
-                 fast: bool | None = None, cudnn_benchmark: bool = True, fast_options: dict | None = None):
+                 channels_last: bool = False, use_cuda_graph: bool | None = None, device=None, seed: int = 0,
+                 fast: bool | None = None, cudnn_benchmark: bool = True, fast_options: dict | None = None,
+                 max_graphs: int = 4):
         if not torch.cuda.is_available():
             raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
@@ -51,8 +53,8 @@ class RaftEngine:
             model = model.to(memory_format=torch.channels_last)
         self.model = model
         self.channels_last = channels_last
-        self.use_cuda_graph = use_cuda_graph
-        self._graphs = {}
+        self._graphs = OrderedDict()      # (kind, input shape, iters, bgr) -> (graph, static inputs, static output), LRU
+        self.max_graphs = max_graphs
         # the hand-scheduled NHWC forward (raft_fast.py) is the default for the configuration the scripts use
         if fast is None:
             fast = not small and not alternate_corr and not mixed_precision and not channels_last
@@ -61,6 +63,9 @@ class RaftEngine:
         if fast:
             from .raft_fast import FastRaft
             self.fast = FastRaft(self.model, corr_precision, **self.fast_options)
+        # CUDA graphs by default on the fast path (7.2 -> 4.0 ms per 768x512 pair): one graph per input shape, captured at
+        # the first call with that shape (about a second), the `max_graphs` most recently used shapes are kept
+        self.use_cuda_graph = (self.fast is not None) if use_cuda_graph is None else bool(use_cuda_graph)
 
     def load_checkpoint(self, path: str):
         self.model.load_state_dict(torch.load(path, map_location='cpu'))
@@ -79,6 +84,17 @@ class RaftEngine:
             self.fast = FastRaft(self.model, self.args.corr_precision, **self.fast_options)
         return self
 
+    def _graph_get(self, key):
+        ent = self._graphs.get(key)
+        if ent is not None:
+            self._graphs.move_to_end(key)
+        return ent
+
+    def _graph_put(self, key, ent):
+        self._graphs[key] = ent
+        while len(self._graphs) > max(1, self.max_graphs):
+            self._graphs.popitem(last=False)   # least recently used shape: its graph and static buffers are released
+
     # ---------------------------------------------------------------- core
     @torch.no_grad()
     def _forward(self, im1: torch.Tensor, im2: torch.Tensor) -> torch.Tensor:
@@ -95,7 +111,7 @@ class RaftEngine:
     @torch.no_grad()
     def _forward_graphed(self, im1: torch.Tensor, im2: torch.Tensor) -> torch.Tensor:
         key = (tuple(im1.shape), self.iters)
-        ent = self._graphs.get(key)
+        ent = self._graph_get(key)
         if ent is None:
             s1, s2 = im1.clone(), im2.clone()
             side = torch.cuda.Stream(device=self.device)
@@ -108,7 +124,7 @@ class RaftEngine:
             with torch.cuda.graph(g):
                 out = self._forward(s1, s2)
             ent = (g, s1, s2, out)
-            self._graphs[key] = ent
+            self._graph_put(key, ent)
         g, s1, s2, out = ent
         s1.copy_(im1)
         s2.copy_(im2)
@@ -128,7 +144,7 @@ class RaftEngine:
     @torch.no_grad()
     def _forward_u8_graphed(self, a: torch.Tensor, b: torch.Tensor, pad, bgr: bool = False) -> torch.Tensor:
         key = ('u8', tuple(a.shape), self.iters, bool(bgr))
-        ent = self._graphs.get(key)
+        ent = self._graph_get(key)
         if ent is None:
             s1, s2 = a.clone(), b.clone()
             side = torch.cuda.Stream(device=self.device)
@@ -141,7 +157,7 @@ class RaftEngine:
             with torch.cuda.graph(g):
                 out = self._forward_u8(s1, s2, pad, bgr)
             ent = (g, s1, s2, out)
-            self._graphs[key] = ent
+            self._graph_put(key, ent)
         g, s1, s2, out = ent
         s1.copy_(a)
         s2.copy_(b)

@@ -168,7 +168,7 @@ def test_raft2_calc_dropin(cuda, golden):
 
 
 def test_cuda_graph_replay_equals_eager(cuda):
-    eager = _engine('basic', cuda)
+    eager = _engine('basic', cuda, use_cuda_graph=False)
     graphed = _engine('basic', cuda, use_cuda_graph=True)
     img1, img2 = gi.raft_inputs('basic')
     a = torch.from_numpy(img1).to(cuda)[None]

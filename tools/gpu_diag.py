@@ -156,7 +156,7 @@ def warp_exact():
 def raft_perf():
     from sd_animation_optical_flow_b200.engine import RaftEngine
     img = torch.randint(0, 256, (1, 768, 512, 3), dtype=torch.uint8, device=dev)
-    for kw in (dict(fast=False), dict(fast=False, use_cuda_graph=True), dict(fast=True), dict(fast=True, use_cuda_graph=True)):
+    for kw in (dict(fast=False), dict(fast=False, use_cuda_graph=True), dict(fast=True, use_cuda_graph=False), dict(fast=True, use_cuda_graph=True)):
         try:
             eng = RaftEngine(iters=20, device=dev, **kw)
             t0 = time.time()
