@@ -187,6 +187,8 @@ def warp(src: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: f
         raise RuntimeError(f'src must be uint8 or float32, got {s.dtype}')
     s = s.contiguous()
     out = torch.empty((B, H, W, C), dtype=s.dtype, device=s.device)
+    if B == 0:   # empty batch: nothing to launch (empty tensors have no device pointer)
+        return out[..., 0] if squeeze_c else out
     lib = load()
     fn = {('cv2_cubic', u8): lib.sdof_warp_cubic_u8, ('cv2_cubic', f32): lib.sdof_warp_cubic_f32,
           ('bilinear', u8): lib.sdof_warp_bilinear_u8, ('bilinear', f32): lib.sdof_warp_bilinear_f32}[(mode, s.dtype)]
@@ -319,6 +321,8 @@ def warp_mask_composite(src: torch.Tensor, base: torch.Tensor, flow: torch.Tenso
         raise RuntimeError('src must be [B or 1,H,W,3] and base [B,H,W,3]')
     out = torch.empty_like(base)
     mask = torch.empty((B, H, W), dtype=u8, device=base.device)
+    if B == 0:
+        return out, mask
     check(load().sdof_warp_mask_composite(ptr(src), ptr(base), ptr(flow), ptr(weight_map), B, int(src.shape[0] == B), H, W,
                                           float(thres), ksize, ptr(out), ptr(mask), stream_ptr(base.device)),
           'sdof_warp_mask_composite')
@@ -498,6 +502,8 @@ def mask_blur_composite(mask: torch.Tensor, image: torch.Tensor | None, referenc
         C = image.shape[3]
         out = torch.empty_like(image)
     blurred = torch.empty_like(mask)
+    if B == 0:
+        return out, blurred
     check(load().sdof_mask_blur_composite(ptr(mask), ptr(image), ptr(reference), B, H, W, C, float(mask_blur), ptr(blurred), ptr(out),
                                           stream_ptr(mask.device)), 'sdof_mask_blur_composite')
     return out, blurred
