@@ -158,3 +158,23 @@ def test_tile_coordinate_division_constants(lib):
         for n in ns:
             if 0 <= n < 2 ** 31:
                 assert lib.sdof_fastdiv_u31(n, d) == n // d, (n, d)
+
+
+def test_header_and_ctypes_binding_agree_on_every_signature():
+    """Parameter count and pointer/scalar kind of every declaration in include/sdof_b200.h against _capi.SIGNATURES
+    (an ABI drift between the documented header and the binding the product uses must fail here, without a GPU)."""
+    from ctypes import c_void_p
+    from sd_animation_optical_flow_b200 import _capi
+    text = open(os.path.join(ROOT, 'include', 'sdof_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    decls = re.findall(r'\b[a-z_0-9]+\s*\*?\s*(sdof_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    assert len(decls) == len(_capi.SIGNATURES)
+    for name, params in decls:
+        params = ' '.join(params.split())
+        plist = [] if params in ('', 'void') else [p.strip() for p in params.split(',')]
+        _, argtypes = _capi.SIGNATURES[name]
+        assert len(plist) == len(argtypes), f'{name}: header has {len(plist)} parameters, binding {len(argtypes)}'
+        for p, a in zip(plist, argtypes):
+            is_ptr_h = '*' in p or 'sdof_stream_t' in p
+            is_ptr_b = a is c_void_p or hasattr(a, 'contents') or a is ctypes.c_char_p
+            assert is_ptr_h == is_ptr_b, f'{name}: parameter "{p}" vs binding {a}'
