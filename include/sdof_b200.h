@@ -314,6 +314,10 @@ int sdof_resize_bicubic_u8(const uint8_t* src, int B, int H, int W, int oh, int 
 /* n / d (d >= 1, n < 2^31) evaluated on the host with the multiply-high constants the tiled kernels use for their tile
  * coordinates: lets the CPU tests pin those constants. */
 uint32_t sdof_fastdiv_u31(uint32_t n, uint32_t d);
+/* Tiles of sdof_warp_cubic_u8's tiled kernel on the current device since the last reset: out[0] = served from the staged
+ * shared-memory source rectangle (the fast path the roofline is quoted on), out[1] = per-pixel global-memory fallback
+ * (source rectangle of the 32x32 tile larger than the group's 62 KB region: non-smooth flow).  Synchronises the device. */
+int sdof_warp_tile_stats(int64_t* out /* host, 2 values */, int reset);
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t sdof_launch_count(void);
 

@@ -191,6 +191,40 @@ def ref_greedy():
     print('greedy.npz order', order)
 
 
+def ref_raft_full():
+    """Full-size goldens of the configurations bench.py times: the reference RAFT (fp32, CPU) at
+    768x512 (config 2/3/4 size, the bench pair of rank 0) and 720x1280 (config 5 size), iters=20 as in ofgen.py:77.
+    flow_low is stored whole, flow_up on the lattice gi.full_lattice (one pixel per 8x8 block) to keep the fixture small."""
+    import torch
+    sys.path.insert(0, os.path.join(REF, 'RAFT', 'core'))
+    from raft import RAFT  # reference RAFT/core/raft.py
+    from sd_animation_optical_flow_b200.raft import fill_weights_by_name
+
+    class namespace:  # ofgen.py:51-53
+        def __contains__(self, m):
+            return hasattr(self, m)
+
+    out = {}
+    for name, cfg in gi.RAFT_FULL_CASES.items():
+        args = namespace()
+        args.small = False
+        args.mixed_precision = False
+        args.alternate_corr = False
+        model = RAFT(args)
+        gi.raft_full_weights(model, name)
+        model.eval()
+        img1, img2 = gi.raft_full_inputs(name)
+        t1 = torch.from_numpy(img1).permute(2, 0, 1).float()[None]
+        t2 = torch.from_numpy(img2).permute(2, 0, 1).float()[None]
+        with torch.no_grad():
+            flow_low, flow_up = model(t1, t2, iters=cfg['iters'], test_mode=True)
+        ys, xs = gi.full_lattice(*cfg['hw'])
+        out[f'{name}_flow_low'] = flow_low[0].numpy().astype(np.float32)
+        out[f'{name}_flow_up_s'] = np.ascontiguousarray(flow_up[0].numpy()[:, ys][:, :, xs]).astype(np.float32)
+        print(name, 'flow_up', tuple(flow_up.shape), 'mean |flow|', float(flow_up.abs().mean()), 'max', float(flow_up.abs().max()))
+    np.savez_compressed(os.path.join(GOLDEN, 'raft_full.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     ref_warp()
@@ -198,3 +232,4 @@ if __name__ == '__main__':
     ref_greedy()
     ref_corr()
     ref_raft()
+    ref_raft_full()

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int16, c_int32, c_int64, c_void_p
 
 import torch
@@ -37,6 +38,7 @@ SIGNATURES = {
     'sdof_abi_version': (c_int, []),
     'sdof_last_error': (c_char_p, []),
     'sdof_launch_count': (c_int64, []),
+    'sdof_warp_tile_stats': (c_int, [POINTER(c_int64), c_int]),
     'sdof_fastdiv_u31': (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
     'sdof_corr_pyramid_layout': (c_int, [c_int64, c_int, c_int, c_int, POINTER(PyramidLayout)]),
     'sdof_corr_volume_workspace_bytes': (c_int64, [c_int] * 8),
@@ -118,13 +120,34 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+_tls = threading.local()
+
+
 def check(rc: int, what: str) -> None:
+    """Status check of a library call; also switches back to the device that was current before `stream_ptr` made the
+    tensors' device current for this call (see stream_ptr)."""
+    prev = getattr(_tls, 'restore_device', None)
+    if prev is not None:
+        _tls.restore_device = None
+        torch.cuda.set_device(prev)
     if rc != 0:
         msg = load().sdof_last_error()
         raise SdofError(f'{what} failed (status {rc}): {msg.decode() if msg else "?"}')
 
 
 def stream_ptr(device=None) -> c_void_p:
+    """Current torch stream of `device`, the stream handle every entry point takes.  The library launches on the CURRENT
+    CUDA device and keys its per-device state (weight tables, SM count, kernel attributes) on it, so when the tensors'
+    device is not the current one it is made current here, for the duration of the call: every wrapper is written as
+    `check(lib.fn(..., stream_ptr(dev)), name)`, arguments are evaluated before the call, and `check` switches back.
+    (The reference's PDCNetAux(device=cuda:N), ofgen_keyframe_inpaint.py:550,1128, runs on a non-default device.)"""
+    if device is not None:
+        idx = torch.device(device).index
+        cur = torch.cuda.current_device()
+        if idx is not None and idx != cur:
+            if getattr(_tls, 'restore_device', None) is None:
+                _tls.restore_device = cur
+            torch.cuda.set_device(idx)
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -32,6 +32,11 @@ int get_cubic_tables(CubicTables* out) {
   return SDOF_OK;
 }
 
+// Diagnostic counters of the tiled kernel: [0] tiles served from the staged shared-memory rectangle, [1] tiles that fell
+// back to the per-pixel global-memory path (source rectangle larger than the group's region).  One atomic pair per group
+// at kernel exit; read (and reset) by sdof_warp_tile_stats.
+__device__ unsigned long long g_wt_stats[2];
+
 // ---------------------------------------------------------------- cubic, u8, C = 3
 // Persistent CTAs (one per SM, 3 groups of 256 threads); a group walks 32x32 output tiles
 // (warp_tiled.cuh).  `old_src_end` is the bound of the per-pixel fallback path (cubic_u8_c3).
@@ -55,6 +60,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
   // HBM stream (8 of the 14 bytes per pixel) is always in flight.
   int b, tyi, txi;
   wt_tile_coords(T, t, b, tyi, txi);
+  int n_tiles = 0, n_fallback = 0;
   float2 f[4];
   {
     const int gx = min(txi * kWtTile + lane, W - 1);
@@ -91,6 +97,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
     // ---- C: taps from shared memory, packed row stores
     const bool seg_full = dst_vec_ok && (tx0 + kWtTile <= W);
     const bool lane_valid = tx0 + lane < W;
+    ++n_tiles;
+    n_fallback += R.staged ? 0 : 1;
     // all four pixels first (independent LDS -> dp2a chains the scheduler can interleave), then the row stores
     unsigned v[4];
     if (R.staged) {
@@ -122,6 +130,10 @@ __global__ void __launch_bounds__(kWtThreads, 1) warp_cubic_u8c3_tiled_kernel(
     b = bn;
     tyi = tyn;
     txi = txn;
+  }
+  if (gt == 0) {
+    atomicAdd(&g_wt_stats[0], (unsigned long long)(n_tiles - n_fallback));
+    if (n_fallback) atomicAdd(&g_wt_stats[1], (unsigned long long)n_fallback);
   }
 }
 
@@ -281,6 +293,23 @@ int sdof_warp_cubic_u8(const uint8_t* src, const float* flow, int B, int src_bat
   warp_cubic_u8c3_tiled_kernel<<<grid, kWtThreads, sizeof(WtSmem), as_stream(stream)>>>(
       tabs.i16, src, flow, dst, T, Hs, Ws, H, W, bstride, sign, old_src_end, dst_vec);
   SDOF_LAUNCH_CHECK("warp_cubic_u8c3_tiled_kernel");
+  return SDOF_OK;
+}
+
+// Diagnostic (host-synchronising): tiles of sdof_warp_cubic_u8's tiled kernel served from the staged shared-memory
+// rectangle (out[0]) and by the per-pixel fallback (out[1]) on the current device since the last reset.
+int sdof_warp_tile_stats(int64_t* out /* host, 2 */, int reset) {
+  using namespace sdof;
+  SDOF_REQUIRE(out != nullptr, "sdof_warp_tile_stats: out is NULL");
+  unsigned long long h[2] = {0, 0};
+  SDOF_CUDA(cudaDeviceSynchronize());
+  SDOF_CUDA(cudaMemcpyFromSymbol(h, g_wt_stats, sizeof(h)));
+  out[0] = (int64_t)h[0];
+  out[1] = (int64_t)h[1];
+  if (reset) {
+    const unsigned long long z[2] = {0, 0};
+    SDOF_CUDA(cudaMemcpyToSymbol(g_wt_stats, z, sizeof(z)));
+  }
   return SDOF_OK;
 }
 

@@ -13,6 +13,7 @@ kernels.  The whole forward for one input shape can be captured into a CUDA grap
 """
 from __future__ import annotations
 
+import contextlib
 from collections import OrderedDict
 from types import SimpleNamespace
 
@@ -20,6 +21,15 @@ import torch
 
 from . import ops
 from .raft import RAFT, InputPadder, fill_weights_by_name
+
+
+def load_raft_state_dict(path: str) -> dict:
+    """State dict of a RAFT checkpoint.  The public `raft-*.pth` files were saved from `nn.DataParallel(RAFT(args))`
+    (which is why the reference wraps its model the same way, ofgen.py:67-68), so their keys carry a `module.` prefix."""
+    sd = torch.load(path, map_location='cpu')
+    if isinstance(sd, dict) and 'state_dict' in sd and not any(k.endswith('.weight') for k in sd):
+        sd = sd['state_dict']
+    return {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in sd.items()}
 
 
 def warp(img: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: float = 1.0) -> torch.Tensor:
@@ -37,17 +47,17 @@ class RaftEngine:
             raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.iters = iters
-        if cudnn_benchmark:
-            # let cuDNN time its engines once per convolution shape (during the first call / the graph warm-up):
-            # its heuristics pick slow kernels for several of RAFT's small-batch shapes
-            torch.backends.cudnn.benchmark = True
+        # let cuDNN time its engines once per convolution shape (during the first call / the graph warm-up): its heuristics
+        # pick slow kernels for several of RAFT's small-batch shapes.  Scoped to this engine's own convolutions
+        # (`_cudnn_scope`), not set process-wide: the host process also runs the Stable-Diffusion model.
+        self.cudnn_benchmark = bool(cudnn_benchmark)
         self.args = SimpleNamespace(small=small, mixed_precision=mixed_precision, alternate_corr=alternate_corr,
                                     corr_precision=corr_precision)
         model = RAFT(self.args)
         if checkpoint is None:
             fill_weights_by_name(model, seed)
         else:
-            model.load_state_dict(torch.load(checkpoint, map_location='cpu'))
+            model.load_state_dict(load_raft_state_dict(checkpoint))
         model = model.to(self.device).eval()
         if channels_last:
             model = model.to(memory_format=torch.channels_last)
@@ -68,7 +78,7 @@ class RaftEngine:
         self.use_cuda_graph = (self.fast is not None) if use_cuda_graph is None else bool(use_cuda_graph)
 
     def load_checkpoint(self, path: str):
-        self.model.load_state_dict(torch.load(path, map_location='cpu'))
+        self.model.load_state_dict(load_raft_state_dict(path))
         self._graphs.clear()
         if self.fast is not None:
             from .raft_fast import FastRaft
@@ -83,6 +93,19 @@ class RaftEngine:
             from .raft_fast import FastRaft
             self.fast = FastRaft(self.model, self.args.corr_precision, **self.fast_options)
         return self
+
+    @contextlib.contextmanager
+    def _scope(self):
+        """Everything this engine launches runs with ITS device current (the C library launches on the current device and
+        keys its tables on it) and, on request, with cuDNN's benchmark mode on for this engine's convolutions only."""
+        prev = torch.backends.cudnn.benchmark
+        try:
+            if self.cudnn_benchmark:
+                torch.backends.cudnn.benchmark = True
+            with torch.cuda.device(self.device):
+                yield
+        finally:
+            torch.backends.cudnn.benchmark = prev
 
     def _graph_get(self, key):
         ent = self._graphs.get(key)
@@ -169,31 +192,38 @@ class RaftEngine:
         """img1, img2: RGB (bgr=True: BGR) uint8 (or float 0..255) CUDA tensors [B,H,W,3].  Returns flow of img1 -> img2
         on img1's grid, [B,H,W,2] fp32 (x, y pixels).  Images are replicate-padded to a multiple of 8
         like the reference (utils/utils.py:7-19); unpad=False reproduces RAFT_2.calc, which returns
-        the padded-size flow (ofgen.py:75-78)."""
+        the padded-size flow (ofgen.py:75-78).  The result is always a fresh tensor owned by the caller."""
         if img1.dim() != 4 or img1.shape[-1] != 3 or img1.shape != img2.shape:
             raise RuntimeError(f'images must both be [B,H,W,3], got {tuple(img1.shape)} and {tuple(img2.shape)}')
         if not img1.is_cuda or not img2.is_cuda:
             raise RuntimeError('estimate_flow takes CUDA tensors; use ofgen.RAFT_2.calc for numpy frames')
-        if self.fast is not None and img1.dtype == torch.uint8 and img2.dtype == torch.uint8:
-            B, H, W, _ = img1.shape
-            pad = InputPadder((H, W))._pad
-            fwd = self._forward_u8_graphed if self.use_cuda_graph else self._forward_u8
-            flow_up = fwd(img1.contiguous(), img2.contiguous(), pad, bgr)
-            if unpad and any(pad):
-                Hp, Wp = flow_up.shape[1:3]
-                return flow_up[:, pad[2]:Hp - pad[3], pad[0]:Wp - pad[1]].contiguous()
-            return flow_up.clone() if self.use_cuda_graph else flow_up
-        if bgr:
-            img1, img2 = img1.flip(-1), img2.flip(-1)
-        im1 = img1.permute(0, 3, 1, 2).float()
-        im2 = img2.permute(0, 3, 1, 2).float()
-        padder = InputPadder(im1.shape)
-        im1, im2 = padder.pad(im1, im2)
-        fwd = self._forward_graphed if self.use_cuda_graph else self._forward
-        flow_up = fwd(im1.contiguous(), im2.contiguous())
-        if unpad:
-            flow_up = padder.unpad(flow_up)
-        return flow_up.permute(0, 2, 3, 1).contiguous()
+        if img1.device != self.device or img2.device != self.device:
+            raise RuntimeError(f'images must live on the engine\'s device {self.device}, got {img1.device} / {img2.device}')
+        with self._scope():
+            if self.fast is not None and img1.dtype == torch.uint8 and img2.dtype == torch.uint8:
+                B, H, W, _ = img1.shape
+                pad = InputPadder((H, W))._pad
+                fwd = self._forward_u8_graphed if self.use_cuda_graph else self._forward_u8
+                flow_up = fwd(img1.contiguous(), img2.contiguous(), pad, bgr)
+                if unpad and any(pad):
+                    Hp, Wp = flow_up.shape[1:3]
+                    flow_up = flow_up[:, pad[2]:Hp - pad[3], pad[0]:Wp - pad[1]]
+                if self.use_cuda_graph:
+                    # the graph's static output buffer is overwritten by the next replay: ALWAYS hand out a copy.  (A slice of
+                    # a B=1 tensor that only trims rows is already "contiguous", so .contiguous() would return the view.)
+                    return flow_up.clone(memory_format=torch.contiguous_format)
+                return flow_up.contiguous()
+            if bgr:
+                img1, img2 = img1.flip(-1), img2.flip(-1)
+            im1 = img1.permute(0, 3, 1, 2).float()
+            im2 = img2.permute(0, 3, 1, 2).float()
+            padder = InputPadder(im1.shape)
+            im1, im2 = padder.pad(im1, im2)
+            fwd = self._forward_graphed if self.use_cuda_graph else self._forward
+            flow_up = fwd(im1.contiguous(), im2.contiguous())
+            if unpad:
+                flow_up = padder.unpad(flow_up)
+            return flow_up.permute(0, 2, 3, 1).contiguous()
 
 
 class RaftFlowConfidence:
@@ -239,14 +269,16 @@ class RaftFlowConfidence:
 _default_engine: RaftEngine | None = None
 
 
-def estimate_flow(img1: torch.Tensor, img2: torch.Tensor, iters: int = 20, engine: RaftEngine | None = None) -> torch.Tensor:
-    """Module-level convenience: flow img1 -> img2 for [B,H,W,3] CUDA images with a process-wide engine."""
+def estimate_flow(img1: torch.Tensor, img2: torch.Tensor, iters: int | None = None, engine: RaftEngine | None = None) -> torch.Tensor:
+    """Module-level convenience: flow img1 -> img2 for [B,H,W,3] CUDA images.  `engine` = a caller-configured engine (its
+    own `iters` is used; passing a different `iters` together with an engine is an error, not a silent reconfiguration);
+    without one a process-wide default engine is created with `iters` (20 = ofgen.py:77 when omitted)."""
     global _default_engine
-    eng = engine
-    if eng is None:
-        if _default_engine is None:
-            _default_engine = RaftEngine(iters=iters)
-        eng = _default_engine
-    if eng.iters != iters:
-        eng.iters = iters
-    return eng.estimate_flow(img1, img2)
+    if engine is not None:
+        if iters is not None and iters != engine.iters:
+            raise ValueError(f'iters={iters} conflicts with the supplied engine (iters={engine.iters}); configure the engine instead')
+        return engine.estimate_flow(img1, img2)
+    want = 20 if iters is None else int(iters)
+    if _default_engine is None or _default_engine.iters != want or _default_engine.device != img1.device:
+        _default_engine = RaftEngine(iters=want, device=img1.device)
+    return _default_engine.estimate_flow(img1, img2)

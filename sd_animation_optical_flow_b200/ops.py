@@ -199,6 +199,14 @@ def warp(src: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: f
     return out[0] if squeeze_b else out
 
 
+def warp_tile_stats(reset: bool = True):
+    """(staged, fallback) tile counts of the tiled u8 cubic warp kernel on the current device since the last reset
+    (diagnostic; synchronises the device)."""
+    buf = (ctypes.c_int64 * 2)()
+    check(load().sdof_warp_tile_stats(buf, int(reset)), 'sdof_warp_tile_stats')
+    return int(buf[0]), int(buf[1])
+
+
 # --------------------------------------------------------------------------- confidence / masks
 def confidence_softmax(weight_map: torch.Tensor):
     """weight_map [B,K,H,W] -> (confidence, log_confidence) [B,H,W] (M1)."""
@@ -440,10 +448,9 @@ def instnorm_nhwc(x: torch.Tensor, stats: torch.Tensor, relu: bool = True, resid
             raise RuntimeError('residual must have the shape of x')
     if stats.dtype != torch.float64 or not stats.is_cuda or stats.numel() < N * C * 2 or not stats.is_contiguous():
         raise RuntimeError('stats must be a contiguous fp64 CUDA tensor with >= N*C*2 elements')
-    s = stream_ptr(x.device)
-    check(load().sdof_instnorm_stats_nhwc(ptr(x), N, hw, C, ptr(stats), s), 'sdof_instnorm_stats_nhwc')
-    check(load().sdof_instnorm_apply_nhwc(ptr(x), ptr(stats), ptr(residual), ptr(x), N, hw, C, float(eps), int(relu), s),
-          'sdof_instnorm_apply_nhwc')
+    check(load().sdof_instnorm_stats_nhwc(ptr(x), N, hw, C, ptr(stats), stream_ptr(x.device)), 'sdof_instnorm_stats_nhwc')
+    check(load().sdof_instnorm_apply_nhwc(ptr(x), ptr(stats), ptr(residual), ptr(x), N, hw, C, float(eps), int(relu),
+                                          stream_ptr(x.device)), 'sdof_instnorm_apply_nhwc')
     return x
 
 

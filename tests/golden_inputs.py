@@ -74,6 +74,44 @@ def raft_inputs(name: str):
     return shifted_pair(h, w, 100 + cfg['seed'])   # RGB uint8 [H,W,3] x2
 
 
+# the sizes bench.py times (configs[1..3]: 768x512; configs[4]: 720x1280), iters as in ofgen.py:77; 'S' is exactly the pair
+# of bench.py's rank 0 (bench.synthetic_pair(0)) with the bench weights (seed 0).  Name-seeded random weights make the
+# update block an amplifier: the flow runs away to ~100 px in 20 iterations (nothing like a trained model), so every case
+# also exists in a `calm` variant whose flow-head output convolution is scaled by `fh_scale` (flow stays a few px, the
+# regime a trained checkpoint works in and the one in which the correlation lookups stay inside the volume).
+RAFT_FULL_CASES = {
+    'S': dict(seed=0, iters=20, hw=(768, 512), pair_seed=1000, shift=(4, -3), fh_scale=1.0),
+    'S_calm': dict(seed=0, iters=20, hw=(768, 512), pair_seed=1000, shift=(4, -3), fh_scale=0.02),
+    'L': dict(seed=0, iters=20, hw=(720, 1280), pair_seed=1077, shift=(5, -2), fh_scale=1.0),
+    'L_calm': dict(seed=0, iters=20, hw=(720, 1280), pair_seed=1077, shift=(5, -2), fh_scale=0.02),
+}
+
+
+def raft_full_inputs(name: str):
+    cfg = RAFT_FULL_CASES[name]
+    h, w = cfg['hw']
+    return shifted_pair(h, w, cfg['pair_seed'], dx=cfg['shift'][0], dy=cfg['shift'][1])
+
+
+def raft_full_weights(model, name: str):
+    """Name-seeded weights of a full-size case on `model` (the reference RAFT or this package's)."""
+    from sd_animation_optical_flow_b200.raft import fill_weights_by_name
+    cfg = RAFT_FULL_CASES[name]
+    fill_weights_by_name(model, cfg['seed'])
+    if cfg['fh_scale'] != 1.0:
+        conv = model.update_block.flow_head.conv2
+        conv.weight.data.mul_(cfg['fh_scale'])
+        conv.bias.data.mul_(cfg['fh_scale'])
+    return model
+
+
+def full_lattice(H: int, W: int):
+    """Pixels of flow_up kept in the fixture: one per 8x8 block, its phase inside the block varying from block to block
+    so that all 64 positions of the convex-upsampling stencil are sampled."""
+    i, j = np.arange(H // 8), np.arange(W // 8)
+    return 8 * i + (3 * i) % 8, 8 * j + (5 * j) % 8
+
+
 WARP_CASES = ('small_u8', 'wild_u8', 'gray_f32', 'rgb_f32')
 
 

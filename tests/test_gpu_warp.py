@@ -46,6 +46,49 @@ def test_cubic_u8_full_size_bit_exact_vs_oracle(cuda, hw):
         assert np.array_equal(out, ref), f'{(out != ref).sum()} bytes differ'
 
 
+def smooth_flow(B, H, W, seed, dev):
+    """The flow generator of bench.py's warp roofline (camera / object motion): per frame a random translation of a few
+    pixels plus a low-frequency deformation (1/64-resolution Gaussian field of 4 px, bicubic-upsampled: |grad| ~ 0.1)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lo = torch.randn((B, 2, -(-H // 64), -(-W // 64)), generator=g, device=dev) * 4
+    f = torch.nn.functional.interpolate(lo, scale_factor=64, mode='bicubic', align_corners=False)[:, :, :H, :W]
+    return (f + 6 * torch.randn((B, 2, 1, 1), generator=g, device=dev)).permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize('hw', [(768, 512), (720, 1280)])
+def test_cubic_u8_full_size_smooth_flow_takes_the_staged_path(cuda, hw):
+    """The STAGED shared-memory path of the tiled kernel (the one the warp roofline is quoted on) at full size, bit-exact
+    against the oracle, with the kernel's own tile counters proving which path ran (the noisy-flow
+    full-size test above only exercises the per-pixel fallback)."""
+    from sd_animation_optical_flow_b200 import ops
+    H, W = hw
+    B = 3
+    rs = np.random.RandomState(W)
+    imgs = rs.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
+    flow = smooth_flow(B, H, W, 11, cuda)
+    ops.warp_tile_stats(reset=True)
+    out = ops.warp(_t(imgs, cuda), flow, 'cv2_cubic', 1.0).cpu().numpy()
+    staged, fallback = ops.warp_tile_stats(reset=True)
+    ntiles = B * -(-H // 32) * -(-W // 32)
+    assert staged + fallback == ntiles
+    print(f'{H}x{W}: {staged} of {ntiles} tiles staged ({100.0 * staged / ntiles:.1f} %)')
+    assert staged >= 0.95 * ntiles
+    fl = flow.cpu().numpy()
+    for b in range(B):
+        ref = wo.warp_frame_pdcnet(imgs[b], fl[b])
+        assert np.array_equal(out[b], ref), f'frame {b}: {(out[b] != ref).sum()} bytes differ'
+    # the same frames warped with x - flow (ofgen.warp_frame) and a shared source (one key frame, B flows)
+    out2 = ops.warp(_t(imgs[:1], cuda), flow, 'cv2_cubic', -1.0).cpu().numpy()
+    staged2, fallback2 = ops.warp_tile_stats(reset=True)
+    assert staged2 >= 0.95 * ntiles
+    assert np.array_equal(out2[1], wo.warp_frame_raft(imgs[0], fl[1]))
+    # and the noisy flow of the test above really is the fallback path
+    noisy = torch.randn((1, H, W, 2), device=cuda) * 12
+    ops.warp(_t(imgs[:1], cuda), noisy, 'cv2_cubic', 1.0)
+    s3, f3 = ops.warp_tile_stats(reset=True)
+    print(f'noisy 12 px flow: {f3} of {s3 + f3} tiles fall back')
+
+
 def test_cubic_u8_batched_and_shared_source(cuda):
     from sd_animation_optical_flow_b200 import ops
     rs = np.random.RandomState(8)
