@@ -24,6 +24,17 @@
 //   stored as one full 128-byte line of that source pixel's level map.
 // * Persistent grid: the flattened tile list (source block major, then level, then patch) is split
 //   into equal contiguous ranges, so a CTA reloads its resident block at most twice.
+// * Round 2: (a) the pyramid can be STORED in fp16 (`OUT_HALF`): half the bytes of the store-bound epilogue and of every
+//   lookup, and the whole 768x512 pyramid (100 MB) fits the 126 MB L2 across the 20 lookups of a pair.  Adjacent lanes
+//   exchange one register per column pair, so a lane stores a packed half2 (x, x+1) of ONE source pixel's map and a
+//   warp instruction still writes whole 64-byte runs.  fp16 storage rounds the volume to an 11-bit significand, which
+//   is what the TF32 convolution that consumes the lookup does to it anyway.
+//   (b) AUTO-RANGED 16-bit operands: a per-tensor power-of-two scale (from an abs-max pass) puts max|f| at 2^13..2^14
+//   before the fp16 conversion and is undone exactly in the epilogue, so the fp16 path neither saturates on large nor
+//   loses bits on tiny features (fp32-SGEMM-like range).
+//   (c) operands live in two separate buffers (source / target) with a small header; the TARGET buffer (the pooled
+//   fmap2 levels) can be shared by all B pairs of a call (`B2 == 1`): in the key-frame scheme fmap2 is the key frame.
+//   (d) per-level patch shape (32x4, 16x8 or 8x16 target pixels) so the small pooled levels waste fewer MMA rows.
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -56,18 +67,28 @@ struct ResMaps {
   CUtensorMap tgt[kRLevels];   // pooled fmap2 level l, 16-bit, dims (C, w_l, h_l, B)
 };
 
+// Operand buffers start with a header: float[0..kAmaxBlocks) partial abs-maxima (corr_absmax_kernel), float[256] = 1/scale,
+// float[257] = scale (corr_prep16_kernel); the 16-bit data follow at kOpHdrBytes.
+constexpr int kOpHdrBytes = 2048;
+constexpr int kAmaxBlocks = 128;
+constexpr int kHdrInvScale = 256, kHdrScale = 257;
+
 struct ResArgs {
   int B, n1, m_tiles, levels, kslabs, slab_elems;
   int tile_begin_level[kRLevels + 1];  // prefix sums of patches per level inside one source block
   int tx_tiles[kRLevels];
   int lh[kRLevels], lw[kRLevels], wp[kRLevels];
+  int pxs[kRLevels];                   // log2 of the level's patch width (patch = 2^pxs x 128/2^pxs target pixels)
   long long pitch[kRLevels];
-  float* out[kRLevels];
+  void* out[kRLevels];                 // float* or __half* (OUT_HALF)
+  const float* src_hdr;                // operand headers: the epilogue undoes the operand scales
+  const float* tgt_hdr;
   int total_tiles;
-  float divisor;
+  float divisor;                       // sqrt(C)
+  float rsqrt_c;                       // 1/sqrt(C) when that is a power of two (use_div == 0)
   int use_div;
   int fmt;  // 0 = fp16, 1 = bf16
-  int patch_x, patch_y;  // patch_x * patch_y = 128
+  int tgt_shared;                      // the target operand has batch 1 and serves every pair of the call
   int debug;             // SDOF_RES_DEBUG: 1 skip stores, 4 skip MMA, 8 skip A loads, 16 skip TMEM loads (experiments only)
 };
 
@@ -108,6 +129,7 @@ __device__ __forceinline__ TileInfo unpack_tile(const ResArgs& a, PackedTile pt)
   return ti;
 }
 
+template <bool OUT_HALF>
 __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(const __grid_constant__ ResMaps maps,
                                                                              const __grid_constant__ ResArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -184,7 +206,7 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
           } else {
             mbar_expect_tx(bar_afull + 8 * stage, kRAStage);
             tma_load_4d(smem_a + stage * kRAStage, &maps.tgt[ti.level], bar_afull + 8 * stage, k * args.slab_elems,
-                        ti.tx * args.patch_x, ti.ty * args.patch_y, ti.b);
+                        ti.tx << args.pxs[ti.level], ti.ty << (7 - args.pxs[ti.level]), args.tgt_shared ? 0 : ti.b);
           }
           if (++stage == kRAStages) {
             stage = 0;
@@ -242,45 +264,25 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
     constexpr int kColsPerWarp = kRN / 4;
     const bool use_div = args.use_div != 0;
     const float divisor = args.divisor;
-    const int patch_x = args.patch_x, patch_y = args.patch_y;
+    // undo the operand scales (exact powers of two) and, when exact, fold in 1/sqrt(C)
+    const float mul = __ldg(args.src_hdr + kHdrInvScale) * __ldg(args.tgt_hdr + kHdrInvScale) * (use_div ? 1.0f : args.rsqrt_c);
     const int mrow = 32 * q + lane;  // TMEM lane = row of the A tile = patch pixel (x fastest)
-    const int py = mrow / patch_x, px = mrow - py * patch_x;
+    const bool odd = (lane & 1) != 0;
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const TileInfo ti = unpack_tile(args, table[t - t_begin]);
       const int l = ti.level;
+      const int pxs = args.pxs[l];
+      const int py = mrow >> pxs, px = mrow & ((1 << pxs) - 1);
       const int m0 = ti.mt * kRN + cq * kColsPerWarp;
       const int mcount = min(kColsPerWarp, args.n1 - m0);  // may be <= 0 for a partial block
       const long long pitch = args.pitch[l];
-      const int y = ti.ty * patch_y + py, x = ti.tx * patch_x + px;
-      const bool in = !(args.debug & 1) && y < args.lh[l] && x < args.lw[l];
-      float* p = args.out[l] + ((long long)ti.b * args.n1 + m0) * pitch + (long long)y * args.wp[l] + x;
-      const bool all_in = __all_sync(0xffffffffu, in);
+      const int y = (ti.ty << (7 - pxs)) + py, x = (ti.tx << pxs) + px;
       const uint32_t ab = it & 1;
 
       mbar_wait(bar_tfull + 8 * ab, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * kRN + cq * kColsPerWarp;
-      auto store_chunk = [&](const uint32_t (&u)[32], int chunk) {
-        const int ncols = mcount - chunk * 32;
-        if (ncols >= 32 && all_in && !use_div) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            *p = __uint_as_float(u[jj]);
-            p += pitch;
-          }
-        } else if (ncols > 0) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            if (jj < ncols) {  // warp-uniform
-              float v = __uint_as_float(u[jj]);
-              if (use_div) v = __fdiv_rn(v, divisor);
-              if (in) *p = v;
-              p += pitch;
-            }
-          }
-        }
-      };
       uint32_t ua[32], ub[32];
       if (!(args.debug & 16)) {
         tmem_ld32(taddr, ua);
@@ -294,8 +296,65 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
-      store_chunk(ua, 0);
-      store_chunk(ub, 1);
+
+      if constexpr (OUT_HALF) {
+        // Lanes (2i, 2i+1) hold x and x+1 of every column (source pixel).  Per column pair (j, j+1) they swap one
+        // register: the even lane ends up with (x, x+1) of column j, the odd lane with (x-1, x) of column j+1, and each
+        // stores ONE packed half2 into its column's map -- 16 lanes x 4 B = a 64-byte run per map and instruction.
+        const int xe = x & ~1;
+        const bool in = !(args.debug & 1) && y < args.lh[l] && xe < args.lw[l];
+        const bool all_in = __all_sync(0xffffffffu, in);
+        __half2* p = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(args.out[l]) +
+                                                ((long long)ti.b * args.n1 + m0 + (odd ? 1 : 0)) * pitch + (long long)y * args.wp[l] + xe);
+        const long long pstep = pitch;  // two columns further, in half2 units
+        auto store_chunk = [&](const uint32_t (&u)[32], int chunk) {
+          const int ncols = mcount - chunk * 32;
+          if (ncols <= 0) return;  // warp-uniform
+          const bool fast = ncols >= 32 && all_in && !use_div;
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 2) {
+            if (!fast && jj >= ncols) break;  // warp-uniform
+            float a = __uint_as_float(u[jj]) * mul, b = __uint_as_float(u[jj + 1]) * mul;
+            if (use_div) {
+              a = __fdiv_rn(a, divisor);
+              b = __fdiv_rn(b, divisor);
+            }
+            const float recv = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
+            const float lo = odd ? recv : a, hi = odd ? b : recv;
+            const __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+            if (fast || (in && jj + (odd ? 1 : 0) < ncols)) *p = v;
+            p += pstep;
+          }
+        };
+        store_chunk(ua, 0);
+        store_chunk(ub, 1);
+      } else {
+        const bool in = !(args.debug & 1) && y < args.lh[l] && x < args.lw[l];
+        const bool all_in = __all_sync(0xffffffffu, in);
+        float* p = reinterpret_cast<float*>(args.out[l]) + ((long long)ti.b * args.n1 + m0) * pitch + (long long)y * args.wp[l] + x;
+        auto store_chunk = [&](const uint32_t (&u)[32], int chunk) {
+          const int ncols = mcount - chunk * 32;
+          if (ncols >= 32 && all_in && !use_div) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              *p = __uint_as_float(u[jj]) * mul;
+              p += pitch;
+            }
+          } else if (ncols > 0) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              if (jj < ncols) {  // warp-uniform
+                float v = __uint_as_float(u[jj]) * mul;
+                if (use_div) v = __fdiv_rn(v, divisor);
+                if (in) *p = v;
+                p += pitch;
+              }
+            }
+          }
+        };
+        store_chunk(ua, 0);
+        store_chunk(ub, 1);
+      }
     }
   }
 
