@@ -94,6 +94,29 @@ int sdof_corr_prepare_operands(const float* fmap1, const float* fmap2, int B, in
 int sdof_corr_pyramid_from_operands(int B, int h1, int w1, int h2, int w2, int C, int levels, int precision,
                                     float* pyramid, void* workspace, int64_t workspace_bytes, sdof_stream_t stream);
 
+/* Round 2: the same path with (a) the pyramid optionally STORED IN FP16 (elem_bytes = 2: half the bytes of the store-bound
+ * volume kernel and of every lookup; the 768x512 pyramid, 100 MB, then stays resident in the 126 MB L2 across the 20 lookups
+ * of a pair; an 11-bit significand is what the TF32 convolution consuming the lookup keeps of it anyway), (b) the two
+ * operands in SEPARATE buffers, so that one target (key-frame) operand serves every pair of a call (B2 = 1) and is built
+ * once per key frame (ofgen_keyframe_inpaint.py:602-625 warps every frame against the same references), and (c) AUTO-RANGED
+ * 16-bit operands: a per-tensor power-of-two scale from an abs-max pass, undone exactly in the epilogue, so FP16 neither
+ * saturates on large nor loses bits on tiny feature magnitudes (the reference's SGEMM has fp32 range, RAFT/core/corr.py:58).
+ *   sdof_corr_pyramid_layout_ex : layout for elem_bytes 4 (== sdof_corr_pyramid_layout) or 2 (row pitch rounded up to
+ *                                 8 halves, offsets / pitches / total_floats counted in ELEMENTS)
+ *   sdof_corr_prepare_src / _tgt : fmap1 [B,h1*w1,C] -> src_ops; fmap2 [B2,h2,w2,C] + its avg-pooled levels -> tgt_ops
+ *                                 (buffers of sdof_corr_{src,tgt}_operand_bytes bytes, 256-byte aligned)
+ *   sdof_corr_pyramid_from_parts: the tcgen05 kernel; B2 == B or 1; pyramid 128-byte aligned.
+ * FP16 / BF16 only, C % 8 == 0, C <= 256 (SDOF_ERR_UNSUPPORTED otherwise).                                        */
+int sdof_corr_pyramid_layout_ex(int64_t rows, int h2, int w2, int levels, int elem_bytes, sdof_pyramid_layout* out /* host */);
+int64_t sdof_corr_src_operand_bytes(int B, int h1, int w1, int C);
+int64_t sdof_corr_tgt_operand_bytes(int B2, int h2, int w2, int C, int levels);
+int sdof_corr_prepare_src(const float* fmap1, int B, int h1, int w1, int C, int precision, void* src_ops, int64_t src_bytes,
+                          sdof_stream_t stream);
+int sdof_corr_prepare_tgt(const float* fmap2, int B2, int h2, int w2, int C, int levels, int precision, void* tgt_ops,
+                          int64_t tgt_bytes, sdof_stream_t stream);
+int sdof_corr_pyramid_from_parts(const void* src_ops, const void* tgt_ops, int B, int h1, int w1, int B2, int h2, int w2, int C,
+                                 int levels, int precision, int elem_bytes, void* pyramid, sdof_stream_t stream);
+
 /* ------------------------------------------------------------------------ C3
  * Windowed bilinear lookup in all pyramid levels for one GRU iteration.
  * coords [B,2,h1,w1] (x then y, level-0 pixels of the target map) ->
@@ -109,6 +132,11 @@ int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, i
  * it without a layout change.                                                                                  */
 int sdof_corr_lookup_nhwc(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
                           int radius, float* out, sdof_stream_t stream);
+
+/* Either lookup on a pyramid of elem_bytes 4 (fp32) or 2 (fp16, sdof_corr_pyramid_layout_ex); channels_last selects the
+ * tensor layouts of sdof_corr_lookup_nhwc.  Output is always fp32. */
+int sdof_corr_lookup_ex(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
+                        int radius, float* out, int channels_last, sdof_stream_t stream);
 
 /* ------------------------------------------------------------------------ K1
  * On-the-fly windowed correlation, no volume.  Same contract as the pybind op

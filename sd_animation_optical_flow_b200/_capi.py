@@ -45,6 +45,13 @@ SIGNATURES = {
     'sdof_corr_volume_pyramid': (c_int, [_P, _P] + [c_int] * 8 + [_P, _P, c_int64, _P]),
     'sdof_corr_prepare_operands': (c_int, [_P, _P] + [c_int] * 9 + [_P, c_int64, _P]),
     'sdof_corr_pyramid_from_operands': (c_int, [c_int] * 8 + [_P, _P, c_int64, _P]),
+    'sdof_corr_pyramid_layout_ex': (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(PyramidLayout)]),
+    'sdof_corr_src_operand_bytes': (c_int64, [c_int] * 4),
+    'sdof_corr_tgt_operand_bytes': (c_int64, [c_int] * 5),
+    'sdof_corr_prepare_src': (c_int, [_P] + [c_int] * 5 + [_P, c_int64, _P]),
+    'sdof_corr_prepare_tgt': (c_int, [_P] + [c_int] * 6 + [_P, c_int64, _P]),
+    'sdof_corr_pyramid_from_parts': (c_int, [_P, _P] + [c_int] * 10 + [_P, _P]),
+    'sdof_corr_lookup_ex': (c_int, [_P, c_int, _P] + [c_int] * 7 + [_P, c_int, _P]),
     'sdof_corr_lookup': (c_int, [_P, _P] + [c_int] * 7 + [_P, _P]),
     'sdof_corr_lookup_nhwc': (c_int, [_P, _P] + [c_int] * 7 + [_P, _P]),
     'sdof_relu_scatter': (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, _P]),
@@ -167,9 +174,10 @@ def require_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
     return t
 
 
-def pyramid_layout(rows: int, h2: int, w2: int, levels: int) -> PyramidLayout:
+def pyramid_layout(rows: int, h2: int, w2: int, levels: int, elem_bytes: int = 4) -> PyramidLayout:
+    """Layout of a pyramid of fp32 (elem_bytes 4) or fp16 (2) elements; offsets / pitches / total_floats count ELEMENTS."""
     lay = PyramidLayout()
-    check(load().sdof_corr_pyramid_layout(rows, h2, w2, levels, ctypes.byref(lay)), 'sdof_corr_pyramid_layout')
+    check(load().sdof_corr_pyramid_layout_ex(rows, h2, w2, levels, elem_bytes, ctypes.byref(lay)), 'sdof_corr_pyramid_layout_ex')
     return lay
 
 

@@ -27,6 +27,13 @@ int launch_corr_prepare_resident(const float* fmap1, const float* fmap2, int B, 
 int launch_corr_pyramid_prepared(int B, int n1, int h2, int w2, int C, int fmt, float* pyramid, const sdof_pyramid_layout& lay,
                                  void* workspace, int64_t workspace_bytes, cudaStream_t st);
 int64_t corr_res_workspace_bytes(int B, int n1, int h2, int w2, int C, int levels);
+// round 2: split operand buffers (source / target, each with a scale header), shared key-frame target, fp16 pyramid
+int64_t corr_res_src_bytes(int B, int n1, int C);
+int64_t corr_res_tgt_bytes(int B2, int h2, int w2, int C, int levels);
+int launch_corr_prepare_parts(const float* fmap1, int B, int n1, void* src_ops, const float* fmap2, int B2, int h2, int w2,
+                              void* tgt_ops, int C, int levels, int fmt, cudaStream_t st);
+int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, int n1, int B2, int h2, int w2, int C, int fmt,
+                              int out_half, void* pyramid, const sdof_pyramid_layout& lay, cudaStream_t st);
 bool corr_res_supported(int C, int levels);
 
 }  // namespace sdof

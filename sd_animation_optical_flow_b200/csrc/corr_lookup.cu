@@ -10,6 +10,8 @@
 // and parks them in a [channels][32] shared tile so the [B, channels, h1, w1] result is
 // written as full 128-byte lines.  Algorithmic bytes per source pixel and iteration:
 // L*(2r+2)^2*4 read + L*(2r+1)^2*4 written = 2896 B for L=4, r=4.
+#include <cuda_fp16.h>
+
 #include "corr.cuh"
 
 namespace sdof {
@@ -20,7 +22,7 @@ constexpr int kStagePitch = kLookupPx + 1;      // +1: conflict-free column writ
 
 struct LookupLevels {
   int levels;
-  const float* base[SDOF_MAX_LEVELS];
+  const void* base[SDOF_MAX_LEVELS];   // float or __half maps (template parameter of the kernel)
   long long pitch[SDOF_MAX_LEVELS];
   int h[SDOF_MAX_LEVELS], w[SDOF_MAX_LEVELS], wp[SDOF_MAX_LEVELS];
 };
@@ -39,8 +41,8 @@ __device__ __forceinline__ int safe_floor(float v, float* frac) {
 // blend the (D+1)x(D+1) window `win` (row-major, [wy][wx]) into D*D outputs, x-major
 // channel order k = D*ix + iy (RAFT/core/corr.py:37-43), and park them in the stage tile.
 __device__ __forceinline__ void blend_window(const float* __restrict__ win, int D, float fx, float fy, float scale,
-                                             float* __restrict__ stage_col, int lane) {
-  const int T1 = D + 1;
+                                             float* __restrict__ stage_col, int lane, int T1 = 0) {
+  if (T1 == 0) T1 = D + 1;   // window row stride
   const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
   for (int k = lane; k < D * D; k += 32) {
     const int ix = k / D, iy = k - ix * D;
@@ -51,8 +53,8 @@ __device__ __forceinline__ void blend_window(const float* __restrict__ win, int 
 }
 
 __device__ __forceinline__ void blend_window_strided(const float* __restrict__ win, int D, float fx, float fy,
-                                                     float* __restrict__ dst, int stride, int lane) {
-  const int T1 = D + 1;
+                                                     float* __restrict__ dst, int stride, int lane, int T1 = 0) {
+  if (T1 == 0) T1 = D + 1;   // window row stride
   const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
   for (int k = lane; k < D * D; k += 32) {
     const int ix = k / D, iy = k - ix * D;
@@ -75,13 +77,18 @@ __device__ __forceinline__ void flush_stage(const float* __restrict__ stage, int
 // 1024-thread CTAs that fill the 148 SMs 1.3 times.
 constexpr int kLookupPxNhwc = 8;
 
-template <int R_T, int L_T, int PX>
+// ET = float: the fp32 pyramid (window taps gathered one by one).  ET = __half: the fp16 pyramid -- a window row is gathered
+// as 2r/2+2 aligned 32-bit words (two taps each), half the load instructions and half the sectors of the fp32 form.
+template <int R_T, int L_T, int PX, typename ET>
 __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
                                                               int N1, int r_rt, float* __restrict__ out, int nhwc) {
   extern __shared__ __align__(16) float smem[];
+  constexpr bool kHalf = sizeof(ET) == 2;
   const int r = R_T ? R_T : r_rt;
   const int L = L_T ? L_T : lv.levels;
-  const int D = 2 * r + 1, T1 = D + 1, T = T1 * T1, DD = D * D;
+  const int D = 2 * r + 1, T1 = D + 1, DD = D * D;
+  const int WS = kHalf ? T1 + 2 : T1;       // window row stride in shared memory (the word gather may start one tap early)
+  const int T = WS * T1;                    // floats per level window
   float* stage = smem;                                                    // [L*DD][kStagePitch]   (planar only)
   float* win_all = smem + (PX == kLookupPx ? L * DD * kStagePitch : 0);   // [PX warps][L][T]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,25 +103,49 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
     const float cy = nhwc ? coords[((int64_t)b * N1 + p) * 2 + 1] : coords[((int64_t)b * 2 + 1) * N1 + p];
     const int64_t row = (int64_t)b * N1 + p;
     float fxs[L_T ? L_T : SDOF_MAX_LEVELS], fys[L_T ? L_T : SDOF_MAX_LEVELS];
+    int xos[L_T ? L_T : SDOF_MAX_LEVELS];
     // gather: with compile-time (r, L) every level's loads are issued before any is consumed
-    constexpr int kTrips = R_T ? ((2 * R_T + 2) * (2 * R_T + 2) + 31) / 32 : (18 * 18 + 31) / 32;
+    constexpr int kItems = kHalf ? (R_T ? (2 * R_T + 2) * (R_T + 2) : 18 * 10) : (R_T ? (2 * R_T + 2) * (2 * R_T + 2) : 18 * 18);
+    constexpr int kTrips = (kItems + 31) / 32;
 #pragma unroll
     for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
       if (l >= L) break;
       const float s = 1.0f / (float)(1 << l);  // coords / 2**l is exact
       const int x0 = safe_floor(cx * s, &fxs[l]) - r;
       const int y0 = safe_floor(cy * s, &fys[l]) - r;
-      const float* map = lv.base[l] + row * lv.pitch[l];
       const int h = lv.h[l], w = lv.w[l], wp = lv.wp[l];
+      if constexpr (kHalf) {
+        const __half* map = reinterpret_cast<const __half*>(lv.base[l]) + row * lv.pitch[l];
+        const int xa = x0 & ~1;               // floor to even (also for negative x0): words are 4-byte aligned (wp % 8 == 0)
+        xos[l] = x0 - xa;
+        const int WR = (T1 >> 1) + 1;         // words per window row
 #pragma unroll
-      for (int j = 0; j < kTrips; ++j) {
-        const int t = lane + 32 * j;
-        if (t < T) {
-          const int wy = t / T1, wx = t - wy * T1;
-          const int gy = y0 + wy, gx = x0 + wx;
-          float v = 0.f;
-          if ((unsigned)gy < (unsigned)h && (unsigned)gx < (unsigned)w) v = __ldg(map + (int64_t)gy * wp + gx);
-          win[l * T + t] = v;
+        for (int j = 0; j < kTrips; ++j) {
+          const int t = lane + 32 * j;
+          if (t < WR * T1) {
+            const int wy = t / WR, wx = t - wy * WR;
+            const int gy = y0 + wy, gx = xa + 2 * wx;
+            float2 v = make_float2(0.f, 0.f);
+            if ((unsigned)gy < (unsigned)h && (unsigned)gx < (unsigned)w) {
+              v = __half22float2(__ldg(reinterpret_cast<const __half2*>(map + (int64_t)gy * wp + gx)));
+              if (gx + 1 >= w) v.y = 0.f;     // odd width: the pair's second tap is the padding column
+            }
+            *reinterpret_cast<float2*>(win + l * T + wy * WS + 2 * wx) = v;
+          }
+        }
+      } else {
+        const float* map = reinterpret_cast<const float*>(lv.base[l]) + row * lv.pitch[l];
+        xos[l] = 0;
+#pragma unroll
+        for (int j = 0; j < kTrips; ++j) {
+          const int t = lane + 32 * j;
+          if (t < T) {
+            const int wy = t / T1, wx = t - wy * T1;
+            const int gy = y0 + wy, gx = x0 + wx;
+            float v = 0.f;
+            if ((unsigned)gy < (unsigned)h && (unsigned)gx < (unsigned)w) v = __ldg(map + (int64_t)gy * wp + gx);
+            win[l * T + t] = v;
+          }
         }
       }
     }
@@ -123,9 +154,9 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
     for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
       if (l >= L) break;
       if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
-        blend_window_strided(win + l * T, D, fxs[l], fys[l], out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane);
+        blend_window_strided(win + l * T + xos[l], D, fxs[l], fys[l], out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane, WS);
       else
-        blend_window(win + l * T, D, fxs[l], fys[l], 1.0f, stage + l * DD * kStagePitch + warp, lane);
+        blend_window(win + l * T + xos[l], D, fxs[l], fys[l], 1.0f, stage + l * DD * kStagePitch + warp, lane, WS);
     }
   }
   if (nhwc) return;
@@ -252,45 +283,52 @@ static int launch_alt_corr(const char* name, const AltCorrArgs& a, int B, cudaSt
 
 extern "C" {
 
-static int corr_lookup_impl(const char* name, const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2,
-                            int levels, int radius, float* out, int nhwc, sdof_stream_t stream) {
+static int corr_lookup_impl(const char* name, const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1,
+                            int h2, int w2, int levels, int radius, float* out, int nhwc, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(pyramid && coords && out, "%s: NULL pointer", name);
   SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "%s: bad sizes", name);
   SDOF_REQUIRE(radius >= 0 && radius <= 8, "%s: radius must be in [0,8], got %d", name, radius);
   SDOF_REQUIRE(B <= 65535, "%s: B > 65535 not supported", name);
+  SDOF_REQUIRE(elem_bytes == 4 || elem_bytes == 2, "%s: elem_bytes must be 4 (fp32 pyramid) or 2 (fp16 pyramid)", name);
+  SDOF_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 3) == 0, "%s: pyramid must be 4-byte aligned", name);
   sdof_pyramid_layout lay;
   const int N1 = h1 * w1;
-  int rc = sdof_corr_pyramid_layout((int64_t)B * N1, h2, w2, levels, &lay);
+  int rc = sdof_corr_pyramid_layout_ex((int64_t)B * N1, h2, w2, levels, elem_bytes, &lay);
   if (rc) return rc;
   if (B == 0) return SDOF_OK;
   LookupLevels lv;
   lv.levels = levels;
   for (int l = 0; l < SDOF_MAX_LEVELS; ++l) {
     const int ll = l < levels ? l : 0;
-    lv.base[l] = pyramid + lay.offset[ll];
+    lv.base[l] = reinterpret_cast<const uint8_t*>(pyramid) + lay.offset[ll] * elem_bytes;
     lv.pitch[l] = lay.pitch[ll];
     lv.h[l] = lay.h[ll];
     lv.w[l] = lay.w[ll];
     lv.wp[l] = lay.wp[ll];
   }
-  const int D = 2 * radius + 1, T = (D + 1) * (D + 1), DD = D * D;
+  const int D = 2 * radius + 1, T1 = D + 1, DD = D * D;
+  const int T = (elem_bytes == 2 ? T1 + 2 : T1) * T1;
   const int px = nhwc ? kLookupPxNhwc : kLookupPx;
   const size_t smem = ((nhwc ? 0 : (size_t)levels * DD * kStagePitch) + (size_t)px * levels * T) * sizeof(float);
   SDOF_REQUIRE(smem <= 200 * 1024, "%s: levels=%d radius=%d need %zu bytes of shared memory", name, levels, radius, smem);
   dim3 grid(ceil_div(N1, px), B);
   cudaStream_t st = as_stream(stream);
-#define SDOF_LOOKUP_LAUNCH(RT, LT, PX)                                                                                       \
-  do {                                                                                                                       \
-    SDOF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT, LT, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    corr_lookup_kernel<RT, LT, PX><<<grid, PX * 32, smem, st>>>(lv, coords, N1, radius, out, nhwc);                          \
+#define SDOF_LOOKUP_LAUNCH(RT, LT, PX, TT)                                                                                       \
+  do {                                                                                                                           \
+    SDOF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT, LT, PX, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    corr_lookup_kernel<RT, LT, PX, TT><<<grid, PX * 32, smem, st>>>(lv, coords, N1, radius, out, nhwc);                          \
   } while (0)
-#define SDOF_LOOKUP_DISPATCH(RT, LT)             \
-  do {                                           \
-    if (nhwc)                                    \
-      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPxNhwc); \
-    else                                         \
-      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPx);     \
+#define SDOF_LOOKUP_DISPATCH(RT, LT)                          \
+  do {                                                        \
+    if (nhwc && elem_bytes == 2)                              \
+      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPxNhwc, __half);      \
+    else if (nhwc)                                            \
+      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPxNhwc, float);       \
+    else if (elem_bytes == 2)                                 \
+      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPx, __half);          \
+    else                                                      \
+      SDOF_LOOKUP_LAUNCH(RT, LT, kLookupPx, float);           \
   } while (0)
   if (radius == 4 && levels == 4)
     SDOF_LOOKUP_DISPATCH(4, 4);
@@ -306,12 +344,18 @@ static int corr_lookup_impl(const char* name, const float* pyramid, const float*
 
 int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
                      int radius, float* out, sdof_stream_t stream) {
-  return corr_lookup_impl("sdof_corr_lookup", pyramid, coords, B, h1, w1, h2, w2, levels, radius, out, 0, stream);
+  return corr_lookup_impl("sdof_corr_lookup", pyramid, 4, coords, B, h1, w1, h2, w2, levels, radius, out, 0, stream);
 }
 
 int sdof_corr_lookup_nhwc(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
                           int radius, float* out, sdof_stream_t stream) {
-  return corr_lookup_impl("sdof_corr_lookup_nhwc", pyramid, coords, B, h1, w1, h2, w2, levels, radius, out, 1, stream);
+  return corr_lookup_impl("sdof_corr_lookup_nhwc", pyramid, 4, coords, B, h1, w1, h2, w2, levels, radius, out, 1, stream);
+}
+
+int sdof_corr_lookup_ex(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
+                        int radius, float* out, int channels_last, sdof_stream_t stream) {
+  return corr_lookup_impl("sdof_corr_lookup_ex", pyramid, elem_bytes, coords, B, h1, w1, h2, w2, levels, radius, out,
+                          channels_last ? 1 : 0, stream);
 }
 
 static int check_alt(const char* name, const float* fmap1, const float* fmap2, const float* coords, float* out, int B,

@@ -376,6 +376,8 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
 struct PrepArgs {
   const float* fmap1;
   const float* fmap2;
+  float* src_hdr;                       // header of the source operand buffer (partials in, scale out); NULL = part not requested
+  float* tgt_hdr;
   void* src16;
   void* tgt16[kRLevels];
   long long src_items;                  // float4 units of fmap1
@@ -385,9 +387,57 @@ struct PrepArgs {
   int nb_src, nb_cells, nb_l2;
   int B, n1, h2, w2, C4, levels;
   int lh[kRLevels], lw[kRLevels];
-  float scale;
   int fmt;
 };
+
+// Per-tensor abs-max, pass 1: kAmaxBlocks partial maxima per tensor into the operand header (no atomics, no reset needed;
+// NaNs are ignored by fmaxf, an infinity switches the scaling off).  blockIdx.y selects the tensor.
+__global__ void __launch_bounds__(256) corr_absmax_kernel(const float4* __restrict__ a, long long na4, float* __restrict__ pa,
+                                                          const float4* __restrict__ b, long long nb4, float* __restrict__ pb) {
+  const float4* x = blockIdx.y == 0 ? a : b;
+  const long long n4 = blockIdx.y == 0 ? na4 : nb4;
+  float* part = blockIdx.y == 0 ? pa : pb;
+  if (x == nullptr || part == nullptr) return;
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {   // four independent loads in flight
+    const float4 v0 = __ldg(x + i), v1 = __ldg(x + i + stride), v2 = __ldg(x + i + 2 * stride), v3 = __ldg(x + i + 3 * stride);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w))));
+  }
+  for (; i < n4; i += stride) {
+    const float4 v = __ldg(x + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    part[blockIdx.x] = m;
+  }
+}
+
+// Pass 2 (inside the conversion kernel): the power-of-two scale that puts the tensor's abs-max at [2^13, 2^14) -- two
+// binades below the fp16 maximum, so 2x2 pooling and rounding cannot overflow.  1 for an all-zero / non-finite tensor.
+__device__ __forceinline__ float scale_from_partials(const float* __restrict__ part, int lane) {
+  float m = 0.f;
+  for (int i = lane; i < kAmaxBlocks; i += 32) m = fmaxf(m, part[i]);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(m, &e);                      // m = f * 2^e, f in [0.5, 1)
+  e = 14 - e;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return ldexpf(1.0f, e);
+}
 
 __device__ __forceinline__ float4 pool4v(float4 a, float4 b, float4 d, float4 e) {
   float4 r;
@@ -419,6 +469,8 @@ __device__ __forceinline__ unsigned short pack16_scalar(float v, int fmt) {
   return *reinterpret_cast<const unsigned short*>(&h);
 }
 
+__device__ __forceinline__ float4 scaled4(float4 v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
+
 __device__ __forceinline__ uint2 pack16(float4 v, int fmt) {
   uint2 o;
   if (fmt == 0) {
@@ -436,15 +488,43 @@ __device__ __forceinline__ uint2 pack16(float4 v, int fmt) {
   return o;
 }
 
-__global__ void __launch_bounds__(256, 3) corr_prep16_kernel(const __grid_constant__ PrepArgs a) {
+constexpr int kPrepSrcPerThread = 4;   // float4 items per thread in the fmap1 section (independent loads in flight)
+
+__global__ void __launch_bounds__(256, 4) corr_prep16_kernel(const __grid_constant__ PrepArgs a) {
   const int C4 = a.C4;
   int blk = blockIdx.x;
-  if (blk < a.nb_src) {
-    const long long i = (long long)blk * 256 + threadIdx.x;
-    if (i < a.src_items) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(a.fmap1) + i);
-      v.x *= a.scale; v.y *= a.scale; v.z *= a.scale; v.w *= a.scale;  // power of two: exact
-      reinterpret_cast<uint2*>(a.src16)[i] = pack16(v, a.fmt);
+  // every CTA derives its tensor's scale from the abs-max partials (128 floats from L2); the first CTA of a tensor's
+  // section publishes it for the correlation kernel's epilogue
+  __shared__ float s_scale;
+  const bool is_src = blk < a.nb_src;
+  if (threadIdx.x < 32) {
+    float* hdr = is_src ? a.src_hdr : a.tgt_hdr;
+    const float sc = scale_from_partials(hdr, threadIdx.x);
+    if (threadIdx.x == 0) {
+      s_scale = sc;
+      if (blk == 0 || blk == a.nb_src) {
+        hdr[kHdrInvScale] = 1.0f / sc;   // exact: power of two
+        hdr[kHdrScale] = sc;
+      }
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  if (is_src) {
+    const long long i0 = (long long)blk * (256 * kPrepSrcPerThread) + threadIdx.x;
+    float4 v[kPrepSrcPerThread];
+#pragma unroll
+    for (int k = 0; k < kPrepSrcPerThread; ++k) {
+      const long long i = i0 + k * 256;
+      if (i < a.src_items) v[k] = __ldg(reinterpret_cast<const float4*>(a.fmap1) + i);
+    }
+#pragma unroll
+    for (int k = 0; k < kPrepSrcPerThread; ++k) {
+      const long long i = i0 + k * 256;
+      if (i < a.src_items) {
+        v[k].x *= scale; v[k].y *= scale; v[k].z *= scale; v[k].w *= scale;  // power of two: exact
+        reinterpret_cast<uint2*>(a.src16)[i] = pack16(v[k], a.fmt);
+      }
     }
     return;
   }
@@ -475,11 +555,11 @@ __global__ void __launch_bounds__(256, 3) corr_prep16_kernel(const __grid_consta
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         const int y = 2 * cy + dy, x = 2 * cx + dx;
-        if (y < a.h2 && x < a.w2) t0[((long long)y * a.w2 + x) * C4 + c] = pack16(v[dy][dx], a.fmt);
+        if (y < a.h2 && x < a.w2) t0[((long long)y * a.w2 + x) * C4 + c] = pack16(scaled4(v[dy][dx], scale), a.fmt);
       }
     if (a.levels > 1 && cy < a.lh[1] && cx < a.lw[1]) {
       uint2* t1 = reinterpret_cast<uint2*>(a.tgt16[1]) + (long long)b * a.lh[1] * a.lw[1] * C4;
-      t1[((long long)cy * a.lw[1] + cx) * C4 + c] = pack16(pool4v(v[0][0], v[0][1], v[1][0], v[1][1]), a.fmt);
+      t1[((long long)cy * a.lw[1] + cx) * C4 + c] = pack16(scaled4(pool4v(v[0][0], v[0][1], v[1][0], v[1][1]), scale), a.fmt);
     }
     return;
   }
@@ -503,7 +583,7 @@ __global__ void __launch_bounds__(256, 3) corr_prep16_kernel(const __grid_consta
         const float4* q = f + ((long long)(4 * y + 2 * dy) * a.w2 + (4 * x + 2 * dx)) * C4 + c;
         l1[dy][dx] = pool4v(__ldg(q), __ldg(q + C4), __ldg(q + (long long)a.w2 * C4), __ldg(q + (long long)a.w2 * C4 + C4));
       }
-    reinterpret_cast<uint2*>(a.tgt16[2])[i] = pack16(pool4v(l1[0][0], l1[0][1], l1[1][0], l1[1][1]), a.fmt);
+    reinterpret_cast<uint2*>(a.tgt16[2])[i] = pack16(scaled4(pool4v(l1[0][0], l1[0][1], l1[1][0], l1[1][1]), scale), a.fmt);
     return;
   }
   blk -= a.nb_l2;
@@ -534,100 +614,124 @@ __global__ void __launch_bounds__(256, 3) corr_prep16_kernel(const __grid_consta
       }
     }
     const float v = __fadd_rn(__fadd_rn(__fadd_rn(qv[0], qv[1]), qv[2]), qv[3]) * 0.25f;
-    reinterpret_cast<unsigned short*>(a.tgt16[l])[r] = pack16_scalar(v, a.fmt);
+    reinterpret_cast<unsigned short*>(a.tgt16[l])[r] = pack16_scalar(v * scale, a.fmt);
   }
 }
 
 // ----------------------------------------------------------------------------- host
 static int64_t al256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
-int64_t corr_res_workspace_bytes(int B, int n1, int h2, int w2, int C, int levels) {
-  int64_t bytes = al256((int64_t)B * n1 * C * 2);
-  for (int l = 0; l < levels; ++l) bytes += al256((int64_t)B * (h2 >> l) * (w2 >> l) * C * 2);
+int64_t corr_res_src_bytes(int B, int n1, int C) { return kOpHdrBytes + al256((int64_t)B * n1 * C * 2); }
+int64_t corr_res_tgt_bytes(int B2, int h2, int w2, int C, int levels) {
+  int64_t bytes = kOpHdrBytes;
+  for (int l = 0; l < levels; ++l) bytes += al256((int64_t)B2 * (h2 >> l) * (w2 >> l) * C * 2);
   return bytes;
+}
+int64_t corr_res_workspace_bytes(int B, int n1, int h2, int w2, int C, int levels) {
+  return corr_res_src_bytes(B, n1, C) + corr_res_tgt_bytes(B, h2, w2, C, levels);
 }
 
 bool corr_res_supported(int C, int levels) { return C % 8 == 0 && C <= kRMaxSlabs * 32 && levels >= 1 && levels <= 6; }
 
-// Pre-pass: 16-bit operand copies of fmap1 (scaled) and of every pooled level of fmap2 into `workspace`.
-// part: 1 = fmap1 only, 2 = fmap2 levels only, 3 = both (a key frame's fmap2 operands can be reused by every
-// pair that shares it).
-int launch_corr_prepare_resident(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, int fmt,
-                                 const sdof_pyramid_layout& lay, void* workspace, int64_t workspace_bytes, int part,
-                                 cudaStream_t st) {
-  const int levels = lay.levels;
+static int check_ops_ptr(const void* p, const char* what) {
+  if (p == nullptr) return fail(SDOF_ERR_INVALID, "%s operand buffer is NULL", what);
+  if ((reinterpret_cast<uintptr_t>(p) & 255) != 0) return fail(SDOF_ERR_INVALID, "%s operand buffer must be 256-byte aligned", what);
+  return SDOF_OK;
+}
+
+// Pre-pass: abs-max + auto-ranged 16-bit copies.  fmap1 != NULL: fmap1 [B, n1, C] -> src_ops; fmap2 != NULL: every
+// avg-pooled level of fmap2 [B2, h2, w2, C] -> tgt_ops (a key frame's target operands are built once and reused by every
+// pair that shares it).  Two launches (partials, conversion) for whichever parts are requested.
+int launch_corr_prepare_parts(const float* fmap1, int B, int n1, void* src_ops, const float* fmap2, int B2, int h2, int w2,
+                              void* tgt_ops, int C, int levels, int fmt, cudaStream_t st) {
   if (!corr_res_supported(C, levels)) return SDOF_ERR_UNSUPPORTED;
-  if (B > 65535) return SDOF_ERR_UNSUPPORTED;
-  const int64_t need = corr_res_workspace_bytes(B, n1, h2, w2, C, levels);
-  if (workspace == nullptr || workspace_bytes < need)
-    return fail(SDOF_ERR_INVALID, "correlation workspace of %lld bytes required, got %lld", (long long)need,
-                (long long)workspace_bytes);
-  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
-    return fail(SDOF_ERR_INVALID, "correlation workspace must be 256-byte aligned");
-  const bool pow4 = (C & (C - 1)) == 0 && (__builtin_ctz(C) % 2 == 0);
+  if (B > 65535 || B2 > 65535) return SDOF_ERR_UNSUPPORTED;
+  int rc;
+  if (fmap1 && (rc = check_ops_ptr(src_ops, "source"))) return rc;
+  if (fmap2 && (rc = check_ops_ptr(tgt_ops, "target"))) return rc;
+  if (!fmap1 && !fmap2) return SDOF_OK;
   PrepArgs pa;
   memset(&pa, 0, sizeof(pa));
-  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   pa.fmap1 = fmap1;
   pa.fmap2 = fmap2;
-  pa.src16 = w;
-  w += al256((int64_t)B * n1 * C * 2);
-  pa.B = B; pa.n1 = n1; pa.h2 = h2; pa.w2 = w2; pa.C4 = C / 4; pa.levels = levels;
-  pa.scale = pow4 ? 1.0f / sqrtf((float)C) : 1.0f;
+  pa.B = fmap2 ? B2 : B; pa.n1 = n1; pa.h2 = h2; pa.w2 = w2; pa.C4 = C / 4; pa.levels = levels;
   pa.fmt = fmt;
-  pa.src_items = (part & 1) ? (int64_t)B * n1 * (C / 4) : 0;
-  pa.cell_items = (part & 2) ? (int64_t)B * ((h2 + 1) / 2) * ((w2 + 1) / 2) * (C / 4) : 0;
-  pa.l2_items = ((part & 2) && levels > 2) ? (int64_t)B * lay.h[2] * lay.w[2] * (C / 4) : 0;
-  pa.deep_begin[0] = 0;
-  for (int l = 0; l < levels; ++l) {
-    pa.lh[l] = lay.h[l];
-    pa.lw[l] = lay.w[l];
-    pa.tgt16[l] = w;
-    w += al256((int64_t)B * lay.h[l] * lay.w[l] * C * 2);
-    if (l >= 3) pa.deep_begin[l - 2] = pa.deep_begin[l - 3] + ((part & 2) ? (int64_t)B * lay.h[l] * lay.w[l] * C : 0);
+  if (fmap1) {
+    pa.src_hdr = reinterpret_cast<float*>(src_ops);
+    pa.src16 = reinterpret_cast<uint8_t*>(src_ops) + kOpHdrBytes;
+    pa.src_items = (int64_t)B * n1 * (C / 4);
   }
-  const long long deep_items = levels > 3 ? pa.deep_begin[levels - 3] : 0;
-  pa.nb_src = (int)ceil_div64(pa.src_items, 256);
+  pa.deep_begin[0] = 0;
+  if (fmap2) {
+    pa.tgt_hdr = reinterpret_cast<float*>(tgt_ops);
+    uint8_t* w = reinterpret_cast<uint8_t*>(tgt_ops) + kOpHdrBytes;
+    pa.cell_items = (int64_t)B2 * ((h2 + 1) / 2) * ((w2 + 1) / 2) * (C / 4);
+    for (int l = 0; l < levels; ++l) {
+      pa.lh[l] = h2 >> l;
+      pa.lw[l] = w2 >> l;
+      pa.tgt16[l] = w;
+      w += al256((int64_t)B2 * pa.lh[l] * pa.lw[l] * C * 2);
+      if (l >= 3) pa.deep_begin[l - 2] = pa.deep_begin[l - 3] + (int64_t)B2 * pa.lh[l] * pa.lw[l] * C;
+    }
+    pa.l2_items = levels > 2 ? (int64_t)B2 * pa.lh[2] * pa.lw[2] * (C / 4) : 0;
+  }
+  const long long deep_items = (fmap2 && levels > 3) ? pa.deep_begin[levels - 3] : 0;
+  pa.nb_src = (int)ceil_div64(pa.src_items, 256 * kPrepSrcPerThread);
   pa.nb_cells = (int)ceil_div64(pa.cell_items, 256);
   pa.nb_l2 = (int)ceil_div64(pa.l2_items, 256);
   const int nb_deep = (int)ceil_div64(deep_items, 256);
   const int nb = pa.nb_src + pa.nb_cells + pa.nb_l2 + nb_deep;
   if (nb == 0) return SDOF_OK;
+  corr_absmax_kernel<<<dim3(kAmaxBlocks, 2), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), pa.src_items, pa.src_hdr,
+                                                            reinterpret_cast<const float4*>(fmap2),
+                                                            fmap2 ? (int64_t)B2 * h2 * w2 * (C / 4) : 0, pa.tgt_hdr);
+  SDOF_LAUNCH_CHECK("corr_absmax_kernel");
   corr_prep16_kernel<<<nb, 256, 0, st>>>(pa);
   SDOF_LAUNCH_CHECK("corr_prep16_kernel");
   return SDOF_OK;
 }
 
-// Main kernel on operands prepared by launch_corr_prepare_resident.
-int launch_corr_pyramid_prepared(int B, int n1, int h2, int w2, int C, int fmt, float* pyramid, const sdof_pyramid_layout& lay,
-                                 void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+// patch width (log2) for a level: the candidate among 32x4 / 16x8 / 8x16 target pixels with the fewest tiles (ties: wider)
+static int pick_patch_shift(int h, int w) {
+  int best = 5, best_tiles = 1 << 30;
+  for (int s = 5; s >= 3; --s) {
+    const int tiles = ceil_div(w, 1 << s) * ceil_div(h, kRM >> s);
+    if (tiles < best_tiles) {
+      best_tiles = tiles;
+      best = s;
+    }
+  }
+  return best;
+}
+
+// Main kernel on prepared operands.  out_half: pyramid stored as fp16 (layout in half elements) instead of fp32.
+// B2 == B, or B2 == 1: one target (key-frame) operand shared by every pair.
+int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, int n1, int B2, int h2, int w2, int C, int fmt,
+                              int out_half, void* pyramid, const sdof_pyramid_layout& lay, cudaStream_t st) {
   const int levels = lay.levels;
   if (!corr_res_supported(C, levels)) return SDOF_ERR_UNSUPPORTED;
   if (B > 65535) return SDOF_ERR_UNSUPPORTED;
-  const int64_t need = corr_res_workspace_bytes(B, n1, h2, w2, C, levels);
-  if (workspace == nullptr || workspace_bytes < need)
-    return fail(SDOF_ERR_INVALID, "correlation workspace of %lld bytes required, got %lld", (long long)need,
-                (long long)workspace_bytes);
+  if (B2 != B && B2 != 1) return fail(SDOF_ERR_INVALID, "target operand batch must be B (%d) or 1, got %d", B, B2);
+  int rc;
+  if ((rc = check_ops_ptr(src_ops, "source")) || (rc = check_ops_ptr(tgt_ops, "target"))) return rc;
   const bool pow4 = (C & (C - 1)) == 0 && (__builtin_ctz(C) % 2 == 0);
   ResArgs ra;
   memset(&ra, 0, sizeof(ra));
   ResMaps maps;
   memset(&maps, 0, sizeof(maps));
-  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
-  void* src16 = w;
-  w += al256((int64_t)B * n1 * C * 2);
-  void* tgt16[kRLevels] = {};
+  const void* src16 = reinterpret_cast<const uint8_t*>(src_ops) + kOpHdrBytes;
+  const uint8_t* w = reinterpret_cast<const uint8_t*>(tgt_ops) + kOpHdrBytes;
+  const void* tgt16[kRLevels] = {};
   int used_levels = 0;
   for (int l = 0; l < levels; ++l) {
     tgt16[l] = w;
-    w += al256((int64_t)B * lay.h[l] * lay.w[l] * C * 2);
+    w += al256((int64_t)B2 * lay.h[l] * lay.w[l] * C * 2);
     if (lay.h[l] >= 1 && lay.w[l] >= 1) used_levels = l + 1;
   }
   if (used_levels == 0) return SDOF_OK;
 
   const CUtensorMapDataType dt = fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const int slab_elems = kSlabBytes / 2;
-  int rc;
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)n1, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)n1 * C * 2};
@@ -641,43 +745,86 @@ int launch_corr_pyramid_prepared(int B, int n1, int h2, int w2, int C, int fmt, 
   ra.slab_elems = slab_elems;
   ra.kslabs = ceil_div(C, slab_elems);
   ra.divisor = sqrtf((float)C);
+  ra.rsqrt_c = pow4 ? 1.0f / sqrtf((float)C) : 1.0f;
   ra.use_div = !pow4;
   ra.fmt = fmt;
-  ra.patch_x = 32;
+  ra.tgt_shared = (B2 == 1 && B > 1) ? 1 : 0;
+  ra.src_hdr = reinterpret_cast<const float*>(src_ops);
+  ra.tgt_hdr = reinterpret_cast<const float*>(tgt_ops);
   {
-    const char* e = getenv("SDOF_RES_PATCHX");
-    if (e && (atoi(e) == 16 || atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 8)) ra.patch_x = atoi(e);
     const char* d = getenv("SDOF_RES_DEBUG");
     ra.debug = d ? atoi(d) : 0;
   }
-  ra.patch_y = kRM / ra.patch_x;
   ra.tile_begin_level[0] = 0;
   for (int l = 0; l < used_levels; ++l) {
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)lay.w[l], (cuuint64_t)lay.h[l], (cuuint64_t)B};
+    const int pxs = pick_patch_shift(lay.h[l], lay.w[l]);
+    const int patch_x = 1 << pxs, patch_y = kRM >> pxs;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)lay.w[l], (cuuint64_t)lay.h[l], (cuuint64_t)B2};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)lay.w[l] * C * 2, (cuuint64_t)lay.h[l] * lay.w[l] * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)ra.patch_x, (cuuint32_t)ra.patch_y, 1};
+    cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)patch_x, (cuuint32_t)patch_y, 1};
     if ((rc = encode_map(&maps.tgt[l], dt, 4, tgt16[l], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, "pooled fmap2 (16-bit)")))
       return rc;
-    const int tyt = ceil_div(lay.h[l], ra.patch_y), txt = ceil_div(lay.w[l], ra.patch_x);
+    const int tyt = ceil_div(lay.h[l], patch_y), txt = ceil_div(lay.w[l], patch_x);
+    if (tyt > 0x3fff || txt > 0x3fff) return SDOF_ERR_UNSUPPORTED;
+    ra.pxs[l] = pxs;
     ra.tx_tiles[l] = txt;
     ra.tile_begin_level[l + 1] = ra.tile_begin_level[l] + tyt * txt;
     ra.lh[l] = lay.h[l];
     ra.lw[l] = lay.w[l];
     ra.wp[l] = lay.wp[l];
     ra.pitch[l] = lay.pitch[l];
-    ra.out[l] = pyramid + lay.offset[l];
+    ra.out[l] = out_half ? static_cast<void*>(reinterpret_cast<__half*>(pyramid) + lay.offset[l])
+                         : static_cast<void*>(reinterpret_cast<float*>(pyramid) + lay.offset[l]);
   }
   const long long total = (long long)B * ra.m_tiles * ra.tile_begin_level[used_levels];
   if (total > 0x7fffffff) return SDOF_ERR_UNSUPPORTED;
   ra.total_tiles = (int)total;
   const int grid = (int)(total < sm_count() ? total : sm_count());
   if (ceil_div64(total, grid) + 1 > kRMaxTilesPerCta) return SDOF_ERR_UNSUPPORTED;  // tile table would not fit
-  SDOF_CUDA(cudaFuncSetAttribute(corr_pyramid_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemTotal));
-  corr_pyramid_resident_kernel<<<grid, kRThreads, kRSmemTotal, st>>>(maps, ra);
+  if (out_half) {
+    SDOF_CUDA(cudaFuncSetAttribute(corr_pyramid_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemTotal));
+    corr_pyramid_resident_kernel<true><<<grid, kRThreads, kRSmemTotal, st>>>(maps, ra);
+  } else {
+    SDOF_CUDA(cudaFuncSetAttribute(corr_pyramid_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemTotal));
+    corr_pyramid_resident_kernel<false><<<grid, kRThreads, kRSmemTotal, st>>>(maps, ra);
+  }
   SDOF_LAUNCH_CHECK("corr_pyramid_resident_kernel");
   return SDOF_OK;
 }
 
+// ---- the round-1 single-workspace entry points, on top of the split operand buffers (source part first)
+static int split_workspace(void* workspace, int64_t workspace_bytes, int B, int n1, int h2, int w2, int C, int levels,
+                           void** src_ops, void** tgt_ops) {
+  const int64_t need = corr_res_workspace_bytes(B, n1, h2, w2, C, levels);
+  if (workspace == nullptr || workspace_bytes < need)
+    return fail(SDOF_ERR_INVALID, "correlation workspace of %lld bytes required, got %lld", (long long)need,
+                (long long)workspace_bytes);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return fail(SDOF_ERR_INVALID, "correlation workspace must be 256-byte aligned");
+  *src_ops = workspace;
+  *tgt_ops = reinterpret_cast<uint8_t*>(workspace) + corr_res_src_bytes(B, n1, C);
+  return SDOF_OK;
+}
+
+int launch_corr_prepare_resident(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, int fmt,
+                                 const sdof_pyramid_layout& lay, void* workspace, int64_t workspace_bytes, int part,
+                                 cudaStream_t st) {
+  if (!corr_res_supported(C, lay.levels)) return SDOF_ERR_UNSUPPORTED;
+  void *so, *to;
+  int rc = split_workspace(workspace, workspace_bytes, B, n1, h2, w2, C, lay.levels, &so, &to);
+  if (rc) return rc;
+  return launch_corr_prepare_parts((part & 1) ? fmap1 : nullptr, B, n1, so, (part & 2) ? fmap2 : nullptr, B, h2, w2, to, C,
+                                   lay.levels, fmt, st);
+}
+
+int launch_corr_pyramid_prepared(int B, int n1, int h2, int w2, int C, int fmt, float* pyramid, const sdof_pyramid_layout& lay,
+                                 void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (!corr_res_supported(C, lay.levels)) return SDOF_ERR_UNSUPPORTED;
+  void *so, *to;
+  int rc = split_workspace(workspace, workspace_bytes, B, n1, h2, w2, C, lay.levels, &so, &to);
+  if (rc) return rc;
+  return launch_corr_pyramid_parts(so, to, B, n1, B, h2, w2, C, fmt, 0, pyramid, lay, st);
+}
 
 int launch_corr_pyramid_resident(const float* fmap1, const float* fmap2, int B, int n1, int h2, int w2, int C, int fmt,
                                  float* pyramid, const sdof_pyramid_layout& lay, void* workspace, int64_t workspace_bytes,
@@ -688,3 +835,90 @@ int launch_corr_pyramid_resident(const float* fmap1, const float* fmap2, int B, 
 }
 
 }  // namespace sdof
+
+// ----------------------------------------------------------------------------- C ABI (round 2): split operands, fp16 pyramid
+extern "C" {
+
+int sdof_corr_pyramid_layout_ex(int64_t rows, int h2, int w2, int levels, int elem_bytes, sdof_pyramid_layout* out) {
+  using namespace sdof;
+  if (elem_bytes == 4) return sdof_corr_pyramid_layout(rows, h2, w2, levels, out);
+  SDOF_REQUIRE(elem_bytes == 2, "sdof_corr_pyramid_layout_ex: elem_bytes must be 4 (fp32) or 2 (fp16), got %d", elem_bytes);
+  SDOF_REQUIRE(out != nullptr, "sdof_corr_pyramid_layout_ex: out is NULL");
+  SDOF_REQUIRE(levels >= 1 && levels <= SDOF_MAX_LEVELS, "sdof_corr_pyramid_layout_ex: levels must be in [1,%d], got %d",
+               SDOF_MAX_LEVELS, levels);
+  SDOF_REQUIRE(rows >= 0 && h2 >= 1 && w2 >= 1, "sdof_corr_pyramid_layout_ex: bad sizes rows=%lld h2=%d w2=%d", (long long)rows, h2, w2);
+  memset(out, 0, sizeof(*out));
+  out->levels = levels;
+  int64_t off = 0;
+  for (int l = 0; l < levels; ++l) {
+    const int h = h2 >> l, w = w2 >> l;
+    const int wp = (w + 7) & ~7;  // rows start 16-byte aligned; an odd width always has a spare padding column
+    out->h[l] = h;
+    out->w[l] = w;
+    out->wp[l] = wp;
+    out->pitch[l] = (int64_t)h * wp;
+    out->offset[l] = off;
+    off += rows * out->pitch[l];
+    off = (off + 63) & ~(int64_t)63;  // keep every level 128-byte aligned
+  }
+  out->total_floats = off;  // in ELEMENTS (halves here)
+  return SDOF_OK;
+}
+
+int64_t sdof_corr_src_operand_bytes(int B, int h1, int w1, int C) { return sdof::corr_res_src_bytes(B, h1 * w1, C); }
+int64_t sdof_corr_tgt_operand_bytes(int B2, int h2, int w2, int C, int levels) {
+  return sdof::corr_res_tgt_bytes(B2, h2, w2, C, levels);
+}
+
+static int fmt_of(int precision) { return precision == SDOF_PREC_FP16 ? 0 : (precision == SDOF_PREC_BF16 ? 1 : -1); }
+
+int sdof_corr_prepare_src(const float* fmap1, int B, int h1, int w1, int C, int precision, void* src_ops, int64_t src_bytes,
+                          sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(fmap1 && src_ops, "sdof_corr_prepare_src: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && C >= 8 && C % 8 == 0, "sdof_corr_prepare_src: bad sizes");
+  SDOF_REQUIRE((reinterpret_cast<uintptr_t>(fmap1) & 15) == 0, "sdof_corr_prepare_src: fmap1 must be 16-byte aligned");
+  if (fmt_of(precision) < 0) return fail(SDOF_ERR_UNSUPPORTED, "sdof_corr_prepare_src: precision must be FP16 or BF16");
+  SDOF_REQUIRE(src_bytes >= corr_res_src_bytes(B, h1 * w1, C), "sdof_corr_prepare_src: operand buffer of %lld bytes required, got %lld",
+               (long long)corr_res_src_bytes(B, h1 * w1, C), (long long)src_bytes);
+  if (B == 0) return SDOF_OK;
+  int rc = launch_corr_prepare_parts(fmap1, B, h1 * w1, src_ops, nullptr, 0, 1, 1, nullptr, C, 1, fmt_of(precision), as_stream(stream));
+  if (rc == SDOF_ERR_UNSUPPORTED) return fail(rc, "sdof_corr_prepare_src: shape not supported by the resident kernel (C %% 8 == 0, C <= 256)");
+  return rc;
+}
+
+int sdof_corr_prepare_tgt(const float* fmap2, int B2, int h2, int w2, int C, int levels, int precision, void* tgt_ops,
+                          int64_t tgt_bytes, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(fmap2 && tgt_ops, "sdof_corr_prepare_tgt: NULL pointer");
+  SDOF_REQUIRE(B2 >= 0 && h2 >= 1 && w2 >= 1 && C >= 8 && C % 8 == 0, "sdof_corr_prepare_tgt: bad sizes");
+  SDOF_REQUIRE(levels >= 1 && levels <= 6, "sdof_corr_prepare_tgt: levels must be in [1,6], got %d", levels);
+  SDOF_REQUIRE((reinterpret_cast<uintptr_t>(fmap2) & 15) == 0, "sdof_corr_prepare_tgt: fmap2 must be 16-byte aligned");
+  if (fmt_of(precision) < 0) return fail(SDOF_ERR_UNSUPPORTED, "sdof_corr_prepare_tgt: precision must be FP16 or BF16");
+  SDOF_REQUIRE(tgt_bytes >= corr_res_tgt_bytes(B2, h2, w2, C, levels), "sdof_corr_prepare_tgt: operand buffer of %lld bytes required, got %lld",
+               (long long)corr_res_tgt_bytes(B2, h2, w2, C, levels), (long long)tgt_bytes);
+  if (B2 == 0) return SDOF_OK;
+  int rc = launch_corr_prepare_parts(nullptr, 0, 0, nullptr, fmap2, B2, h2, w2, tgt_ops, C, levels, fmt_of(precision), as_stream(stream));
+  if (rc == SDOF_ERR_UNSUPPORTED) return fail(rc, "sdof_corr_prepare_tgt: shape not supported by the resident kernel (C %% 8 == 0, C <= 256)");
+  return rc;
+}
+
+int sdof_corr_pyramid_from_parts(const void* src_ops, const void* tgt_ops, int B, int h1, int w1, int B2, int h2, int w2, int C,
+                                 int levels, int precision, int elem_bytes, void* pyramid, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(src_ops && tgt_ops && pyramid, "sdof_corr_pyramid_from_parts: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1 && C >= 8 && C % 8 == 0, "sdof_corr_pyramid_from_parts: bad sizes");
+  SDOF_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "sdof_corr_pyramid_from_parts: elem_bytes must be 2 or 4");
+  SDOF_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 127) == 0, "sdof_corr_pyramid_from_parts: pyramid must be 128-byte aligned");
+  if (fmt_of(precision) < 0) return fail(SDOF_ERR_UNSUPPORTED, "sdof_corr_pyramid_from_parts: precision must be FP16 or BF16");
+  sdof_pyramid_layout lay;
+  int rc = sdof_corr_pyramid_layout_ex((int64_t)B * h1 * w1, h2, w2, levels, elem_bytes, &lay);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  rc = launch_corr_pyramid_parts(src_ops, tgt_ops, B, h1 * w1, B2, h2, w2, C, fmt_of(precision), elem_bytes == 2, pyramid, lay,
+                                 as_stream(stream));
+  if (rc == SDOF_ERR_UNSUPPORTED) return fail(rc, "sdof_corr_pyramid_from_parts: shape not supported by the resident kernel");
+  return rc;
+}
+
+}  // extern "C"

@@ -187,6 +187,88 @@ class RaftEngine:
         g.replay()
         return out  # overwritten by the next replay: estimate_flow copies (unpad / contiguous) before returning
 
+    # ---------------------------------------------------------------- key-frame scheme
+    @torch.no_grad()
+    def encode_key(self, key_img: torch.Tensor, bgr: bool = False):
+        """Encode ONE key frame (uint8 [H,W,3] or [1,H,W,3], CUDA) for `estimate_flow_keyed`: fnet(key) and the pooled 16-bit
+        correlation operands are computed here, once, instead of once per pair (ofgen_pixel_inpaint.py:335 and
+        ofgen_keyframe_inpaint.py:602-625 run every non-key frame against the same key / reference frames)."""
+        if self.fast is None:
+            raise RuntimeError('key-frame feature reuse needs the fast path (basic model, fast=True)')
+        if key_img.dim() == 3:
+            key_img = key_img[None]
+        if key_img.dim() != 4 or key_img.shape[0] != 1 or key_img.shape[-1] != 3 or key_img.dtype != torch.uint8 or not key_img.is_cuda:
+            raise RuntimeError(f'key frame must be a uint8 CUDA tensor [H,W,3] or [1,H,W,3], got {tuple(key_img.shape)} {key_img.dtype}')
+        with self._scope():
+            H, W = key_img.shape[1:3]
+            pad = InputPadder((H, W))._pad
+            im = ops.normalize_pad_u8(key_img.contiguous(), pad, channels=4, bgr=bgr)
+            kf = self.fast.encode_key(im, normalized=True)
+            kf.shape, kf.bgr = (H, W), bool(bgr)
+            return kf
+
+    @torch.no_grad()
+    def _forward_keyed(self, frames: torch.Tensor, key, pad, bgr: bool) -> torch.Tensor:
+        im1 = ops.normalize_pad_u8(frames, pad, channels=4, bgr=bgr)
+        _, flow_up = self.fast.forward(im1, None, self.iters, normalized=True, key=key)
+        return flow_up
+
+    @torch.no_grad()
+    def estimate_flow_keyed(self, key, frames: torch.Tensor, unpad: bool = True, bgr: bool | None = None) -> torch.Tensor:
+        """Flow of every frame [B,H,W,3] (uint8 CUDA) -> the key frame, on the FRAME's grid: RAFT(image1 = frame, image2 = key),
+        i.e. `frame(x) ~ key(x + flow(x))`, the convention `pdcnet_of.warp_frame(key_ai, flow)` consumes (x + flow) and the
+        one in which the key's features are shared by all pairs.  `key` = encode_key(key_img).  Returns [B,H,W,2] fp32.
+        With CUDA graphs the graph is captured per (shape, key object): replays for the same key reuse its operands."""
+        if self.fast is None:
+            raise RuntimeError('key-frame feature reuse needs the fast path (basic model, fast=True)')
+        if frames.dim() != 4 or frames.shape[-1] != 3 or frames.dtype != torch.uint8 or not frames.is_cuda:
+            raise RuntimeError(f'frames must be a uint8 CUDA tensor [B,H,W,3], got {tuple(frames.shape)} {frames.dtype}')
+        if tuple(frames.shape[1:3]) != tuple(key.shape):
+            raise RuntimeError(f'frames are {tuple(frames.shape[1:3])}, the key frame was {tuple(key.shape)}')
+        bgr = key.bgr if bgr is None else bool(bgr)
+        with self._scope():
+            B, H, W, _ = frames.shape
+            pad = InputPadder((H, W))._pad
+            frames = frames.contiguous()
+            if self.use_cuda_graph:
+                # the key's tensors are baked into the graph as addresses: one graph per shape, re-pointed at a new key by
+                # copying the new key's feature map / operand buffers into the static ones
+                gk = ('keyed', tuple(frames.shape), self.iters, bgr)
+                ent = self._graph_get(gk)
+                if ent is None:
+                    s1 = frames.clone()
+                    skey = type(key)(key.fmap2.clone(), None)
+                    if key.target is not None:
+                        skey.target = ops.CorrTarget.__new__(ops.CorrTarget)
+                        skey.target.__dict__.update(key.target.__dict__)
+                        skey.target.buf = key.target.buf.clone()
+                    side = torch.cuda.Stream(device=self.device)
+                    side.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            self._forward_keyed(s1, skey, pad, bgr)
+                    torch.cuda.current_stream(self.device).wait_stream(side)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        out = self._forward_keyed(s1, skey, pad, bgr)
+                    ent = (g, s1, skey, out, [None])
+                    self._graph_put(gk, ent)
+                g, s1, skey, out, cur = ent
+                if cur[0] is not key:            # a different key than the one the static buffers hold: refresh them
+                    skey.fmap2.copy_(key.fmap2)
+                    if key.target is not None:
+                        skey.target.buf.copy_(key.target.buf)
+                    cur[0] = key
+                s1.copy_(frames)
+                g.replay()
+                flow_up = out
+            else:
+                flow_up = self._forward_keyed(frames, key, pad, bgr)
+            if unpad and any(pad):
+                Hp, Wp = flow_up.shape[1:3]
+                flow_up = flow_up[:, pad[2]:Hp - pad[3], pad[0]:Wp - pad[1]]
+            return flow_up.clone(memory_format=torch.contiguous_format) if self.use_cuda_graph else flow_up.contiguous()
+
     @torch.no_grad()
     def estimate_flow(self, img1: torch.Tensor, img2: torch.Tensor, unpad: bool = True, bgr: bool = False) -> torch.Tensor:
         """img1, img2: RGB (bgr=True: BGR) uint8 (or float 0..255) CUDA tensors [B,H,W,3].  Returns flow of img1 -> img2

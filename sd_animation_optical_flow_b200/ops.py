@@ -19,49 +19,130 @@ f32, u8 = torch.float32, torch.uint8
 
 # --------------------------------------------------------------------------- correlation
 class CorrPyramid:
-    """The correlation volume and its pooled levels in one HBM buffer (see
-    sdof_pyramid_layout in include/sdof_b200.h)."""
+    """The correlation volume and its pooled levels in one HBM buffer (see sdof_pyramid_layout /
+    sdof_corr_pyramid_layout_ex in include/sdof_b200.h): fp32, or fp16 (`buf.dtype == torch.float16`)."""
 
     def __init__(self, buf: torch.Tensor, layout, B: int, h1: int, w1: int, h2: int, w2: int, levels: int):
         self.buf, self.layout = buf, layout
         self.B, self.h1, self.w1, self.h2, self.w2, self.levels = B, h1, w1, h2, w2, levels
 
+    @property
+    def elem_bytes(self) -> int:
+        return self.buf.element_size()
+
     def level(self, l: int) -> torch.Tensor:
         """View of level l shaped like the reference's corr_pyramid[l]:
-        [B*h1*w1, 1, h_l, w_l] (RAFT/core/corr.py:21-27); strided when w_l % 4 != 0."""
+        [B*h1*w1, 1, h_l, w_l] (RAFT/core/corr.py:21-27); strided when the row pitch is padded."""
         lay = self.layout
         rows = self.B * self.h1 * self.w1
         return torch.as_strided(self.buf, (rows, 1, lay.h[l], lay.w[l]), (lay.pitch[l], 0, lay.wp[l], 1), lay.offset[l])
 
 
-def corr_volume_pyramid(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor, levels: int = 4,
-                        precision: str = 'fp16') -> CorrPyramid:
-    """fmap1 [B,h1,w1,C], fmap2 [B,h2,w2,C] fp32 channels-last -> CorrPyramid (C1 + C2)."""
-    require_cuda(fmap1_nhwc, 'fmap1', f32)
-    require_cuda(fmap2_nhwc, 'fmap2', f32)
-    if fmap1_nhwc.dim() != 4 or fmap2_nhwc.dim() != 4:
-        raise RuntimeError('feature maps must be [B,h,w,C]')
-    B, h1, w1, C = fmap1_nhwc.shape
-    B2, h2, w2, C2 = fmap2_nhwc.shape
-    if B != B2 or C != C2:
-        raise RuntimeError(f'fmap1 {tuple(fmap1_nhwc.shape)} and fmap2 {tuple(fmap2_nhwc.shape)} disagree on batch/channels')
-    if precision not in PRECISIONS:
-        raise ValueError(f'precision must be one of {sorted(PRECISIONS)}, got {precision!r}')
-    lib = load()
-    lay = _capi.pyramid_layout(B * h1 * w1, h2, w2, levels)
-    dev = fmap1_nhwc.device
-    buf = torch.empty(max(int(lay.total_floats), 1), dtype=f32, device=dev)
-    ws_bytes = int(lib.sdof_corr_volume_workspace_bytes(B, h1, w1, h2, w2, C, levels, PRECISIONS[precision]))
-    ws = torch.empty(ws_bytes, dtype=u8, device=dev) if ws_bytes else None
-    check(lib.sdof_corr_volume_pyramid(ptr(fmap1_nhwc), ptr(fmap2_nhwc), B, h1, w1, h2, w2, C, levels,
-                                       PRECISIONS[precision], ptr(buf), ptr(ws), ws_bytes, stream_ptr(dev)),
-          'sdof_corr_volume_pyramid')
+STORAGE = {'fp32': (f32, 4), 'fp16': (torch.float16, 2)}
+
+
+def _new_pyramid(B, h1, w1, h2, w2, levels, storage, device) -> CorrPyramid:
+    dt, eb = STORAGE[storage]
+    lay = _capi.pyramid_layout(B * h1 * w1, h2, w2, levels, eb)
+    buf = torch.empty(max(int(lay.total_floats), 64), dtype=dt, device=device)
     return CorrPyramid(buf, lay, B, h1, w1, h2, w2, levels)
 
 
+class CorrTarget:
+    """Prepared 16-bit TARGET operand of the fp16/bf16 correlation path: fmap2 and its avg-pooled levels, auto-ranged
+    (sdof_corr_prepare_tgt).  In the key-frame scheme fmap2 belongs to the key frame: build it once (batch 1) and hand it to
+    every `corr_volume_pyramid(..., target=...)` / `CorrSource.pyramid` call of the pairs that share the key."""
+
+    def __init__(self, fmap2_nhwc: torch.Tensor, levels: int = 4, precision: str = 'fp16'):
+        require_cuda(fmap2_nhwc, 'fmap2', f32)
+        if precision not in ('fp16', 'bf16'):
+            raise ValueError("prepared operands exist only for precision 'fp16' / 'bf16'")
+        if fmap2_nhwc.dim() != 4:
+            raise RuntimeError('fmap2 must be [B2,h2,w2,C]')
+        self.B2, self.h2, self.w2, self.C = fmap2_nhwc.shape
+        self.levels, self.precision = levels, precision
+        lib = load()
+        n = int(lib.sdof_corr_tgt_operand_bytes(self.B2, self.h2, self.w2, self.C, levels))
+        self.buf = torch.empty(n, dtype=u8, device=fmap2_nhwc.device)
+        check(lib.sdof_corr_prepare_tgt(ptr(fmap2_nhwc), self.B2, self.h2, self.w2, self.C, levels, PRECISIONS[precision],
+                                        ptr(self.buf), n, stream_ptr(self.buf.device)), 'sdof_corr_prepare_tgt')
+
+
+class CorrSource:
+    """Prepared 16-bit SOURCE operand (fmap1, auto-ranged; sdof_corr_prepare_src)."""
+
+    def __init__(self, fmap1_nhwc: torch.Tensor, precision: str = 'fp16'):
+        require_cuda(fmap1_nhwc, 'fmap1', f32)
+        if precision not in ('fp16', 'bf16'):
+            raise ValueError("prepared operands exist only for precision 'fp16' / 'bf16'")
+        if fmap1_nhwc.dim() != 4:
+            raise RuntimeError('fmap1 must be [B,h1,w1,C]')
+        self.B, self.h1, self.w1, self.C = fmap1_nhwc.shape
+        self.precision = precision
+        lib = load()
+        n = int(lib.sdof_corr_src_operand_bytes(self.B, self.h1, self.w1, self.C))
+        self.buf = torch.empty(n, dtype=u8, device=fmap1_nhwc.device)
+        check(lib.sdof_corr_prepare_src(ptr(fmap1_nhwc), self.B, self.h1, self.w1, self.C, PRECISIONS[precision], ptr(self.buf), n,
+                                        stream_ptr(self.buf.device)), 'sdof_corr_prepare_src')
+
+    def pyramid(self, target: CorrTarget, storage: str = 'fp16', out: CorrPyramid | None = None) -> CorrPyramid:
+        """The tcgen05 kernel alone on prepared operands; target.B2 must be B or 1 (shared key frame)."""
+        if target.C != self.C or target.precision != self.precision or target.B2 not in (1, self.B):
+            raise RuntimeError('source and target operands disagree (channels / precision / batch)')
+        if out is None:
+            out = _new_pyramid(self.B, self.h1, self.w1, target.h2, target.w2, target.levels, storage, self.buf.device)
+        check(load().sdof_corr_pyramid_from_parts(ptr(self.buf), ptr(target.buf), self.B, self.h1, self.w1, target.B2, target.h2,
+                                                  target.w2, self.C, target.levels, PRECISIONS[self.precision], out.elem_bytes,
+                                                  ptr(out.buf), stream_ptr(self.buf.device)), 'sdof_corr_pyramid_from_parts')
+        return out
+
+
+def corr_volume_pyramid(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor | None, levels: int = 4,
+                        precision: str = 'fp16', storage: str = 'fp32', target: CorrTarget | None = None) -> CorrPyramid:
+    """fmap1 [B,h1,w1,C], fmap2 [B,h2,w2,C] fp32 channels-last -> CorrPyramid (C1 + C2).
+    storage 'fp16' (fp16 / bf16 precision only) stores the pyramid in half precision; `target` = a prepared CorrTarget
+    (then fmap2 is ignored), which may have batch 1 = one key frame shared by all B pairs."""
+    require_cuda(fmap1_nhwc, 'fmap1', f32)
+    if fmap1_nhwc.dim() != 4:
+        raise RuntimeError('feature maps must be [B,h,w,C]')
+    if precision not in PRECISIONS:
+        raise ValueError(f'precision must be one of {sorted(PRECISIONS)}, got {precision!r}')
+    if storage not in STORAGE:
+        raise ValueError(f"storage must be 'fp32' or 'fp16', got {storage!r}")
+    B, h1, w1, C = fmap1_nhwc.shape
+    if target is not None or storage == 'fp16':
+        if precision not in ('fp16', 'bf16'):
+            raise ValueError("fp16 pyramid storage / prepared targets need precision 'fp16' or 'bf16'")
+        if target is None:
+            require_cuda(fmap2_nhwc, 'fmap2', f32)
+            if fmap2_nhwc.dim() != 4 or fmap2_nhwc.shape[0] not in (1, B) or fmap2_nhwc.shape[3] != C:
+                raise RuntimeError(f'fmap1 {tuple(fmap1_nhwc.shape)} and fmap2 {tuple(fmap2_nhwc.shape)} disagree on batch/channels')
+            if B == 0:
+                return _new_pyramid(B, h1, w1, fmap2_nhwc.shape[1], fmap2_nhwc.shape[2], levels, storage, fmap1_nhwc.device)
+            target = CorrTarget(fmap2_nhwc, levels, precision)
+        if B == 0:
+            return _new_pyramid(B, h1, w1, target.h2, target.w2, target.levels, storage, fmap1_nhwc.device)
+        return CorrSource(fmap1_nhwc, precision).pyramid(target, storage)
+    require_cuda(fmap2_nhwc, 'fmap2', f32)
+    if fmap2_nhwc.dim() != 4:
+        raise RuntimeError('feature maps must be [B,h,w,C]')
+    B2, h2, w2, C2 = fmap2_nhwc.shape
+    if B != B2 or C != C2:
+        raise RuntimeError(f'fmap1 {tuple(fmap1_nhwc.shape)} and fmap2 {tuple(fmap2_nhwc.shape)} disagree on batch/channels')
+    lib = load()
+    dev = fmap1_nhwc.device
+    pyr = _new_pyramid(B, h1, w1, h2, w2, levels, 'fp32', dev)
+    ws_bytes = int(lib.sdof_corr_volume_workspace_bytes(B, h1, w1, h2, w2, C, levels, PRECISIONS[precision]))
+    ws = torch.empty(ws_bytes, dtype=u8, device=dev) if ws_bytes else None
+    check(lib.sdof_corr_volume_pyramid(ptr(fmap1_nhwc), ptr(fmap2_nhwc), B, h1, w1, h2, w2, C, levels,
+                                       PRECISIONS[precision], ptr(pyr.buf), ptr(ws), ws_bytes, stream_ptr(dev)),
+          'sdof_corr_volume_pyramid')
+    return pyr
+
+
 class CorrOperands:
-    """Prepared 16-bit operands of the fp16/bf16 correlation path (sdof_corr_prepare_operands): lets the pooled
-    feature pyramid of a key frame (fmap2) be built once and reused by every pair that shares it."""
+    """Round-1 single-workspace form of the prepared operands (sdof_corr_prepare_operands / sdof_corr_pyramid_from_operands,
+    fp32 pyramid).  New code uses CorrSource / CorrTarget."""
 
     def __init__(self, B, h1, w1, h2, w2, C, levels, precision, device):
         if precision not in ('fp16', 'bf16'):
@@ -92,9 +173,7 @@ class CorrOperands:
     def pyramid(self, out: 'CorrPyramid | None' = None) -> 'CorrPyramid':
         B, h1, w1, h2, w2, C = self.shape
         if out is None:
-            lay = _capi.pyramid_layout(B * h1 * w1, h2, w2, self.levels)
-            buf = torch.empty(max(int(lay.total_floats), 1), dtype=f32, device=self.workspace.device)
-            out = CorrPyramid(buf, lay, B, h1, w1, h2, w2, self.levels)
+            out = _new_pyramid(B, h1, w1, h2, w2, self.levels, 'fp32', self.workspace.device)
         check(load().sdof_corr_pyramid_from_operands(B, h1, w1, h2, w2, C, self.levels, PRECISIONS[self.precision], ptr(out.buf),
                                                      ptr(self.workspace), self.workspace.numel(),
                                                      stream_ptr(self.workspace.device)), 'sdof_corr_pyramid_from_operands')
@@ -102,7 +181,7 @@ class CorrOperands:
 
 
 def corr_lookup(pyr: CorrPyramid, coords: torch.Tensor, radius: int = 4, out: torch.Tensor | None = None) -> torch.Tensor:
-    """coords [B,2,h1,w1] -> [B, levels*(2r+1)^2, h1, w1] (C3)."""
+    """coords [B,2,h1,w1] -> [B, levels*(2r+1)^2, h1, w1] (C3); fp32 output from an fp32 or fp16 pyramid."""
     require_cuda(coords, 'coords', f32)
     if tuple(coords.shape) != (pyr.B, 2, pyr.h1, pyr.w1):
         raise RuntimeError(f'coords must be {(pyr.B, 2, pyr.h1, pyr.w1)}, got {tuple(coords.shape)}')
@@ -111,8 +190,10 @@ def corr_lookup(pyr: CorrPyramid, coords: torch.Tensor, radius: int = 4, out: to
         out = torch.empty((pyr.B, ch, pyr.h1, pyr.w1), dtype=f32, device=coords.device)
     else:
         require_cuda(out, 'out', f32)
-    check(load().sdof_corr_lookup(ptr(pyr.buf), ptr(coords), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2, pyr.levels, radius,
-                                  ptr(out), stream_ptr(coords.device)), 'sdof_corr_lookup')
+    if pyr.B == 0:
+        return out
+    check(load().sdof_corr_lookup_ex(ptr(pyr.buf), pyr.elem_bytes, ptr(coords), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2, pyr.levels,
+                                     radius, ptr(out), 0, stream_ptr(coords.device)), 'sdof_corr_lookup_ex')
     return out
 
 
@@ -354,8 +435,8 @@ def ellipse_half_widths(ksize: int):
 # --------------------------------------------------------------------------- RAFT update-loop glue (NHWC)
 def corr_lookup_nhwc(pyr: CorrPyramid, coords_nhwc: torch.Tensor, radius: int, out: torch.Tensor) -> torch.Tensor:
     """coords [B,h1,w1,2] -> out [B,h1,w1,levels*(2r+1)^2], channels-last."""
-    check(load().sdof_corr_lookup_nhwc(ptr(pyr.buf), ptr(coords_nhwc), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2, pyr.levels, radius,
-                                       ptr(out), stream_ptr(out.device)), 'sdof_corr_lookup_nhwc')
+    check(load().sdof_corr_lookup_ex(ptr(pyr.buf), pyr.elem_bytes, ptr(coords_nhwc), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2,
+                                     pyr.levels, radius, ptr(out), 1, stream_ptr(out.device)), 'sdof_corr_lookup_ex')
     return out
 
 

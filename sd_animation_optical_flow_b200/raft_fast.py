@@ -135,12 +135,22 @@ class FastEncoder:
         return self._cl(F.conv2d(x, w, b, stride=stride, padding=pad))
 
 
+class KeyFeatures:
+    """What a key frame contributes to every pair that uses it as image2 (SURVEY §8a flow-direction note): its feature map
+    and, on the 16-bit correlation path, the prepared TARGET operand (the avg-pooled fmap2 levels, built once)."""
+
+    def __init__(self, fmap2_nhwc: torch.Tensor, target):
+        self.fmap2, self.target = fmap2_nhwc, target
+
+
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
-                 own_fh2: bool = True):
+                 own_fh2: bool = True, corr_storage: str | None = None):
         """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
-        convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical."""
+        convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical.
+        corr_storage: 'fp16' / 'fp32' pyramid storage (default: fp16 with 16-bit correlation operands, else fp32)."""
         self.side_streams, self.own_convf1, self.own_fh2 = side_streams, own_convf1, own_fh2
+        self.corr_storage = corr_storage or ('fp16' if corr_precision in ('fp16', 'bf16') else 'fp32')
         if model.small:
             raise ValueError('FastRaft implements the basic RAFT model (the one the ofgen scripts use)')
         self.model = model
@@ -226,9 +236,21 @@ class FastRaft:
         return st
 
     @torch.no_grad()
-    def forward(self, image1: torch.Tensor, image2: torch.Tensor, iters: int = 20, normalized: bool = False):
+    def encode_key(self, image2: torch.Tensor, normalized: bool = False) -> KeyFeatures:
+        """Feature map (+ prepared correlation target) of ONE key frame [1,3|4,H,W]: fnet's InstanceNorm is per image, so
+        encoding the key alone gives exactly the features it has inside a pair batch."""
+        im2 = image2 if normalized else (2 * (image2 / 255.0) - 1.0).contiguous()
+        fmap2 = _to_nhwc(self.fnet(im2))
+        target = ops.CorrTarget(fmap2, 4, self.corr_precision) if self.corr_precision in ('fp16', 'bf16') else None
+        return KeyFeatures(fmap2, target)
+
+    @torch.no_grad()
+    def forward(self, image1: torch.Tensor, image2: torch.Tensor | None, iters: int = 20, normalized: bool = False,
+                key: KeyFeatures | None = None):
         """image1/2: [B,3,H,W] float 0..255 (H, W multiples of 8), or with normalized=True already 2*(x/255)-1 (any memory
         format; ops.normalize_pad_u8 hands over channels-last).  Returns (flow_low [B,h,w,2], flow_up [B,H,W,2]).
+        key: the encoded key frame serving as image2 of all B pairs (then `image2` is ignored): fnet(key) and the pooled
+        correlation operands are not recomputed per pair.
 
         Two independent chains run on a side stream (fork/join with events, so a CUDA-graph capture records them as
         parallel branches): the context encoder next to the feature encoder + correlation pyramid, and in every
@@ -247,7 +269,7 @@ class FastRaft:
             im1, im2 = image1, image2
         else:
             im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
-            im2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+            im2 = (2 * (image2 / 255.0) - 1.0).contiguous() if key is None else None
         H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128]
         HX = torch.empty((B, h, w, hd + xc), device=dev)                 # [h | motion | flow]      (update.py:47 minus inp)
         RH = torch.empty((B, h, w, hd), device=dev)                       # r*h                      (update.py:50)
@@ -273,8 +295,16 @@ class FastRaft:
                 ZRMAP[p].copy_(self._conv(inp, self.zr_ctx[p], bias=True))
                 QMAP[p].copy_(self._conv(inp, self.q_ctx[p], bias=True))
             del cn, inp
-        fmaps = self.fnet(torch.cat([im1, im2], 0))                       # ---- feature encoder + all-pairs volume
-        pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps[:B]), _to_nhwc(fmaps[B:]), 4, self.corr_precision)
+        if key is None:                                                   # ---- feature encoder + all-pairs volume
+            fmaps = self.fnet(torch.cat([im1, im2], 0))
+            pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps[:B]), _to_nhwc(fmaps[B:]), 4, self.corr_precision, self.corr_storage)
+        else:                                                             # key frame: its features / operands exist already
+            fmaps = self.fnet(im1)
+            if key.target is not None:
+                pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps), None, 4, self.corr_precision, self.corr_storage, target=key.target)
+            else:
+                pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps), key.fmap2.expand(B, -1, -1, -1).contiguous(), 4,
+                                              self.corr_precision, self.corr_storage)
         del fmaps
         main.wait_stream(side)
 

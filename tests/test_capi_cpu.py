@@ -93,8 +93,31 @@ def test_workspace_sizes(lib):
     assert ws(0) == 2 * n * 256 * 4         # tf32: rounded copies
     assert ws(1) == 4 * n * 256 * 4         # 3xtf32: hi + lo
     pooled = n + n // 4 + n // 16 + n // 64
-    assert ws(4) == max((n + pooled) * 256 * 2, 2 * n * 256 * 4)   # fp16: 16-bit fmap1 + pooled fmap2 levels (or the tf32 fallback)
-    assert ws(2) == (n + pooled) * 256 * 2                          # bf16
+    hdr = 2 * 2048                          # one scale header per operand buffer (source, target)
+    assert ws(4) == max((n + pooled) * 256 * 2 + hdr, 2 * n * 256 * 4)   # fp16: 16-bit fmap1 + pooled fmap2 levels (or the tf32 fallback)
+    assert ws(2) == (n + pooled) * 256 * 2 + hdr                          # bf16
+    assert lib.sdof_corr_src_operand_bytes(1, 96, 64, 256) + lib.sdof_corr_tgt_operand_bytes(1, 96, 64, 256, 4) == ws(2)
+    assert lib.sdof_corr_tgt_operand_bytes(1, 96, 64, 256, 4) == pooled * 256 * 2 + 2048   # a shared key-frame target: batch 1
+
+
+def test_fp16_pyramid_layout(lib):
+    """sdof_corr_pyramid_layout_ex: elem_bytes 4 == the fp32 layout; elem_bytes 2 = rows padded to 8 halves (an odd width
+    always has a spare column for the half2 pair store), levels 128-byte aligned, sizes in elements."""
+    import ctypes
+    from sd_animation_optical_flow_b200 import _capi
+    a, b = _capi.PyramidLayout(), _capi.PyramidLayout()
+    assert lib.sdof_corr_pyramid_layout(6144, 96, 64, 4, ctypes.byref(a)) == 0
+    assert lib.sdof_corr_pyramid_layout_ex(6144, 96, 64, 4, 4, ctypes.byref(b)) == 0
+    assert bytes(a) == bytes(b)
+    assert lib.sdof_corr_pyramid_layout_ex(6144, 96, 64, 4, 2, ctypes.byref(b)) == 0
+    assert list(b.w[:4]) == [64, 32, 16, 8] and list(b.wp[:4]) == [64, 32, 16, 8]
+    assert b.total_floats * 2 == 6144 * (96 * 64 + 48 * 32 + 24 * 16 + 12 * 8) * 2      # 100.3 MB: half of the fp32 pyramid
+    assert lib.sdof_corr_pyramid_layout_ex(396, 18, 22, 4, 2, ctypes.byref(b)) == 0
+    assert list(b.w[:4]) == [22, 11, 5, 2] and list(b.wp[:4]) == [24, 16, 8, 8]
+    for l in range(4):
+        assert b.wp[l] > b.w[l] or b.w[l] % 2 == 0
+        assert (b.offset[l] * 2) % 128 == 0
+    assert lib.sdof_corr_pyramid_layout_ex(1, 8, 8, 4, 3, ctypes.byref(b)) != 0
 
 
 def test_product_path_has_no_cpu_fallback():

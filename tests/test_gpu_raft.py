@@ -215,3 +215,68 @@ def test_config5_size_fast_path_equals_module_forward(cuda):
     e = (fast.estimate_flow(c, d2) - slow.estimate_flow(c, d2)).norm(dim=-1)
     assert fast.estimate_flow(c, d2).shape == (1, 250, 333, 2) and float(e.mean()) <= 2e-3
     assert fast.estimate_flow(c, d2, unpad=False).shape == (1, 256, 336, 2)
+
+
+def test_graph_output_is_a_copy_when_only_rows_are_padded(cuda):
+    """B=1 and height-only padding (132x160 -> 136x160): the unpadded slice of the graph's static output
+    is 'contiguous', so it must be cloned explicitly -- a second call must not overwrite the first result."""
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    f1, f2 = gi.shifted_pair(132, 160, 91)
+    a = torch.from_numpy(f1).to(cuda)[None]
+    b = torch.from_numpy(f2).to(cuda)[None]
+    graphed = RaftEngine(checkpoint=None, iters=4, seed=3, device=cuda, use_cuda_graph=True)
+    eager = RaftEngine(checkpoint=None, iters=4, seed=3, device=cuda, use_cuda_graph=False)
+    first = graphed.estimate_flow(a, b)
+    keep = first.clone()
+    second = graphed.estimate_flow(b, a)          # same graph key, different inputs
+    assert first.data_ptr() != second.data_ptr()
+    assert torch.equal(first, keep), 'the first result was overwritten by the next replay'
+    assert first.shape == (1, 132, 160, 2)
+    assert torch.allclose(first, eager.estimate_flow(a, b), atol=1e-4)
+    assert not torch.allclose(first, second, atol=1e-2)
+
+
+def test_keyed_flow_equals_pairwise_flow(cuda):
+    """estimate_flow_keyed(key, frames) == estimate_flow(frames, key repeated): fnet(key) and the pooled correlation operands
+    computed once per key (InstanceNorm is per image, so the key's features do not depend on the batch it is encoded in)."""
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    canvas = gi.texture(128 + 32, 160 + 32, 321)
+    frames = np.stack([canvas[4 * i:4 * i + 128, 3 * i:3 * i + 160] for i in range(4)])
+    key2 = gi.texture(128, 160, 322)
+    fr = torch.from_numpy(frames).to(cuda)
+    for graph in (False, True):
+        eng = RaftEngine(checkpoint=None, iters=4, seed=0, device=cuda, use_cuda_graph=graph)
+        k = eng.encode_key(fr[0])
+        flow_k = eng.estimate_flow_keyed(k, fr[1:])
+        flow_p = eng.estimate_flow(fr[1:], fr[:1].expand(3, -1, -1, -1).contiguous())
+        assert flow_k.shape == flow_p.shape == (3, 128, 160, 2)
+        d = (flow_k - flow_p).norm(dim=-1)
+        print(f'keyed vs pairwise (graph={graph}): EPE mean {float(d.mean()):.2e} max {float(d.max()):.2e}')
+        assert float(d.max()) <= 1e-3
+        # a second key through the same graph (static operand buffers are refreshed), then the first one again
+        k2 = eng.encode_key(torch.from_numpy(key2).to(cuda))
+        f2 = eng.estimate_flow_keyed(k2, fr[1:])
+        p2 = eng.estimate_flow(fr[1:], torch.from_numpy(key2).to(cuda)[None].expand(3, -1, -1, -1).contiguous())
+        assert float((f2 - p2).norm(dim=-1).max()) <= 1e-3
+        assert torch.allclose(eng.estimate_flow_keyed(k, fr[1:]), flow_k, atol=1e-5)
+
+
+def test_engine_on_a_device_that_is_not_current(cuda):
+    """engine, warp and masks on cuda:1 while cuda:0 is current (PDCNetAux(device=cuda:N))."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from sd_animation_optical_flow_b200 import ops
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    d1 = torch.device('cuda', 1)
+    torch.cuda.set_device(0)
+    f1, f2 = gi.raft_inputs('basic')
+    e0 = RaftEngine(checkpoint=None, iters=3, seed=0, device=cuda)
+    e1 = RaftEngine(checkpoint=None, iters=3, seed=0, device=d1)
+    r0 = e0.estimate_flow(torch.from_numpy(f1).to(cuda)[None], torch.from_numpy(f2).to(cuda)[None])
+    r1 = e1.estimate_flow(torch.from_numpy(f1).to(d1)[None], torch.from_numpy(f2).to(d1)[None])
+    assert torch.cuda.current_device() == 0 and r1.device == d1
+    assert torch.allclose(r0, r1.to(cuda), atol=1e-4)
+    img = torch.from_numpy(f1).to(d1)
+    w1 = ops.warp(img, r1[0])
+    w0 = ops.warp(img.to(cuda), r1[0].to(cuda))
+    assert torch.cuda.current_device() == 0 and torch.equal(w0, w1.to(cuda))

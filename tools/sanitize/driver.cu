@@ -92,6 +92,37 @@ static void corr_case(int B, int h, int w, int C, int precision, const char* nam
   cudaFree(f1); cudaFree(f2); cudaFree(pyr); cudaFree(ws); cudaFree(dc); cudaFree(dn); cudaFree(out);
 }
 
+// round-2 path: split operands (shared key-frame target, B2 = 1), fp16-stored pyramid, lookup reading it
+static void corr_half_case(int B, int h, int w, int C) {
+  const int levels = 4, r = 4;
+  sdof_pyramid_layout lay;
+  SD(sdof_corr_pyramid_layout_ex((int64_t)B * h * w, h, w, levels, 2, &lay));
+  float* f1 = dfloats((size_t)B * h * w * C, 300.f);      // auto-ranging: far from unit scale
+  float* key = dfloats((size_t)h * w * C, 1e-3f);
+  const int64_t sb = sdof_corr_src_operand_bytes(B, h, w, C), tb = sdof_corr_tgt_operand_bytes(1, h, w, C, levels);
+  void* so = dalloc<uint8_t>((size_t)sb);
+  void* to = dalloc<uint8_t>((size_t)tb);
+  uint16_t* pyr = dalloc<uint16_t>((size_t)lay.total_floats);
+  SD(sdof_corr_prepare_tgt(key, 1, h, w, C, levels, SDOF_PREC_FP16, to, tb, nullptr));
+  SD(sdof_corr_prepare_src(f1, B, h, w, C, SDOF_PREC_FP16, so, sb, nullptr));
+  SD(sdof_corr_pyramid_from_parts(so, to, B, h, w, 1, h, w, C, levels, SDOF_PREC_FP16, 2, pyr, nullptr));
+  std::vector<float> hn((size_t)B * h * w * 2);
+  for (int b = 0; b < B; ++b)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        hn[(((size_t)b * h + y) * w + x) * 2 + 0] = x + 7.f * frand();
+        hn[(((size_t)b * h + y) * w + x) * 2 + 1] = y + 7.f * frand();
+      }
+  float* dn = dalloc<float>(hn.size());
+  CK(cudaMemcpy(dn, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice));
+  float* out = dalloc<float>((size_t)B * 324 * h * w);
+  SD(sdof_corr_lookup_ex(pyr, 2, dn, B, h, w, h, w, levels, r, out, 1, nullptr));
+  SD(sdof_corr_lookup_ex(pyr, 2, dn, B, h, w, h, w, levels, r, out, 0, nullptr));   // (coords read as planar: any values do)
+  CK(cudaDeviceSynchronize());
+  printf("ok corr fp16-stored pyramid, shared target B=%d %dx%d C=%d\n", B, h, w, C);
+  cudaFree(f1); cudaFree(key); cudaFree(so); cudaFree(to); cudaFree(pyr); cudaFree(dn); cudaFree(out);
+}
+
 static void alt_corr_case(int B, int h, int w, int C) {
   float* f1 = dfloats((size_t)B * h * w * C, 1.f);
   float* f2 = dfloats((size_t)B * h * w * C, 1.f);
@@ -234,6 +265,8 @@ int main(int argc, char** argv) {
     corr_case(1, 24, 40, 256, SDOF_PREC_TF32, "tf32");    // streaming kernel
     corr_case(1, 18, 22, 64, SDOF_PREC_3XTF32, "3xtf32");
     corr_case(1, 10, 12, 32, SDOF_PREC_FP32, "fp32");
+    corr_half_case(2, 24, 40, 256);                       // 32x4 / 16x8 / 8x16 patches, partial source block
+    corr_half_case(1, 18, 22, 64);                        // odd pooled widths 11, 5: the pair store's padding column
     alt_corr_case(1, 20, 24, 256);
   }
   if (all || !strcmp(what, "warp")) {
