@@ -23,6 +23,7 @@ constexpr int kStagePitch = kLookupPx + 1;      // +1: conflict-free column writ
 struct LookupLevels {
   int levels;
   const void* base[SDOF_MAX_LEVELS];   // float or __half maps (template parameter of the kernel)
+  const void* header;                  // start of the pyramid buffer (fp16 pyramids: float[0] = factor)
   long long pitch[SDOF_MAX_LEVELS];
   int h[SDOF_MAX_LEVELS], w[SDOF_MAX_LEVELS], wp[SDOF_MAX_LEVELS];
 };
@@ -53,9 +54,10 @@ __device__ __forceinline__ void blend_window(const float* __restrict__ win, int 
 }
 
 __device__ __forceinline__ void blend_window_strided(const float* __restrict__ win, int D, float fx, float fy,
-                                                     float* __restrict__ dst, int stride, int lane, int T1 = 0) {
+                                                     float* __restrict__ dst, int stride, int lane, int T1 = 0, float scale = 1.0f) {
   if (T1 == 0) T1 = D + 1;   // window row stride
-  const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+  // the (power-of-two, or 1) scale of an fp16 pyramid goes into the four blend weights
+  const float w00 = (1.f - fx) * (1.f - fy) * scale, w01 = fx * (1.f - fy) * scale, w10 = (1.f - fx) * fy * scale, w11 = fx * fy * scale;
   for (int k = lane; k < D * D; k += 32) {
     const int ix = k / D, iy = k - ix * D;
     const float* q = win + iy * T1 + ix;
@@ -96,6 +98,9 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
   const int p0 = blockIdx.x * PX;
   const int p = p0 + warp;
   float* win = win_all + warp * L * T;
+  // fp16 pyramid: stored values are raw accumulators of the auto-ranged operands; the header holds the factor back to
+  // correlation units (sdof_corr_pyramid_layout_ex).  levels share one header, lv.base[0] is 128 bytes behind it.
+  const float factor = kHalf ? __ldg(reinterpret_cast<const float*>(lv.header)) : 1.0f;
   if (p < N1) {
     // nhwc: coords [B,h,w,2] and out [B,h,w,CH] (channels-last, for the NHWC update loop); else the
     // reference's planar layouts coords [B,2,h,w] / out [B,CH,h,w]
@@ -154,9 +159,9 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
     for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
       if (l >= L) break;
       if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
-        blend_window_strided(win + l * T + xos[l], D, fxs[l], fys[l], out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane, WS);
+        blend_window_strided(win + l * T + xos[l], D, fxs[l], fys[l], out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane, WS, factor);
       else
-        blend_window(win + l * T + xos[l], D, fxs[l], fys[l], 1.0f, stage + l * DD * kStagePitch + warp, lane, WS);
+        blend_window(win + l * T + xos[l], D, fxs[l], fys[l], factor, stage + l * DD * kStagePitch + warp, lane, WS);
     }
   }
   if (nhwc) return;
@@ -299,6 +304,7 @@ static int corr_lookup_impl(const char* name, const void* pyramid, int elem_byte
   if (B == 0) return SDOF_OK;
   LookupLevels lv;
   lv.levels = levels;
+  lv.header = pyramid;
   for (int l = 0; l < SDOF_MAX_LEVELS; ++l) {
     const int ll = l < levels ? l : 0;
     lv.base[l] = reinterpret_cast<const uint8_t*>(pyramid) + lay.offset[ll] * elem_bytes;

@@ -83,6 +83,7 @@ struct ResArgs {
   void* out[kRLevels];                 // float* or __half* (OUT_HALF)
   const float* src_hdr;                // operand headers: the epilogue undoes the operand scales
   const float* tgt_hdr;
+  float* out_factor;                   // fp16 pyramid header (float[0]): stored * factor = correlation
   int total_tiles;
   float divisor;                       // sqrt(C)
   float rsqrt_c;                       // 1/sqrt(C) when that is a power of two (use_div == 0)
@@ -268,6 +269,11 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
     const float mul = __ldg(args.src_hdr + kHdrInvScale) * __ldg(args.tgt_hdr + kHdrInvScale) * (use_div ? 1.0f : args.rsqrt_c);
     const int mrow = 32 * q + lane;  // TMEM lane = row of the A tile = patch pixel (x fastest)
     const bool odd = (lane & 1) != 0;
+    if (OUT_HALF && blockIdx.x == 0 && threadIdx.x == 0) {
+      // fp16 pyramid: stored value = raw accumulator; true correlation = stored * factor (read by the lookup kernel)
+      const float f = __ldg(args.src_hdr + kHdrInvScale) * __ldg(args.tgt_hdr + kHdrInvScale);
+      *args.out_factor = use_div ? __fdiv_rn(f, divisor) : f * args.rsqrt_c;
+    }
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const TileInfo ti = unpack_tile(args, table[t - t_begin]);
@@ -298,46 +304,55 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
       if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
 
       if constexpr (OUT_HALF) {
+        // The operands were scaled so that |accumulator| < 2^15 (corr_prep16_kernel), so the raw fp32 accumulator converts
+        // to fp16 without overflow and WITHOUT a multiply; the pyramid header carries the factor the lookup applies.
         // Lanes (2i, 2i+1) hold x and x+1 of every column (source pixel).  Per column pair (j, j+1) they swap one
         // register: the even lane ends up with (x, x+1) of column j, the odd lane with (x-1, x) of column j+1, and each
         // stores ONE packed half2 into its column's map -- 16 lanes x 4 B = a 64-byte run per map and instruction.
         const int xe = x & ~1;
-        const bool in = !(args.debug & 1) && y < args.lh[l] && xe < args.lw[l];
+        const bool in = y < args.lh[l] && xe < args.lw[l];
         const bool all_in = __all_sync(0xffffffffu, in);
+        const bool do_store = !(args.debug & 1);
         __half2* p = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(args.out[l]) +
                                                 ((long long)ti.b * args.n1 + m0 + (odd ? 1 : 0)) * pitch + (long long)y * args.wp[l] + xe);
         const long long pstep = pitch;  // two columns further, in half2 units
         auto store_chunk = [&](const uint32_t (&u)[32], int chunk) {
           const int ncols = mcount - chunk * 32;
-          if (ncols <= 0) return;  // warp-uniform
-          const bool fast = ncols >= 32 && all_in && !use_div;
+          if (ncols >= 32 && all_in) {
 #pragma unroll
-          for (int jj = 0; jj < 32; jj += 2) {
-            if (!fast && jj >= ncols) break;  // warp-uniform
-            float a = __uint_as_float(u[jj]) * mul, b = __uint_as_float(u[jj + 1]) * mul;
-            if (use_div) {
-              a = __fdiv_rn(a, divisor);
-              b = __fdiv_rn(b, divisor);
+            for (int jj = 0; jj < 32; jj += 2) {
+              const uint32_t mine = odd ? u[jj + 1] : u[jj];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? u[jj] : u[jj + 1], 1);
+              const __half2 v = __floats2half2_rn(__uint_as_float(odd ? recv : mine), __uint_as_float(odd ? mine : recv));
+              if (do_store) *p = v;
+              p += pstep;
             }
-            const float recv = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
-            const float lo = odd ? recv : a, hi = odd ? b : recv;
-            const __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-            if (fast || (in && jj + (odd ? 1 : 0) < ncols)) *p = v;
-            p += pstep;
+          } else if (ncols > 0) {
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 2) {
+              if (jj < ncols) {  // warp-uniform
+                const uint32_t mine = odd ? u[jj + 1] : u[jj];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? u[jj] : u[jj + 1], 1);
+                const __half2 v = __floats2half2_rn(__uint_as_float(odd ? recv : mine), __uint_as_float(odd ? mine : recv));
+                if (do_store && in && jj + (odd ? 1 : 0) < ncols) *p = v;
+                p += pstep;
+              }
+            }
           }
         };
         store_chunk(ua, 0);
         store_chunk(ub, 1);
       } else {
-        const bool in = !(args.debug & 1) && y < args.lh[l] && x < args.lw[l];
+        const bool in = y < args.lh[l] && x < args.lw[l];
         const bool all_in = __all_sync(0xffffffffu, in);
+        const bool do_store = !(args.debug & 1);
         float* p = reinterpret_cast<float*>(args.out[l]) + ((long long)ti.b * args.n1 + m0) * pitch + (long long)y * args.wp[l] + x;
         auto store_chunk = [&](const uint32_t (&u)[32], int chunk) {
           const int ncols = mcount - chunk * 32;
           if (ncols >= 32 && all_in && !use_div) {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
-              *p = __uint_as_float(u[jj]) * mul;
+              if (do_store) *p = __uint_as_float(u[jj]) * mul;
               p += pitch;
             }
           } else if (ncols > 0) {
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
               if (jj < ncols) {  // warp-uniform
                 float v = __uint_as_float(u[jj]) * mul;
                 if (use_div) v = __fdiv_rn(v, divisor);
-                if (in) *p = v;
+                if (in && do_store) *p = v;
                 p += pitch;
               }
             }
@@ -388,6 +403,7 @@ struct PrepArgs {
   int B, n1, h2, w2, C4, levels;
   int lh[kRLevels], lw[kRLevels];
   int fmt;
+  int src_exp, tgt_exp;                 // see scale_from_partials
 };
 
 // Per-tensor abs-max, pass 1: kAmaxBlocks partial maxima per tensor into the operand header (no atomics, no reset needed;
@@ -424,9 +440,13 @@ __global__ void __launch_bounds__(256) corr_absmax_kernel(const float4* __restri
   }
 }
 
-// Pass 2 (inside the conversion kernel): the power-of-two scale that puts the tensor's abs-max at [2^13, 2^14) -- two
-// binades below the fp16 maximum, so 2x2 pooling and rounding cannot overflow.  1 for an all-zero / non-finite tensor.
-__device__ __forceinline__ float scale_from_partials(const float* __restrict__ part, int lane) {
+// Pass 2 (inside the conversion kernel): the power-of-two scale of a tensor from its abs-max partials; 1 for an all-zero /
+// non-finite tensor.
+// The scales of the two tensors are chosen so that C * max|f1 s1| * max|f2 s2| < 2^15: the fp32 accumulator of ANY pair of
+// pixels then fits fp16, so the fp16-stored pyramid is written without a rescale or a clamp (target_exp: amax * s lands in
+// [2^(target_exp-1), 2^target_exp); for C = 256: 2^4 for fmap1, 2^3 for fmap2).  fp16 keeps 11 significant bits down to
+// 2^-14, i.e. for every element larger than 2^-17 of the tensor's maximum.
+__device__ __forceinline__ float scale_from_partials(const float* __restrict__ part, int lane, int target_exp) {
   float m = 0.f;
   for (int i = lane; i < kAmaxBlocks; i += 32) m = fmaxf(m, part[i]);
 #pragma unroll
@@ -434,7 +454,7 @@ __device__ __forceinline__ float scale_from_partials(const float* __restrict__ p
   if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
   int e;
   frexpf(m, &e);                      // m = f * 2^e, f in [0.5, 1)
-  e = 14 - e;
+  e = target_exp - e;
   e = e < -100 ? -100 : (e > 100 ? 100 : e);
   return ldexpf(1.0f, e);
 }
@@ -499,7 +519,7 @@ __global__ void __launch_bounds__(256, 4) corr_prep16_kernel(const __grid_consta
   const bool is_src = blk < a.nb_src;
   if (threadIdx.x < 32) {
     float* hdr = is_src ? a.src_hdr : a.tgt_hdr;
-    const float sc = scale_from_partials(hdr, threadIdx.x);
+    const float sc = scale_from_partials(hdr, threadIdx.x, is_src ? a.src_exp : a.tgt_exp);
     if (threadIdx.x == 0) {
       s_scale = sc;
       if (blk == 0 || blk == a.nb_src) {
@@ -656,6 +676,12 @@ int launch_corr_prepare_parts(const float* fmap1, int B, int n1, void* src_ops, 
   pa.fmap2 = fmap2;
   pa.B = fmap2 ? B2 : B; pa.n1 = n1; pa.h2 = h2; pa.w2 = w2; pa.C4 = C / 4; pa.levels = levels;
   pa.fmt = fmt;
+  {
+    int L = 0;
+    while ((1 << L) < C) ++L;
+    pa.src_exp = (15 - L + 1) / 2;   // ceil
+    pa.tgt_exp = (15 - L) / 2;       // floor: src_exp + tgt_exp + L == 15
+  }
   if (fmap1) {
     pa.src_hdr = reinterpret_cast<float*>(src_ops);
     pa.src16 = reinterpret_cast<uint8_t*>(src_ops) + kOpHdrBytes;
@@ -775,6 +801,7 @@ int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, i
     ra.pitch[l] = lay.pitch[l];
     ra.out[l] = out_half ? static_cast<void*>(reinterpret_cast<__half*>(pyramid) + lay.offset[l])
                          : static_cast<void*>(reinterpret_cast<float*>(pyramid) + lay.offset[l]);
+    ra.out_factor = reinterpret_cast<float*>(pyramid);   // fp16 layout: the first 128 bytes are the header
   }
   const long long total = (long long)B * ra.m_tiles * ra.tile_begin_level[used_levels];
   if (total > 0x7fffffff) return SDOF_ERR_UNSUPPORTED;
@@ -849,7 +876,7 @@ int sdof_corr_pyramid_layout_ex(int64_t rows, int h2, int w2, int levels, int el
   SDOF_REQUIRE(rows >= 0 && h2 >= 1 && w2 >= 1, "sdof_corr_pyramid_layout_ex: bad sizes rows=%lld h2=%d w2=%d", (long long)rows, h2, w2);
   memset(out, 0, sizeof(*out));
   out->levels = levels;
-  int64_t off = 0;
+  int64_t off = 64;  // 128-byte header: float[0] = factor (stored value * factor = correlation), written by the volume kernel
   for (int l = 0; l < levels; ++l) {
     const int h = h2 >> l, w = w2 >> l;
     const int wp = (w + 7) & ~7;  // rows start 16-byte aligned; an odd width always has a spare padding column

@@ -42,7 +42,7 @@ class RaftEngine:
                  corr_precision: str = 'fp16', alternate_corr: bool = False, mixed_precision: bool = False,
                  channels_last: bool = False, use_cuda_graph: bool | None = None, device=None, seed: int = 0,
                  fast: bool | None = None, cudnn_benchmark: bool = True, fast_options: dict | None = None,
-                 max_graphs: int = 4):
+                 max_graphs: int = 4, flow_head_scale: float = 1.0):
         if not torch.cuda.is_available():
             raise RuntimeError('RaftEngine needs a CUDA device (B200); there is no CPU path')
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
@@ -55,7 +55,7 @@ class RaftEngine:
                                     corr_precision=corr_precision)
         model = RAFT(self.args)
         if checkpoint is None:
-            fill_weights_by_name(model, seed)
+            fill_weights_by_name(model, seed, flow_head_scale)   # no checkpoint: name-seeded random-init weights
         else:
             model.load_state_dict(load_raft_state_dict(checkpoint))
         model = model.to(self.device).eval()

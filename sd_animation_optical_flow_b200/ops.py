@@ -32,10 +32,25 @@ class CorrPyramid:
 
     def level(self, l: int) -> torch.Tensor:
         """View of level l shaped like the reference's corr_pyramid[l]:
-        [B*h1*w1, 1, h_l, w_l] (RAFT/core/corr.py:21-27); strided when the row pitch is padded."""
+        [B*h1*w1, 1, h_l, w_l] (RAFT/core/corr.py:21-27); strided when the row pitch is padded.
+        For an fp16 pyramid these are the STORED values (raw accumulators of the auto-ranged operands): multiply by
+        `factor`, or use `level_values`, for correlation units."""
         lay = self.layout
         rows = self.B * self.h1 * self.w1
         return torch.as_strided(self.buf, (rows, 1, lay.h[l], lay.w[l]), (lay.pitch[l], 0, lay.wp[l], 1), lay.offset[l])
+
+    @property
+    def factor(self) -> torch.Tensor:
+        """0-d fp32 tensor: stored value * factor = correlation (1 for an fp32 pyramid; an fp16 pyramid keeps it in the
+        128-byte header of the buffer, where the lookup kernel reads it)."""
+        if self.buf.dtype == f32:
+            return torch.ones((), dtype=f32, device=self.buf.device)
+        return self.buf[:2].view(f32)[0]
+
+    def level_values(self, l: int) -> torch.Tensor:
+        """Level l in correlation units, fp32 (a copy for an fp16 pyramid)."""
+        v = self.level(l)
+        return v if v.dtype == f32 else v.float() * self.factor
 
 
 STORAGE = {'fp32': (f32, 4), 'fp16': (torch.float16, 2)}

@@ -361,11 +361,14 @@ class RAFT(nn.Module):
         return preds
 
 
-def fill_weights_by_name(module: nn.Module, seed: int = 0) -> nn.Module:
+def fill_weights_by_name(module: nn.Module, seed: int = 0, flow_head_scale: float = 1.0) -> nn.Module:
     """Deterministic weights that depend only on (seed, parameter name, shape),
     not on module construction order: lets the reference RAFT (golden
     generator) and this RAFT (tests, bench 'random-init weights') hold
-    identical parameters without shipping a 21 MB checkpoint."""
+    identical parameters without shipping a 21 MB checkpoint.
+    flow_head_scale != 1 scales the flow head's output convolution (update_block.flow_head.conv2): plain random weights make
+    the update block an amplifier (the flow runs away to ~100 px in 20 iterations); 0.02 keeps the flow at a few px, the
+    regime a trained checkpoint works in (tests/golden_inputs.py RAFT_FULL_CASES `calm`, bench.py)."""
     sd = module.state_dict()
     with torch.no_grad():
         for name in sorted(sd):
@@ -384,5 +387,7 @@ def fill_weights_by_name(module: nn.Module, seed: int = 0) -> nn.Module:
                 v = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
             else:
                 v = 0.05 * torch.randn(t.shape, generator=g)
+            if flow_head_scale != 1.0 and name.startswith('update_block.flow_head.conv2.'):
+                v = v * flow_head_scale
             t.copy_(v.to(t.dtype))
     return module

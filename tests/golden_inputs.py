@@ -97,12 +97,7 @@ def raft_full_weights(model, name: str):
     """Name-seeded weights of a full-size case on `model` (the reference RAFT or this package's)."""
     from sd_animation_optical_flow_b200.raft import fill_weights_by_name
     cfg = RAFT_FULL_CASES[name]
-    fill_weights_by_name(model, cfg['seed'])
-    if cfg['fh_scale'] != 1.0:
-        conv = model.update_block.flow_head.conv2
-        conv.weight.data.mul_(cfg['fh_scale'])
-        conv.bias.data.mul_(cfg['fh_scale'])
-    return model
+    return fill_weights_by_name(model, cfg['seed'], flow_head_scale=cfg['fh_scale'])
 
 
 def full_lattice(H: int, W: int):

@@ -111,7 +111,8 @@ def test_fp16_pyramid_layout(lib):
     assert bytes(a) == bytes(b)
     assert lib.sdof_corr_pyramid_layout_ex(6144, 96, 64, 4, 2, ctypes.byref(b)) == 0
     assert list(b.w[:4]) == [64, 32, 16, 8] and list(b.wp[:4]) == [64, 32, 16, 8]
-    assert b.total_floats * 2 == 6144 * (96 * 64 + 48 * 32 + 24 * 16 + 12 * 8) * 2      # 100.3 MB: half of the fp32 pyramid
+    assert b.offset[0] == 64                                                              # 128-byte header (the factor)
+    assert b.total_floats * 2 == 6144 * (96 * 64 + 48 * 32 + 24 * 16 + 12 * 8) * 2 + 128  # 100.3 MB: half of the fp32 pyramid
     assert lib.sdof_corr_pyramid_layout_ex(396, 18, 22, 4, 2, ctypes.byref(b)) == 0
     assert list(b.w[:4]) == [22, 11, 5, 2] and list(b.wp[:4]) == [24, 16, 8, 8]
     for l in range(4):

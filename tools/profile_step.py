@@ -28,6 +28,17 @@ if mode == 'step':
     ops.warp(sty, eng.estimate_flow(a, b), 'cv2_cubic', -1.0)
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
+elif mode == 'corr16':
+    # the round-2 product path: fp16 operands (auto-ranged), fp16-stored pyramid, lookup reading it
+    hh, ww = (90, 160) if prec == 'L' else (96, 64)
+    f1 = torch.randn((1, hh, ww, 256), generator=g, device=dev)
+    f2 = torch.randn((1, hh, ww, 256), generator=g, device=dev)
+    coords_nhwc = (coords_grid(1, hh, ww, dev) + 2 * torch.randn((1, 2, hh, ww), generator=g, device=dev)).permute(0, 2, 3, 1).contiguous()
+    look_nhwc = torch.empty((1, hh, ww, 324), device=dev)
+    for _ in range(3):
+        pyr = ops.corr_volume_pyramid(f1, f2, 4, 'fp16', 'fp16')
+        ops.corr_lookup_nhwc(pyr, coords_nhwc, 4, look_nhwc)
+    torch.cuda.synchronize()
 else:
     f1 = torch.randn((1, 96, 64, 256), generator=g, device=dev)
     f2 = torch.randn((1, 96, 64, 256), generator=g, device=dev)

@@ -136,7 +136,7 @@ def measure(dev=None, sizes=((96, 64), (90, 160)), raft_sizes=((768, 512),), ite
                 for alt in ((False, True) if ref_op is not None else (False,)):
                     args = _Namespace()
                     args.small, args.mixed_precision, args.alternate_corr = False, False, alt
-                    model = fill_weights_by_name(RefRAFT(args), 0).to(dev).eval()
+                    model = fill_weights_by_name(RefRAFT(args), 0, flow_head_scale=0.02).to(dev).eval()   # bench.py's weights
                     tag = 'alternate_corr' if alt else 'corrblock'
                     for conv_tf32 in ((True,) if quick else (True, False)):
                         torch.backends.cudnn.allow_tf32 = conv_tf32     # torch's default is True: what the unmodified reference runs
@@ -152,7 +152,7 @@ def measure(dev=None, sizes=((96, 64), (90, 160)), raft_sizes=((768, 512),), ite
                     del model
                 # ours on the same pair, same weights: device-resident estimate_flow (bench defaults)
                 torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
-                eng = RaftEngine(checkpoint=None, iters=iters, seed=0, device=dev)
+                eng = RaftEngine(checkpoint=None, iters=iters, seed=0, flow_head_scale=0.02, device=dev)
                 a = torch.from_numpy(f1).to(dev)[None]
                 b = torch.from_numpy(f2).to(dev)[None]
                 row['ours_estimate_flow_ms'] = round(_time(lambda: eng.estimate_flow(a, b), 10, torch, warm=3) * 1e3, 3)

@@ -28,6 +28,16 @@ def main():
             if k in hdr:
                 i = hdr.index(k)
                 print(f'   {k:88s} {r[i]:>16s} {units[i]}')
+        # warp stall reasons (cycles a warp waits per issued instruction), largest first
+        stalls = []
+        for i, k in enumerate(hdr):
+            if 'issue_stalled' in k and k.endswith('_per_warp_active.pct') and 'not_issued' not in k:
+                try:
+                    stalls.append((float(r[i].replace(',', '')), k))
+                except ValueError:
+                    pass
+        for v, k in sorted(stalls, reverse=True)[:8]:
+            print(f'   stall {k[len("smsp__average_warps_issue_stalled_"):-len("_per_warp_active.pct")]:80s} {v:>16.2f} %')
 
 
 if __name__ == '__main__':
