@@ -44,12 +44,12 @@ __device__ __forceinline__ int safe_floor(float v, float* frac) {
 __device__ __forceinline__ void blend_window(const float* __restrict__ win, int D, float fx, float fy, float scale,
                                              float* __restrict__ stage_col, int lane, int T1 = 0) {
   if (T1 == 0) T1 = D + 1;   // window row stride
-  const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+  // `scale` goes into the four blend weights (same arithmetic as blend_window_strided: both output layouts agree bit for bit)
+  const float w00 = (1.f - fx) * (1.f - fy) * scale, w01 = fx * (1.f - fy) * scale, w10 = (1.f - fx) * fy * scale, w11 = fx * fy * scale;
   for (int k = lane; k < D * D; k += 32) {
     const int ix = k / D, iy = k - ix * D;
     const float* q = win + iy * T1 + ix;
-    float v = q[0] * w00 + q[1] * w01 + q[T1] * w10 + q[T1 + 1] * w11;
-    stage_col[k * kStagePitch] = v * scale;
+    stage_col[k * kStagePitch] = q[0] * w00 + q[1] * w01 + q[T1] * w10 + q[T1 + 1] * w11;
   }
 }
 
