@@ -180,6 +180,12 @@ int sdof_warp_bilinear_u8(const uint8_t* src, const float* flow, int B, int src_
 int sdof_warp_bilinear_f32(const float* src, const float* flow, int B, int src_batched, int Hs, int Ws, int C, int H,
                            int W, float sign, float* dst, sdof_stream_t stream);
 
+/* W3: cv2.resize(src, (Wd, Hd), interpolation=cv2.INTER_CUBIC) for float32 images, the two resizes of warp_frame_latent
+ * (pdcnet_of.py:24,30; dup ofgen_pixel_inpaint.py:92-103) around the cubic warp: src [B,Hs,Ws,C] -> dst [B,Hd,Wd,C], both
+ * channels-last.  OpenCV's float path restated (1/scale in double, float32 a = -0.75 weights, border replication, no
+ * antialiasing); agrees with cv2 to 2e-7 of the image range at the x8 / /8 ratios the reference uses. */
+int sdof_resize_cubic_f32(const float* src, int B, int Hs, int Ws, int C, int Hd, int Wd, float* dst, sdof_stream_t stream);
+
 /* Host-side copy of the 1024x16 int16 bicubic weight table the u8 kernel uses
  * (out: host int16[16384]); lets CPU tests pin it against OpenCV without a GPU. */
 int sdof_cubic_table_i16(int16_t* out /* host */);

@@ -234,3 +234,49 @@ def warp_frame_latent(latent_chw: np.ndarray, flow: np.ndarray, sign: float = 1.
     rem = remap_cubic(big, mx, my)
     small = cv2.resize(rem, (lw, lh), interpolation=cv2.INTER_CUBIC)
     return np.ascontiguousarray(np.transpose(small, (2, 0, 1)))
+
+
+# ----------------------------------------------------------------------------- cv2.resize(INTER_CUBIC), float32
+def _cubic_coeffs_f32(x: np.ndarray) -> np.ndarray:
+    """OpenCV's interpolateCubic (imgproc/resize.cpp), A = -0.75, evaluated in float32; returns [..., 4]."""
+    A = np.float32(-0.75)
+    x = x.astype(np.float32)
+    one = np.float32(1.0)
+    c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    c2 = ((A + np.float32(2)) * (one - x) - (A + np.float32(3))) * (one - x) * (one - x) + one
+    c3 = one - c0 - c1 - c2
+    return np.stack([c0, c1, c2, c3], -1).astype(np.float32)
+
+
+def _resize_axis_table(n_src: int, n_dst: int):
+    """Per destination index: the four source indices (replicated at the borders) and the float32 weights of
+    cv::resize's INTER_CUBIC: f = float((d + 0.5) * scale - 0.5) with scale = 1 / (n_dst / n_src) in double, s = floor(f)."""
+    scale = 1.0 / (float(n_dst) / float(n_src))
+    d = np.arange(n_dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    frac = (f - s.astype(np.float32)).astype(np.float32)
+    idx = np.clip(s[:, None] + np.arange(-1, 3)[None, :], 0, n_src - 1)
+    return idx, _cubic_coeffs_f32(frac)
+
+
+def resize_cubic_f32(img: np.ndarray, dsize_wh) -> np.ndarray:
+    """cv2.resize(img, (w, h), interpolation=cv2.INTER_CUBIC) for float32 images [H,W] / [H,W,C], restated: horizontal pass
+    into float32 rows (taps summed left to right), then the vertical pass; no antialiasing (INTER_CUBIC never has any)."""
+    wd, hd = dsize_wh
+    src = img.astype(np.float32)
+    squeeze = src.ndim == 2
+    if squeeze:
+        src = src[:, :, None]
+    hs, ws = src.shape[:2]
+    xi, xw = _resize_axis_table(ws, wd)
+    yi, yw = _resize_axis_table(hs, hd)
+    rows = np.zeros((hs, wd, src.shape[2]), np.float32)
+    for k in range(4):
+        rows = (rows + src[:, xi[:, k], :] * xw[None, :, k, None]).astype(np.float32) if k else (src[:, xi[:, k], :] * xw[None, :, k, None]).astype(np.float32)
+    out = None
+    for k in range(4):
+        term = (rows[yi[:, k]] * yw[:, k, None, None]).astype(np.float32)
+        out = term if out is None else (out + term).astype(np.float32)
+    return out[:, :, 0] if squeeze else out

@@ -73,6 +73,7 @@ SIGNATURES = {
     'sdof_warp_cubic_f32': (c_int, [_P, _P] + [c_int] * 7 + [c_float, _P, _P]),
     'sdof_warp_bilinear_u8': (c_int, [_P, _P] + [c_int] * 7 + [c_float, _P, _P]),
     'sdof_warp_bilinear_f32': (c_int, [_P, _P] + [c_int] * 7 + [c_float, _P, _P]),
+    'sdof_resize_cubic_f32': (c_int, [_P] + [c_int] * 6 + [_P, _P]),
     'sdof_cubic_table_i16': (c_int, [POINTER(c_int16)]),
     'sdof_ellipse_half_widths': (c_int, [c_int, POINTER(c_int32)]),
     'sdof_confidence_softmax': (c_int, [_P] + [c_int] * 4 + [_P, _P, _P]),

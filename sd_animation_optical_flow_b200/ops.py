@@ -295,6 +295,28 @@ def warp(src: torch.Tensor, flow: torch.Tensor, mode: str = 'cv2_cubic', sign: f
     return out[0] if squeeze_b else out
 
 
+def resize_cubic(src: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """cv2.resize(src, (ow, oh), interpolation=cv2.INTER_CUBIC) of float32 channels-last images [B,H,W,C] / [H,W,C] / [H,W]
+    on the device (W3: the latent resizes of warp_frame_latent, pdcnet_of.py:24,30)."""
+    require_cuda(src, 'src', f32)
+    s = src
+    if s.dim() == 2:
+        s = s[None, :, :, None]
+    elif s.dim() == 3:
+        s = s[None]
+    if s.dim() != 4:
+        raise RuntimeError(f'src must be [B,H,W,C], [H,W,C] or [H,W], got {tuple(src.shape)}')
+    B, H, W, C = s.shape
+    if oh < 1 or ow < 1:
+        raise RuntimeError('resize_cubic: bad output size')
+    out = torch.empty((B, oh, ow, C), dtype=f32, device=s.device)
+    if B:
+        check(load().sdof_resize_cubic_f32(ptr(s), B, H, W, C, oh, ow, ptr(out), stream_ptr(s.device)), 'sdof_resize_cubic_f32')
+    if src.dim() == 2:
+        return out[0, :, :, 0]
+    return out[0] if src.dim() == 3 else out
+
+
 def warp_tile_stats(reset: bool = True):
     """(staged, fallback) tile counts of the tiled u8 cubic warp kernel on the current device since the last reset
     (diagnostic; synchronises the device)."""

@@ -52,24 +52,24 @@ def warp_frame(frame: np.ndarray, flow: np.ndarray, device=None) -> np.ndarray:
 
 
 def warp_frame_latent(latent: torch.Tensor, flow: np.ndarray, device=None) -> torch.Tensor:
-    """latent [1,C,h,w] (CPU or CUDA) -> CPU tensor [1,C,h,w]: cubic-resize to the flow's size,
-    cubic warp (device), cubic-resize back.  The two cv2.resize calls are the reference's own
-    host glue (pdcnet_of.py:24,30) and stay on the host."""
-    import cv2
+    """latent [1,C,h,w] (CPU or CUDA) -> CPU tensor [1,C,h,w] (pdcnet_of.py:19-32): cubic-resize to the flow's size, cubic
+    warp, cubic-resize back -- all three on the device (csrc/resize.cu restates cv2.resize INTER_CUBIC for float images),
+    one H2D of latent + flow and one D2H of the result."""
     dev = _device(device)
-    lat = np.ascontiguousarray(latent.detach().cpu().numpy().squeeze(0).transpose(1, 2, 0))
+    if latent.dim() != 4 or latent.shape[0] != 1:
+        raise RuntimeError(f'latent must be [1,C,h,w], got {tuple(latent.shape)}')
+    lat = latent.detach().to(dev, torch.float32)[0].permute(1, 2, 0).contiguous()       # 'c h w -> h w c'
     lh, lw = lat.shape[:2]
     h, w = flow.shape[:2]
-    big = cv2.resize(lat, (w, h), interpolation=cv2.INTER_CUBIC)
-    if big.ndim == 2:
-        big = big[:, :, None]
-    warped = ops.warp(_h2d(big.astype(np.float32), dev), _h2d(np.asarray(flow, dtype=np.float32), dev),
-                      mode='cv2_cubic', sign=1.0)
-    warped = _d2h(warped)
-    small = cv2.resize(warped, (lw, lh), interpolation=cv2.INTER_CUBIC)
-    if small.ndim == 2:
-        small = small[:, :, None]
-    return torch.from_numpy(np.ascontiguousarray(small.transpose(2, 0, 1)))[None]
+    fl = _h2d(np.asarray(flow, dtype=np.float32), dev)
+    big = ops.resize_cubic(lat, h, w)
+    C = big.shape[2]
+    if C <= 4:
+        warped = ops.warp(big, fl, mode='cv2_cubic', sign=1.0)
+    else:                                   # the warp kernels take up to 4 channels per call (cv2.remap's own limit)
+        warped = torch.cat([ops.warp(big[:, :, c:c + 4].contiguous(), fl, mode='cv2_cubic', sign=1.0) for c in range(0, C, 4)], 2)
+    small = ops.resize_cubic(warped.contiguous(), lh, lw)
+    return small.permute(2, 0, 1)[None].contiguous().cpu()
 
 
 def _load_densematching(ckpt_path: str):

@@ -171,11 +171,37 @@ def test_zero_flow_is_identity_at_config5_size(cuda):
 
 
 def test_warp_frame_latent(cuda):
+    """W3 with no host arithmetic: both cv2.resize(INTER_CUBIC) calls of pdcnet_of.py:19-32 run in csrc/resize.cu.  Against
+    the oracle (which calls cv2.resize itself): 2e-5 abs on unit-variance latents, as for the float warp."""
     from sd_animation_optical_flow_b200 import pdcnet_of
     rs = np.random.RandomState(4)
-    lat = torch.from_numpy(rs.standard_normal((1, 4, 12, 16)).astype(np.float32))
-    flow = (3.0 * rs.standard_normal((96, 128, 2))).astype(np.float32)
-    out = pdcnet_of.warp_frame_latent(lat, flow)
-    ref = wo.warp_frame_latent(lat[0].numpy(), flow)
-    assert out.shape == (1, 4, 12, 16)
-    np.testing.assert_allclose(out[0].numpy(), ref, rtol=0, atol=2e-5)
+    for (lh, lw, C) in ((12, 16, 4), (96, 64, 4), (10, 14, 3)):
+        lat = torch.from_numpy(rs.standard_normal((1, C, lh, lw)).astype(np.float32))
+        flow = (3.0 * rs.standard_normal((8 * lh, 8 * lw, 2))).astype(np.float32)
+        out = pdcnet_of.warp_frame_latent(lat, flow)
+        ref = wo.warp_frame_latent(lat[0].numpy(), flow)
+        assert out.shape == (1, C, lh, lw) and out.device.type == 'cpu' and out.dtype == torch.float32
+        np.testing.assert_allclose(out[0].numpy(), ref, rtol=0, atol=2e-5)
+        assert torch.equal(pdcnet_of.warp_frame_latent(lat.to(cuda), flow), out)       # CUDA latents are taken as they are
+
+
+@pytest.mark.parametrize('case', [(12, 16, 4, 96, 128), (96, 128, 4, 12, 16), (96, 64, 4, 768, 512), (768, 512, 4, 96, 64),
+                                  (17, 23, 3, 50, 41), (50, 41, 1, 17, 23), (33, 20, 6, 100, 7), (5, 7, 2, 5, 7)])
+def test_resize_cubic_f32_vs_cv2_and_oracle(cuda, case):
+    """csrc/resize.cu against the NumPy restatement (same operation order: 1e-6 of the range) and against cv2.resize itself
+    (3e-7 at the integer ratios the reference uses, 3e-6 at arbitrary ratios, see tests/test_oracle_warp.py)."""
+    import cv2
+    from sd_animation_optical_flow_b200 import ops
+    hs, ws, c, hd, wd = case
+    rs = np.random.RandomState(hs + wd)
+    img = (3 * rs.standard_normal((2, hs, ws, c))).astype(np.float32)
+    out = ops.resize_cubic(_t(img, cuda), hd, wd).cpu().numpy()
+    rng = float(np.abs(img).max())
+    integer_ratio = (hd % hs == 0 and wd % ws == 0) or (hs % hd == 0 and ws % wd == 0)
+    for b in range(2):
+        ora = wo.resize_cubic_f32(img[b], (wd, hd))
+        ref = cv2.resize(img[b], (wd, hd), interpolation=cv2.INTER_CUBIC).reshape(hd, wd, c)
+        assert np.abs(out[b] - ora).max() <= 1e-6 * rng
+        assert np.abs(out[b] - ref).max() <= (3e-7 if integer_ratio else 3e-6) * rng
+    one = ops.resize_cubic(_t(img[0, :, :, 0], cuda), hd, wd)
+    assert one.shape == (hd, wd) and torch.equal(one, _t(out[0, :, :, 0], cuda))

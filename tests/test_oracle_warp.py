@@ -65,3 +65,21 @@ def test_zero_flow_is_identity():
     assert np.array_equal(wo.warp_frame_pdcnet(img, flow), img)
     assert np.array_equal(wo.warp_frame_raft(img, flow), img)
     assert np.array_equal(wo.warp_bilinear(img, flow), img)
+
+
+def test_resize_cubic_restatement_matches_cv2():
+    """oracle.resize_cubic_f32 (OpenCV's float INTER_CUBIC resize restated) against cv2.resize itself: 3e-7 of the image range
+    at the integer ratios warp_frame_latent uses (x8 up, /8 down, pdcnet_of.py:24,30), 3e-6 at arbitrary ratios (OpenCV's
+    SIMD / IPP paths fuse and reorder the same float operations)."""
+    import cv2
+    rs = np.random.RandomState(21)
+    for (hs, ws, c, hd, wd, tol) in [(12, 16, 4, 96, 128, 3e-7), (96, 128, 4, 12, 16, 3e-7), (96, 64, 4, 768, 512, 3e-7),
+                                      (768, 512, 4, 96, 64, 3e-7), (90, 160, 4, 720, 1280, 3e-7), (17, 23, 3, 50, 41, 3e-6),
+                                      (50, 41, 1, 17, 23, 3e-6), (5, 7, 2, 5, 7, 0.0), (33, 20, 4, 100, 7, 3e-6)]:
+        img = (3 * rs.standard_normal((hs, ws, c))).astype(np.float32)
+        if c == 1:
+            img = img[:, :, 0]
+        ref = cv2.resize(img, (wd, hd), interpolation=cv2.INTER_CUBIC)
+        got = wo.resize_cubic_f32(img, (wd, hd))
+        assert got.shape == ref.shape and got.dtype == np.float32
+        assert np.abs(got - ref).max() <= tol * np.abs(img).max(), (hs, ws, c, hd, wd)
