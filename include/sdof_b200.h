@@ -309,6 +309,26 @@ int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float b
                           int hx_stride, int hx_off, float* rhx, int rhx_stride, int rhx_off, int B, int h, int w,
                           float* scratch, sdof_stream_t stream);
 
+/* The SepConvGRU of the update block (RAFT/core/update.py:32-60) on tcgen05, one GRU pass = two launches (csrc/conv_tc.cu):
+ * tap-shifted implicit GEMM by TMA (activations NHWC fp16, out-of-image taps zero-filled = the convolution's padding),
+ * fp16 operands / fp32 accumulation in TMEM, gate arithmetic in the epilogue.  `horizontal` = 1: the 1x5 pass
+ * (convz1/convr1/convq1), 0: the 5x1 pass (convz2/convr2/convq2).  All fp16 buffers 128-byte aligned.
+ *   sdof_motion_tail16 : hx16[:, 128:254] = relu(mc + mf + bias)[:, :126], hx16[:, 254:256] = flow: the motion encoder's
+ *                        output convolution (update.py:95-96; mc, mf = its two partial sums [npix,128]) written as the
+ *                        fp16 GRU input [npix, hx16_stride]; channels [0,128) of hx16 hold the hidden state
+ *   sdof_gru_zr_tc     : [z | r | q_x] = conv(hx16[B,h,w,256], w_zr16[384][5][256]); z = sigmoid(. + zrmap[:, :128]) -> z
+ *                        [npix,128] fp32; rh16 = fp16(sigmoid(. + zrmap[:, 128:]) * h) [npix,128]; qx = the r-independent
+ *                        share of convq [npix,128] fp32.  zrmap [npix,256] / qmap [npix,128] = bias + convolution of the
+ *                        iteration-invariant context features (computed once per pair)
+ *   sdof_gru_q_tc      : q = conv(rh16, w_q16[128][5][128]); h = (1 - z) h + z tanh(q + qx + qmap) in place (fp32) and
+ *                        hx16[:, 0:128] = fp16(h)                                                                    */
+int sdof_motion_tail16(const float* mc, const float* mf, const float* bias, const float* flow, int64_t npix, void* hx16, int hx16_stride,
+                       sdof_stream_t stream);
+int sdof_gru_zr_tc(const void* hx16, const void* w_zr16, const float* zrmap, const float* h, int B, int hh, int ww, int horizontal,
+                   float* z, void* rh16, float* qx, sdof_stream_t stream);
+int sdof_gru_q_tc(const void* rh16, const void* w_q16, const float* qmap, const float* qx, const float* z, int B, int hh, int ww,
+                  int horizontal, float* h, void* hx16, int hx16_stride, sdof_stream_t stream);
+
 /* ---------------------------------------------------------------- before the path: key-frame detector
  * frame_generator's edge-change detector (ofgen_pixel_inpaint.py:127-176, 300-312), bit-exact to OpenCV:
  *   sdof_detect_edges   : edges = cv2.dilate(cv2.Canny(V(frame), low, high), ones(k,k)) with V = max(B,G,R) (8-bit HSV

@@ -57,6 +57,9 @@ SIGNATURES = {
     'sdof_relu_scatter': (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, _P]),
     'sdof_gru_rh': (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     'sdof_gru_update': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    'sdof_motion_tail16': (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, _P]),
+    'sdof_gru_zr_tc': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    'sdof_gru_q_tc': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P]),
     'sdof_flow_update': (c_int, [_P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     'sdof_convex_upsample': (c_int, [_P, _P, c_float, _P, c_int, c_int, c_int, _P, _P]),
     'sdof_instnorm_relu_nchw': (c_int, [_P, _P, c_int64, c_int64, c_float, c_int, _P]),

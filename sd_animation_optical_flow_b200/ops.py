@@ -508,6 +508,45 @@ def gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor, hx: torch.Ten
           'sdof_gru_update')
 
 
+f16 = torch.float16
+
+
+def gru_weights16(w: torch.Tensor) -> torch.Tensor:
+    """Conv weight [Cout, Cin, 1, 5] or [Cout, Cin, 5, 1] -> K-major fp16 [Cout, 5*Cin] (k = tap*Cin + c) for the tcgen05 GRU."""
+    co, ci, kh, kw = w.shape
+    if (kh, kw) not in ((1, 5), (5, 1)):
+        raise RuntimeError(f'expected a 1x5 or 5x1 kernel, got {kh}x{kw}')
+    taps = w.reshape(co, ci, 5).permute(0, 2, 1)
+    return taps.reshape(co, 5 * ci).to(f16).contiguous()
+
+
+def motion_tail16(mc: torch.Tensor, mf: torch.Tensor, bias: torch.Tensor, flow: torch.Tensor, hx16: torch.Tensor) -> None:
+    """hx16[..., 128:254] = relu(mc + mf + bias)[..., :126]; hx16[..., 254:256] = flow (fp16 GRU input, csrc/conv_tc.cu)."""
+    npix = flow.numel() // 2
+    check(load().sdof_motion_tail16(ptr(mc), ptr(mf), ptr(bias), ptr(flow), npix, ptr(hx16), hx16.shape[-1], stream_ptr(hx16.device)),
+          'sdof_motion_tail16')
+
+
+def gru_zr_tc(hx16: torch.Tensor, w_zr16: torch.Tensor, zrmap: torch.Tensor, h: torch.Tensor, horizontal: bool, z: torch.Tensor,
+              rh16: torch.Tensor, qx: torch.Tensor) -> None:
+    """z | r | q_x convolution of one SepConvGRU pass on tcgen05 with the gate arithmetic fused (sdof_gru_zr_tc)."""
+    B, hh, ww, C = hx16.shape
+    if C != 256 or hx16.dtype != f16 or tuple(w_zr16.shape) != (384, 5 * 256) or w_zr16.dtype != f16:
+        raise RuntimeError('gru_zr_tc: hx16 must be fp16 [B,h,w,256] and w_zr16 fp16 [384, 1280]')
+    check(load().sdof_gru_zr_tc(ptr(hx16), ptr(w_zr16), ptr(zrmap), ptr(h), B, hh, ww, int(horizontal), ptr(z), ptr(rh16), ptr(qx),
+                                stream_ptr(hx16.device)), 'sdof_gru_zr_tc')
+
+
+def gru_q_tc(rh16: torch.Tensor, w_q16: torch.Tensor, qmap: torch.Tensor, qx: torch.Tensor, z: torch.Tensor, horizontal: bool,
+             h: torch.Tensor, hx16: torch.Tensor) -> None:
+    """q convolution + hidden-state update of one SepConvGRU pass on tcgen05 (sdof_gru_q_tc); h is updated in place."""
+    B, hh, ww, C = rh16.shape
+    if C != 128 or rh16.dtype != f16 or tuple(w_q16.shape) != (128, 5 * 128) or w_q16.dtype != f16:
+        raise RuntimeError('gru_q_tc: rh16 must be fp16 [B,h,w,128] and w_q16 fp16 [128, 640]')
+    check(load().sdof_gru_q_tc(ptr(rh16), ptr(w_q16), ptr(qmap), ptr(qx), ptr(z), B, hh, ww, int(horizontal), ptr(h), ptr(hx16),
+                               hx16.shape[-1], stream_ptr(rh16.device)), 'sdof_gru_q_tc')
+
+
 def flow_update(delta: torch.Tensor | None, coords1: torch.Tensor, flow: torch.Tensor, hx: torch.Tensor | None, hx_off: int,
                 rhx: torch.Tensor | None, rhx_off: int, delta_bias=(0.0, 0.0)) -> None:
     B, h, w, _ = coords1.shape

@@ -145,12 +145,19 @@ class KeyFeatures:
 
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
-                 own_fh2: bool = True, corr_storage: str | None = None):
+                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False):
         """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
         convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical.
         corr_storage: 'fp16' / 'fp32' pyramid storage (default: fp16 with 16-bit correlation operands, else fp32)."""
         self.side_streams, self.own_convf1, self.own_fh2 = side_streams, own_convf1, own_fh2
         self.corr_storage = corr_storage or ('fp16' if corr_precision in ('fp16', 'bf16') else 'fp32')
+        # tc_gru: the SepConvGRU on tcgen05 (csrc/conv_tc.cu: fp16 operands, gate arithmetic in the epilogue) instead of
+        # cuDNN TF32 convolutions + element-wise glue kernels.  Correct and parity-tested, but OFF by default: measured on the
+        # B200 (tools/gru_bench.py, in-graph, 768x512 batch 1) gru_zr_tc 18.4 us vs cuDNN 11.8 + gru_rh 3.2, gru_q_tc 12.1 vs
+        # 6.2 + 3.9, whole step 4.40 vs 3.91 ms; at batch 8 146 vs 82 us.  cuDNN's kernels for these shapes are 2-SM
+        # (cta_group::2) tiles with cluster multicast, which halve the L2 -> SM operand traffic this one-CTA-per-tile kernel
+        # pays in full (26 B/clk/SM through TMA); profiles/README.md has the numbers and what closing the gap needs.
+        self.tc_gru = bool(tc_gru)
         if model.small:
             raise ValueError('FastRaft implements the basic RAFT model (the one the ofgen scripts use)')
         self.model = model
@@ -186,6 +193,9 @@ class FastRaft:
             self.q.append((wq[:, :hd].contiguous(memory_format=CL), bq, cq.padding))
             self.zr_ctx.append((wzr[:, ctx].contiguous(memory_format=CL), bzr, cz.padding))
             self.q_ctx.append((wq[:, ctx].contiguous(memory_format=CL), bq, cq.padding))
+        # K-major fp16 copies of the per-iteration GRU filters for the tcgen05 path
+        self.zr16 = [ops.gru_weights16(w[0]) for w in self.zr]
+        self.q16 = [ops.gru_weights16(w[0]) for w in self.q]
         self.fh1, self.fh2 = _w(fh.conv1), _w(fh.conv2)
         self.convf1_t = e.convf1.weight.detach().permute(2, 3, 1, 0).contiguous()      # [7,7,2,128] for conv7x7_c2_relu
         self.fh2_t = fh.conv2.weight.detach().permute(2, 3, 0, 1).contiguous()         # [3,3,2,256] for flowhead2_update
@@ -270,9 +280,17 @@ class FastRaft:
         else:
             im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
             im2 = (2 * (image2 / 255.0) - 1.0).contiguous() if key is None else None
-        H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128]
-        HX = torch.empty((B, h, w, hd + xc), device=dev)                 # [h | motion | flow]      (update.py:47 minus inp)
-        RH = torch.empty((B, h, w, hd), device=dev)                       # r*h                      (update.py:50)
+        tc = self.tc_gru
+        H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128] (fp32 master copy)
+        if tc:                                                            # tcgen05 GRU: the conv operands exist only in fp16
+            HX16 = torch.empty((B, h, w, hd + xc), device=dev, dtype=torch.float16)   # [h | motion | flow]
+            RH16 = torch.empty((B, h, w, hd), device=dev, dtype=torch.float16)        # r*h
+            Z = torch.empty((B, h, w, hd), device=dev)                    # sigmoid(z)
+            QX = torch.empty((B, h, w, hd), device=dev)                   # r-independent share of q
+            HX = RH = None
+        else:
+            HX = torch.empty((B, h, w, hd + xc), device=dev)             # [h | motion | flow]      (update.py:47 minus inp)
+            RH = torch.empty((B, h, w, hd), device=dev)                   # r*h                      (update.py:50)
         ZRMAP = [torch.empty((B, h, w, 2 * hd), device=dev) for _ in (0, 1)]   # bias + conv(inp) of convz|convr, per GRU pass
         QMAP = [torch.empty((B, h, w, hd), device=dev) for _ in (0, 1)]        # bias + conv(inp) of convq
         MF = torch.empty((B, h, w, 128), device=dev)                      # flow-branch share of the motion-encoder output conv
@@ -289,7 +307,10 @@ class FastRaft:
         with torch.cuda.stream(side):                                     # ---- context encoder branch
             cn = self.cnet(im1).permute(0, 2, 3, 1)
             torch.tanh(cn[..., :hd], out=H)
-            HX[..., :hd] = H
+            if tc:
+                HX16[..., :hd] = H
+            else:
+                HX[..., :hd] = H
             inp = torch.relu(cn[..., hd:]).contiguous()
             for p in (0, 1):                                              # once per pair: the context share of the GRU convolutions
                 ZRMAP[p].copy_(self._conv(inp, self.zr_ctx[p], bias=True))
@@ -319,12 +340,18 @@ class FastRaft:
             c2 = self._conv_relu(self._conv_relu(corr, self.convc1), self.convc2)   # cor (192 channels)
             mc = self._conv(c2, self.conv_cor)                            # 126 (+2 zero) channels, cor share
             main.wait_stream(side)
-            ops.relu_scatter(mc, HX, mo, c_valid=126, bias=self.conv[1], src2=MF)
-            for p in (0, 1):                                              # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
-                zr = self._conv(HX, self.zr[p])                           # [z | r | x-share of q], 3*hd channels
-                ops.gru_rh(zr, H, RH, bias_zr=ZRMAP[p])
-                q = self._conv(RH, self.q[p])                             # r*h share of q
-                ops.gru_update(zr, q, H, HX, bias_zr=ZRMAP[p], bias_q=QMAP[p])
+            if tc:
+                ops.motion_tail16(mc, MF, self.conv[1], flow, HX16)       # relu(conv([cor | flo])) | flow -> fp16 GRU input
+                for p in (0, 1):                                          # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
+                    ops.gru_zr_tc(HX16, self.zr16[p], ZRMAP[p], H, p == 0, Z, RH16, QX)
+                    ops.gru_q_tc(RH16, self.q16[p], QMAP[p], QX, Z, p == 0, H, HX16)
+            else:
+                ops.relu_scatter(mc, HX, mo, c_valid=126, bias=self.conv[1], src2=MF)
+                for p in (0, 1):                                          # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
+                    zr = self._conv(HX, self.zr[p])                       # [z | r | x-share of q], 3*hd channels
+                    ops.gru_rh(zr, H, RH, bias_zr=ZRMAP[p])
+                    q = self._conv(RH, self.q[p])                         # r*h share of q
+                    ops.gru_update(zr, q, H, HX, bias_zr=ZRMAP[p], bias_q=QMAP[p])
             if self.own_fh2:
                 ops.flowhead2_update(self._conv_relu(H, self.fh1), self.fh2_t, self._fh2_bias, coords1, flow, HX, fo, None, 0,
                                      scratch=fh_scratch)

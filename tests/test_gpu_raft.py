@@ -280,3 +280,63 @@ def test_engine_on_a_device_that_is_not_current(cuda):
     w1 = ops.warp(img, r1[0])
     w0 = ops.warp(img.to(cuda), r1[0].to(cuda))
     assert torch.cuda.current_device() == 0 and torch.equal(w0, w1.to(cuda))
+
+
+@pytest.mark.parametrize('shape', [(1, 96, 64), (2, 22, 40), (1, 11, 20), (1, 45, 80)])
+def test_tcgen05_gru_kernels_vs_torch(cuda, shape):
+    """csrc/conv_tc.cu (one SepConvGRU pass = gru_zr_tc + gru_q_tc, tap-shifted implicit GEMM on tcgen05 with the gate
+    arithmetic in the epilogue) against F.conv2d in fp32 on the SAME fp16-rounded operands: what differs is the summation
+    order and the fp16 rounding of r*h / h, so 2e-3 abs on O(1) gates (operand precision = TF32's 11 bits)."""
+    import torch.nn.functional as F
+    from sd_animation_optical_flow_b200 import ops
+    B, h, w = shape
+    g = torch.Generator(device=cuda).manual_seed(h)
+    rnd = lambda *s: torch.randn(s, generator=g, device=cuda)
+    for horizontal in (True, False):
+        ks = (1, 5) if horizontal else (5, 1)
+        pad = (0, 2) if horizontal else (2, 0)
+        w_zr = rnd(384, 256, *ks) * 0.03
+        w_q = rnd(128, 128, *ks) * 0.05
+        H = torch.tanh(rnd(B, h, w, 128))
+        hx16 = torch.cat([H, torch.relu(rnd(B, h, w, 126)), 3 * rnd(B, h, w, 2)], -1).half().contiguous()
+        zrmap, qmap = rnd(B, h, w, 256) * 0.5, rnd(B, h, w, 128) * 0.5
+        # reference in fp32 on the fp16-rounded operands
+        x = hx16.float().permute(0, 3, 1, 2)
+        zrq = F.conv2d(x, w_zr.half().float(), None, padding=pad).permute(0, 2, 3, 1)
+        z_ref = torch.sigmoid(zrq[..., :128] + zrmap[..., :128])
+        rh_ref = (torch.sigmoid(zrq[..., 128:256] + zrmap[..., 128:]) * H).half()
+        qx_ref = zrq[..., 256:]
+        q_ref = F.conv2d(rh_ref.float().permute(0, 3, 1, 2), w_q.half().float(), None, padding=pad).permute(0, 2, 3, 1)
+        h_ref = (1 - z_ref) * H + z_ref * torch.tanh(q_ref + qx_ref + qmap)
+        Z, QX = torch.empty_like(H), torch.empty_like(H)
+        RH16 = torch.empty((B, h, w, 128), dtype=torch.float16, device=cuda)
+        Hc = H.clone()
+        ops.gru_zr_tc(hx16, ops.gru_weights16(w_zr), zrmap, Hc, horizontal, Z, RH16, QX)
+        assert float((Z - z_ref).abs().max()) <= 1e-3
+        assert float((QX - qx_ref).abs().max()) <= 2e-3
+        assert float((RH16.float() - rh_ref.float()).abs().max()) <= 2e-3
+        keep_tail = hx16[..., 128:].clone()
+        ops.gru_q_tc(RH16, ops.gru_weights16(w_q), qmap, QX, Z, horizontal, Hc, hx16)
+        assert float((Hc - h_ref).abs().max()) <= 3e-3
+        assert torch.equal(hx16[..., :128], Hc.half()) and torch.equal(hx16[..., 128:], keep_tail)
+    # motion-encoder tail -> fp16 GRU input
+    mc, mf, bias, flow = rnd(B, h, w, 128), rnd(B, h, w, 128), rnd(128), 5 * rnd(B, h, w, 2)
+    hx = torch.zeros((B, h, w, 256), dtype=torch.float16, device=cuda)
+    ops.motion_tail16(mc, mf, bias, flow, hx)
+    want = torch.cat([torch.relu(mc + mf + bias)[..., :126], flow], -1).half()
+    assert torch.equal(hx[..., 128:], want) and float(hx[..., :128].abs().max()) == 0
+
+
+def test_tcgen05_gru_path_equals_cudnn_gru_path(cuda):
+    """FastRaft with the tensor-core GRU (opt-in, fast_options=dict(tc_gru=True)) against the default forward with cuDNN
+    convolutions (TF32 off in this module) + glue kernels."""
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    f1, f2 = gi.shifted_pair(128, 160, 55)
+    a = torch.from_numpy(f1).to(cuda)[None]
+    b = torch.from_numpy(f2).to(cuda)[None]
+    tc = RaftEngine(checkpoint=None, iters=8, seed=0, flow_head_scale=0.02, device=cuda, use_cuda_graph=False, fast_options=dict(tc_gru=True))
+    ref = RaftEngine(checkpoint=None, iters=8, seed=0, flow_head_scale=0.02, device=cuda, use_cuda_graph=False)
+    assert tc.fast.tc_gru and not ref.fast.tc_gru
+    d = (tc.estimate_flow(a, b) - ref.estimate_flow(a, b)).norm(dim=-1)
+    print(f'tcgen05 GRU vs cuDNN fp32 GRU: EPE mean {float(d.mean()):.2e} max {float(d.max()):.2e}')
+    assert float(d.mean()) <= 2e-3 and float(d.max()) <= 2e-2

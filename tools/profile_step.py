@@ -28,6 +28,20 @@ if mode == 'step':
     ops.warp(sty, eng.estimate_flow(a, b), 'cv2_cubic', -1.0)
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
+elif mode == 'gru':
+    # the tcgen05 GRU kernels at the batch-1 size
+    B, hh, ww = 1, 96, 64
+    rnd = lambda *s: torch.randn(s, generator=g, device=dev)
+    Hs = torch.tanh(rnd(B, hh, ww, 128))
+    hx16 = torch.cat([Hs, torch.relu(rnd(B, hh, ww, 126)), rnd(B, hh, ww, 2)], -1).half().contiguous()
+    zrmap, qmap = rnd(B, hh, ww, 256), rnd(B, hh, ww, 128)
+    Z, QX = torch.empty_like(Hs), torch.empty_like(Hs)
+    RH16 = torch.empty((B, hh, ww, 128), dtype=torch.float16, device=dev)
+    wz, wq = ops.gru_weights16(rnd(384, 256, 1, 5) * 0.03), ops.gru_weights16(rnd(128, 128, 1, 5) * 0.05)
+    for _ in range(3):
+        ops.gru_zr_tc(hx16, wz, zrmap, Hs, True, Z, RH16, QX)
+        ops.gru_q_tc(RH16, wq, qmap, QX, Z, True, Hs, hx16)
+    torch.cuda.synchronize()
 elif mode == 'corr16':
     # the round-2 product path: fp16 operands (auto-ranged), fp16-stored pyramid, lookup reading it
     hh, ww = (90, 160) if prec == 'L' else (96, 64)

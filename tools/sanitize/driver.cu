@@ -256,6 +256,36 @@ static void glue_case(int B, int h, int w) {
   printf("ok RAFT glue B=%d %dx%d\n", B, h, w);
 }
 
+// tcgen05 SepConvGRU kernels (csrc/conv_tc.cu): both passes, a size with partial tiles
+static void gru_tc_case(int B, int h, int w) {
+  const size_t npix = (size_t)B * h * w;
+  std::vector<uint16_t> hz(npix * 256, 0x3400 /* 0.25 in fp16 */);
+  uint16_t* hx16 = dalloc<uint16_t>(npix * 256 + 64);
+  CK(cudaMemcpy(hx16, hz.data(), npix * 256 * 2, cudaMemcpyHostToDevice));
+  std::vector<uint16_t> wz((size_t)384 * 1280, 0x2000), wq((size_t)128 * 640, 0x2000);
+  uint16_t* dwz = dalloc<uint16_t>(wz.size());
+  uint16_t* dwq = dalloc<uint16_t>(wq.size());
+  CK(cudaMemcpy(dwz, wz.data(), wz.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dwq, wq.data(), wq.size() * 2, cudaMemcpyHostToDevice));
+  float* zrmap = dfloats(npix * 256, 0.5f);
+  float* qmap = dfloats(npix * 128, 0.5f);
+  float* hid = dfloats(npix * 128, 0.9f);
+  float* z = dalloc<float>(npix * 128);
+  float* qx = dalloc<float>(npix * 128);
+  uint16_t* rh16 = dalloc<uint16_t>(npix * 128 + 64);
+  float* mc = dfloats(npix * 128, 1.f);
+  float* mf = dfloats(npix * 128, 1.f);
+  float* bias = dfloats(128, 0.1f);
+  float* flow = dfloats(npix * 2, 3.f);
+  SD(sdof_motion_tail16(mc, mf, bias, flow, (int64_t)npix, hx16, 256, nullptr));
+  for (int horizontal = 1; horizontal >= 0; --horizontal) {
+    SD(sdof_gru_zr_tc(hx16, dwz, zrmap, hid, B, h, w, horizontal, z, rh16, qx, nullptr));
+    SD(sdof_gru_q_tc(rh16, dwq, qmap, qx, z, B, h, w, horizontal, hid, hx16, 256, nullptr));
+  }
+  CK(cudaDeviceSynchronize());
+  printf("ok tcgen05 GRU B=%d %dx%d\n", B, h, w);
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
   const bool all = !strcmp(what, "all");
@@ -275,6 +305,10 @@ int main(int argc, char** argv) {
   }
   if (all || !strcmp(what, "mask")) mask_case(1, 90, 124);
   if (all || !strcmp(what, "glue")) glue_case(2, 12, 20);
+  if (all || !strcmp(what, "gru")) {
+    gru_tc_case(1, 24, 64);     // full 32x4 patches
+    gru_tc_case(2, 11, 20);     // partial tiles on both axes, B > 1
+  }
   printf("driver done\n");
   return 0;
 }
