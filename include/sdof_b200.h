@@ -290,6 +290,12 @@ int sdof_instnorm_stats_nhwc(const float* x, int N, int64_t hw, int C, double* s
 int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* residual, float* y, int N, int64_t hw, int C,
                              float eps, int relu, sdof_stream_t stream);
 int sdof_add_relu(const float* a, const float* b, float* y, int64_t n, sdof_stream_t stream);
+/* The same two kernels on fp16 activations (x, y, residual: dense [N, hw, C] halves, 8-byte aligned quads; statistics still
+ * accumulate in fp32 partials / fp64 atomics): the feature encoder can run its cuDNN convolutions in fp16 -- the same 11-bit
+ * operand precision TF32 gives, at half the activation bytes. */
+int sdof_instnorm_stats_nhwc_h(const void* x, int N, int64_t hw, int C, double* stats, sdof_stream_t stream);
+int sdof_instnorm_apply_nhwc_h(const void* x, const double* stats, const void* residual, void* y, int N, int64_t hw, int C,
+                               float eps, int relu, sdof_stream_t stream);
 /* Input side of RAFT_2.calc / RAFT.forward (ofgen.py:72-76, RAFT/core/raft.py:89-90, utils/utils.py:7-19) in one pass:
  * img u8 [B,H,W,3] -> out f32 [B,Hp,Wp,Cout] (NHWC) = 2*(x/255)-1 of the replicate-padded frame; pixel (y,x) of out reads
  * img at (clamp(y-top), clamp(x-left)).  Cout = 3, or 4 with a zero fourth channel (lets cuDNN run the 7x7 stem

@@ -65,6 +65,8 @@ SIGNATURES = {
     'sdof_instnorm_relu_nchw': (c_int, [_P, _P, c_int64, c_int64, c_float, c_int, _P]),
     'sdof_instnorm_stats_nhwc': (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     'sdof_instnorm_apply_nhwc': (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_float, c_int, _P]),
+    'sdof_instnorm_stats_nhwc_h': (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
+    'sdof_instnorm_apply_nhwc_h': (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_float, c_int, _P]),
     'sdof_add_relu': (c_int, [_P, _P, _P, c_int64, _P]),
     'sdof_normalize_pad_u8_nhwc': (c_int, [_P] + [c_int] * 9 + [_P, _P]),
     'sdof_conv7x7_c2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),

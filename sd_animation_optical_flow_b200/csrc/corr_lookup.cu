@@ -65,6 +65,37 @@ __device__ __forceinline__ void blend_window_strided(const float* __restrict__ w
   }
 }
 
+// Compile-time window: the (output index -> window offset) map of a lane is the same for every level, so it is computed once
+// (`BlendMap`) and a level's blend is 4 LDS + 4 FMA + 1 store per output, fully unrolled (the generic loops above spend ~35
+// instructions per output on index arithmetic: 760 instructions per pixel in the round-1 kernel).
+template <int D>
+struct BlendMap {
+  static constexpr int kTrips = (D * D + 31) / 32;
+  int off[kTrips];   // iy * WS + ix of output k = lane + 32 t (window offset of its top-left tap)
+  __device__ __forceinline__ void init(int lane, int WS) {
+#pragma unroll
+    for (int t = 0; t < kTrips; ++t) {
+      const int k = lane + 32 * t;
+      const int ix = k / D, iy = k - ix * D;
+      off[t] = iy * WS + ix;
+    }
+  }
+};
+
+template <int D>
+__device__ __forceinline__ void blend_fast(const float* __restrict__ win, const BlendMap<D>& bm, int WS, float fx, float fy, float scale,
+                                           float* __restrict__ dst, int stride, int lane) {
+  const float w00 = (1.f - fx) * (1.f - fy) * scale, w01 = fx * (1.f - fy) * scale, w10 = (1.f - fx) * fy * scale, w11 = fx * fy * scale;
+#pragma unroll
+  for (int t = 0; t < BlendMap<D>::kTrips; ++t) {
+    const int k = lane + 32 * t;
+    if (k < D * D) {
+      const float* q = win + bm.off[t];
+      dst[k * stride] = q[0] * w00 + q[1] * w01 + q[WS] * w10 + q[WS + 1] * w11;
+    }
+  }
+}
+
 // coalesced write-out of the CTA's [channels][32] stage tile
 __device__ __forceinline__ void flush_stage(const float* __restrict__ stage, int channels, float* __restrict__ out,
                                             int64_t out_chan_stride, int p0, int N1) {
@@ -83,7 +114,8 @@ constexpr int kLookupPxNhwc = 8;
 // as 2r/2+2 aligned 32-bit words (two taps each), half the load instructions and half the sectors of the fp32 form.
 template <int R_T, int L_T, int PX, typename ET>
 __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
-                                                              int N1, int r_rt, float* __restrict__ out, int nhwc) {
+                                                              int N1, int r_rt, float* __restrict__ out) {
+  constexpr bool nhwc = PX != kLookupPx;   // the 8-warp CTA shape is the channels-last form (no stage tile)
   extern __shared__ __align__(16) float smem[];
   constexpr bool kHalf = sizeof(ET) == 2;
   const int r = R_T ? R_T : r_rt;
@@ -155,13 +187,26 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
       }
     }
     __syncwarp();
+    if constexpr (R_T != 0) {
+      BlendMap<2 * R_T + 1> bm;
+      bm.init(lane, WS);
 #pragma unroll
-    for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
-      if (l >= L) break;
-      if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
-        blend_window_strided(win + l * T + xos[l], D, fxs[l], fys[l], out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane, WS, factor);
-      else
-        blend_window(win + l * T + xos[l], D, fxs[l], fys[l], factor, stage + l * DD * kStagePitch + warp, lane, WS);
+      for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
+        if (l >= L) break;
+        if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
+          blend_fast<2 * R_T + 1>(win + l * T + xos[l], bm, WS, fxs[l], fys[l], factor, out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane);
+        else
+          blend_fast<2 * R_T + 1>(win + l * T + xos[l], bm, WS, fxs[l], fys[l], factor, stage + l * DD * kStagePitch + warp, kStagePitch, lane);
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
+        if (l >= L) break;
+        if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
+          blend_window_strided(win + l * T + xos[l], D, fxs[l], fys[l], out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane, WS, factor);
+        else
+          blend_window(win + l * T + xos[l], D, fxs[l], fys[l], factor, stage + l * DD * kStagePitch + warp, lane, WS);
+      }
     }
   }
   if (nhwc) return;
@@ -323,7 +368,7 @@ static int corr_lookup_impl(const char* name, const void* pyramid, int elem_byte
 #define SDOF_LOOKUP_LAUNCH(RT, LT, PX, TT)                                                                                       \
   do {                                                                                                                           \
     SDOF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT, LT, PX, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    corr_lookup_kernel<RT, LT, PX, TT><<<grid, PX * 32, smem, st>>>(lv, coords, N1, radius, out, nhwc);                          \
+    corr_lookup_kernel<RT, LT, PX, TT><<<grid, PX * 32, smem, st>>>(lv, coords, N1, radius, out);                          \
   } while (0)
 #define SDOF_LOOKUP_DISPATCH(RT, LT)                          \
   do {                                                        \

@@ -15,6 +15,7 @@
 // All are HBM/L2-bound element-wise work: float4 vectorised, grid-stride.
 #include "sdof_common.cuh"
 
+#include <cuda_fp16.h>
 namespace sdof {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
@@ -325,54 +326,115 @@ namespace sdof {
 
 constexpr int kInThreads = 256;
 
-__global__ void __launch_bounds__(kInThreads) instnorm_stats_nhwc_kernel(const float4* __restrict__ x, double* __restrict__ stats,
-                                                                        int64_t hw, int C4, int px_per_cta) {
-  __shared__ float4 red_s[kInThreads], red_q[kInThreads];
+// channel quads of an fp32 (float4) or fp16 (uint2 = 4 halves) channels-last tensor
+__device__ __forceinline__ float4 ldq(const float4* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float4 ldq(const uint2* p, int64_t i) {
+  const uint2 v = p[i];
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void stq(float4* p, int64_t i, float4 v) { p[i] = v; }
+__device__ __forceinline__ void stq(uint2* p, int64_t i, float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&a);
+  o.y = *reinterpret_cast<const uint32_t*>(&b);
+  p[i] = o;
+}
+
+// Round 2: the statistics pass was 18-21 us per layer-1 tensor (25-50 MB): four 8/16-byte loads in flight per thread at one
+// CTA-pair per SM leave the memory system idle, and 592 CTAs x 16 threads x 8 fp64 atomics pile ~300 serialised atomics on
+// each of the 256 addresses.  Now: 16-byte loads (8 halves / 4 floats), eight of them in flight per thread, two 512-thread
+// CTAs per SM for the whole tensor (64 KB in flight per SM), and one atomic pair per channel per CTA.
+constexpr int kStThreads = 512;
+template <typename ST> struct StatLoad;
+template <> struct StatLoad<float4> {      // one 16-byte load = 4 channels
+  static constexpr int kCh = 4;
+  static __device__ __forceinline__ void ld(const float4* p, int64_t i, float (&v)[8]) {
+    const float4 a = p[i];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+};
+template <> struct StatLoad<uint2> {       // one 16-byte load = 8 channels (two quads)
+  static constexpr int kCh = 8;
+  static __device__ __forceinline__ void ld(const uint2* p, int64_t i, float (&v)[8]) {
+    const uint4 a = reinterpret_cast<const uint4*>(p)[i];
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&a.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&a.w));
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+  }
+};
+
+template <typename ST>
+__global__ void __launch_bounds__(kStThreads, 2) instnorm_stats_nhwc_kernel(const ST* __restrict__ x, double* __restrict__ stats,
+                                                                        int64_t hw, int C, int px_per_cta) {
+  constexpr int kCh = StatLoad<ST>::kCh;
+  extern __shared__ float st_red[];            // [2][kStThreads][kCh]
   const int n = blockIdx.y;
-  const int npl = kInThreads / C4;          // pixel lanes
-  const int T = npl * C4;                   // active threads (a multiple of C4, so a thread keeps its channel quad)
+  const int G = C / kCh;                        // 16-byte groups per pixel
+  const int npl = kStThreads / G;               // pixel lanes
+  const int T = npl * G;                        // active threads (a multiple of G: a thread keeps its channel group)
   const int64_t p0 = (int64_t)blockIdx.x * px_per_cta;
   const int64_t p1 = p0 + px_per_cta < hw ? p0 + px_per_cta : hw;
-  const float4* xs = x + ((int64_t)n * hw + p0) * C4;
-  const int64_t cnt = (p1 - p0) * C4;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  const ST* xs = x + ((int64_t)n * hw + p0) * (C / 4);   // ST counts channel quads
+  const int64_t cnt = (p1 - p0) * G;
+  float s[kCh], q[kCh];
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) s[k] = q[k] = 0.f;
   if ((int)threadIdx.x < T) {
-    // four independent loads in flight per thread (the serial version ran at 2.4 TB/s, latency-bound)
+    constexpr int kU = 32 / kCh;   // loads in flight per thread: 32 values = 64 (fp16) / 128 (fp32) bytes; two CTAs per SM fit 64 registers
     int64_t i = threadIdx.x;
-    for (; i + 3 * (int64_t)T < cnt; i += 4 * (int64_t)T) {
-      const float4 v0 = xs[i], v1 = xs[i + T], v2 = xs[i + 2 * T], v3 = xs[i + 3 * T];  // default caching: the apply kernel re-reads x from L2
-      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
-      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
-      q.x += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
-      q.y += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
-      q.z += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
-      q.w += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+    for (; i + (kU - 1) * (int64_t)T < cnt; i += kU * (int64_t)T) {
+      float v[kU][8];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) StatLoad<ST>::ld(xs, i + u * (int64_t)T, v[u]);   // default caching: the apply kernel re-reads x from L2
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        float ps = 0.f, pq = 0.f;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          ps += v[u][k];
+          pq += v[u][k] * v[u][k];
+        }
+        s[k] += ps;
+        q[k] += pq;
+      }
     }
     for (; i < cnt; i += T) {
-      const float4 v = xs[i];
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+      float v[8];
+      StatLoad<ST>::ld(xs, i, v);
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        s[k] += v[k];
+        q[k] += v[k] * v[k];
+      }
     }
   }
-  red_s[threadIdx.x] = s;
-  red_q[threadIdx.x] = q;
+  float* rs = st_red + (size_t)threadIdx.x * kCh;
+  float* rq = st_red + (size_t)(kStThreads + threadIdx.x) * kCh;
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    rs[k] = s[k];
+    rq[k] = q[k];
+  }
   __syncthreads();
-  if ((int)threadIdx.x < C4) {
-    for (int l = 1; l < npl; ++l) {
-      const float4 a = red_s[l * C4 + threadIdx.x], b = red_q[l * C4 + threadIdx.x];
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+  // thread c < C sums channel c over the pixel lanes (fp32 partial of this CTA, fp64 across CTAs)
+  for (int c = threadIdx.x; c < C; c += kStThreads) {
+    const int g = c / kCh, k = c - g * kCh;
+    float ts = 0.f, tq = 0.f;
+    for (int l = 0; l < npl; ++l) {
+      ts += st_red[(size_t)(l * G + g) * kCh + k];
+      tq += st_red[(size_t)(kStThreads + l * G + g) * kCh + k];
     }
-    double* o = stats + ((int64_t)n * C4 + threadIdx.x) * 8;   // [c][2] for 4 channels
-    atomicAdd(o + 0, (double)s.x); atomicAdd(o + 1, (double)q.x);
-    atomicAdd(o + 2, (double)s.y); atomicAdd(o + 3, (double)q.y);
-    atomicAdd(o + 4, (double)s.z); atomicAdd(o + 5, (double)q.z);
-    atomicAdd(o + 6, (double)s.w); atomicAdd(o + 7, (double)q.w);
+    double* o = stats + ((int64_t)n * C + c) * 2;
+    atomicAdd(o, (double)ts);
+    atomicAdd(o + 1, (double)tq);
   }
 }
 
-__global__ void __launch_bounds__(kInThreads) instnorm_apply_nhwc_kernel(const float4* __restrict__ x, const double* __restrict__ stats,
-                                                                        const float4* __restrict__ res, float4* __restrict__ y,
+template <typename ST>
+__global__ void __launch_bounds__(kInThreads) instnorm_apply_nhwc_kernel(const ST* __restrict__ x, const double* __restrict__ stats,
+                                                                        const ST* __restrict__ res, ST* __restrict__ y,
                                                                         int64_t hw, int C4, int px_per_cta, float eps, int relu) {
   __shared__ float mean_s[512], rstd_s[512];
   const int n = blockIdx.y;
@@ -397,15 +459,15 @@ __global__ void __launch_bounds__(kInThreads) instnorm_apply_nhwc_kernel(const f
   const int64_t base = ((int64_t)n * hw + p0) * C4;
   const int64_t cnt = (p1 - p0) * C4;
   for (int64_t i = threadIdx.x; i < cnt; i += T) {
-    const float4 v = x[base + i];
+    const float4 v = ldq(x, base + i);
     float4 o;
     o.x = (v.x - m.x) * r.x; o.y = (v.y - m.y) * r.y; o.z = (v.z - m.z) * r.z; o.w = (v.w - m.w) * r.w;
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     if (res) {
-      const float4 a = res[base + i];
+      const float4 a = ldq(res, base + i);
       o.x = fmaxf(a.x + o.x, 0.f); o.y = fmaxf(a.y + o.y, 0.f); o.z = fmaxf(a.z + o.z, 0.f); o.w = fmaxf(a.w + o.w, 0.f);
     }
-    y[base + i] = o;
+    stq(y, base + i, o);
   }
 }
 
@@ -429,21 +491,52 @@ static int instnorm_px_per_cta(int N, int64_t hw) {
 
 extern "C" {
 
+static int instnorm_stats_impl(const void* x, int elem_bytes, int N, int64_t hw, int C, double* stats, sdof_stream_t stream);
+static int instnorm_apply_impl(const void* x, int elem_bytes, const double* stats, const void* residual, void* y, int N, int64_t hw, int C,
+                               float eps, int relu, sdof_stream_t stream);
+
 int sdof_instnorm_stats_nhwc(const float* x, int N, int64_t hw, int C, double* stats, sdof_stream_t stream) {
+  return instnorm_stats_impl(x, 4, N, hw, C, stats, stream);
+}
+int sdof_instnorm_stats_nhwc_h(const void* x, int N, int64_t hw, int C, double* stats, sdof_stream_t stream) {
+  return instnorm_stats_impl(x, 2, N, hw, C, stats, stream);
+}
+int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* residual, float* y, int N, int64_t hw, int C, float eps,
+                             int relu, sdof_stream_t stream) {
+  return instnorm_apply_impl(x, 4, stats, residual, y, N, hw, C, eps, relu, stream);
+}
+int sdof_instnorm_apply_nhwc_h(const void* x, const double* stats, const void* residual, void* y, int N, int64_t hw, int C, float eps,
+                               int relu, sdof_stream_t stream) {
+  return instnorm_apply_impl(x, 2, stats, residual, y, N, hw, C, eps, relu, stream);
+}
+
+static int instnorm_stats_impl(const void* x, int elem_bytes, int N, int64_t hw, int C, double* stats, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(x && stats, "sdof_instnorm_stats_nhwc: NULL pointer");
   SDOF_REQUIRE(N >= 0 && N <= 65535 && hw >= 1 && C >= 4 && C % 4 == 0 && C <= 512, "sdof_instnorm_stats_nhwc: need C %% 4 == 0, 4 <= C <= 512");
   SDOF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sdof_instnorm_stats_nhwc: x must be 16-byte aligned");
   if (N == 0) return SDOF_OK;
-  const int ppc = instnorm_px_per_cta(N, hw);
-  dim3 grid((unsigned)ceil_div64(hw, ppc), N);
-  instnorm_stats_nhwc_kernel<<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), stats, hw, C / 4, ppc);
+  {
+    // the whole tensor over two CTAs per SM (at least 32 pixels each)
+    int64_t want = ceil_div64((int64_t)N * hw, (int64_t)sm_count() * 2);
+    if (want < 32) want = 32;
+    const int sppc = (int)(want > (1 << 20) ? (1 << 20) : want);
+    dim3 sgrid((unsigned)ceil_div64(hw, sppc), N);
+    if (elem_bytes == 2) {
+      SDOF_REQUIRE(C % 8 == 0, "sdof_instnorm_stats_nhwc_h: C must be a multiple of 8");
+      instnorm_stats_nhwc_kernel<uint2><<<sgrid, kStThreads, 2 * kStThreads * 8 * sizeof(float), as_stream(stream)>>>(
+          reinterpret_cast<const uint2*>(x), stats, hw, C, sppc);
+    } else {
+      instnorm_stats_nhwc_kernel<float4><<<sgrid, kStThreads, 2 * kStThreads * 4 * sizeof(float), as_stream(stream)>>>(
+          reinterpret_cast<const float4*>(x), stats, hw, C, sppc);
+    }
+  }
   SDOF_LAUNCH_CHECK("instnorm_stats_nhwc_kernel");
   return SDOF_OK;
 }
 
-int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* residual, float* y, int N, int64_t hw, int C, float eps,
-                             int relu, sdof_stream_t stream) {
+static int instnorm_apply_impl(const void* x, int elem_bytes, const double* stats, const void* residual, void* y, int N, int64_t hw, int C,
+                               float eps, int relu, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(x && stats && y, "sdof_instnorm_apply_nhwc: NULL pointer");
   SDOF_REQUIRE(N >= 0 && N <= 65535 && hw >= 1 && C >= 4 && C % 4 == 0 && C <= 512, "sdof_instnorm_apply_nhwc: need C %% 4 == 0, 4 <= C <= 512");
@@ -452,9 +545,14 @@ int sdof_instnorm_apply_nhwc(const float* x, const double* stats, const float* r
   if (N == 0) return SDOF_OK;
   const int ppc = instnorm_px_per_cta(N, hw);
   dim3 grid((unsigned)ceil_div64(hw, ppc), N);
-  instnorm_apply_nhwc_kernel<<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), stats,
-                                                                        reinterpret_cast<const float4*>(residual),
-                                                                        reinterpret_cast<float4*>(y), hw, C / 4, ppc, eps, relu);
+  if (elem_bytes == 2)
+    instnorm_apply_nhwc_kernel<uint2><<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const uint2*>(x), stats,
+                                                                                 reinterpret_cast<const uint2*>(residual),
+                                                                                 reinterpret_cast<uint2*>(y), hw, C / 4, ppc, eps, relu);
+  else
+    instnorm_apply_nhwc_kernel<float4><<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), stats,
+                                                                                  reinterpret_cast<const float4*>(residual),
+                                                                                  reinterpret_cast<float4*>(y), hw, C / 4, ppc, eps, relu);
   SDOF_LAUNCH_CHECK("instnorm_apply_nhwc_kernel");
   return SDOF_OK;
 }

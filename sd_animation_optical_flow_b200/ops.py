@@ -587,27 +587,36 @@ def _nhwc_dims(x: torch.Tensor):
     return N, C, H * W
 
 
-def require_cuda_cl(t: torch.Tensor, name: str) -> None:
-    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != f32 or t.dim() != 4:
-        raise RuntimeError(f'{name} must be a 4-D fp32 CUDA tensor')
+def require_cuda_cl(t: torch.Tensor, name: str, dtypes=(f32,)) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype not in dtypes or t.dim() != 4:
+        raise RuntimeError(f'{name} must be a 4-D CUDA tensor of dtype {" / ".join(str(d) for d in dtypes)}')
     if not t.is_contiguous(memory_format=torch.channels_last):
         raise RuntimeError(f'{name} must be dense channels_last (NHWC)')
 
 
 def instnorm_nhwc(x: torch.Tensor, stats: torch.Tensor, relu: bool = True, residual: torch.Tensor | None = None,
                   eps: float = 1e-5) -> torch.Tensor:
-    """In-place InstanceNorm2d(no affine) (+ReLU) (+ `relu(residual + .)`) on a channels-last [N,C,H,W] tensor.
+    """In-place InstanceNorm2d(no affine) (+ReLU) (+ `relu(residual + .)`) on a channels-last [N,C,H,W] tensor, fp32 or fp16
+    (statistics always accumulate in fp32 partials / fp64 atomics).
     stats: zeroed fp64 scratch with at least N*C*2 elements (consumed by this call)."""
-    N, C, hw = _nhwc_dims(x)
+    require_cuda_cl(x, 'x', (f32, torch.float16))
+    N, C, H, W = x.shape
+    hw = H * W
     if residual is not None:
-        require_cuda_cl(residual, 'residual')
+        require_cuda_cl(residual, 'residual', (x.dtype,))
         if residual.shape != x.shape:
             raise RuntimeError('residual must have the shape of x')
     if stats.dtype != torch.float64 or not stats.is_cuda or stats.numel() < N * C * 2 or not stats.is_contiguous():
         raise RuntimeError('stats must be a contiguous fp64 CUDA tensor with >= N*C*2 elements')
-    check(load().sdof_instnorm_stats_nhwc(ptr(x), N, hw, C, ptr(stats), stream_ptr(x.device)), 'sdof_instnorm_stats_nhwc')
-    check(load().sdof_instnorm_apply_nhwc(ptr(x), ptr(stats), ptr(residual), ptr(x), N, hw, C, float(eps), int(relu),
-                                          stream_ptr(x.device)), 'sdof_instnorm_apply_nhwc')
+    lib = load()
+    if x.dtype == f32:
+        check(lib.sdof_instnorm_stats_nhwc(ptr(x), N, hw, C, ptr(stats), stream_ptr(x.device)), 'sdof_instnorm_stats_nhwc')
+        check(lib.sdof_instnorm_apply_nhwc(ptr(x), ptr(stats), ptr(residual), ptr(x), N, hw, C, float(eps), int(relu),
+                                           stream_ptr(x.device)), 'sdof_instnorm_apply_nhwc')
+    else:
+        check(lib.sdof_instnorm_stats_nhwc_h(ptr(x), N, hw, C, ptr(stats), stream_ptr(x.device)), 'sdof_instnorm_stats_nhwc_h')
+        check(lib.sdof_instnorm_apply_nhwc_h(ptr(x), ptr(stats), ptr(residual), ptr(x), N, hw, C, float(eps), int(relu),
+                                             stream_ptr(x.device)), 'sdof_instnorm_apply_nhwc_h')
     return x
 
 

@@ -60,8 +60,15 @@ class FastEncoder:
 
     N_NORMS = 15   # stem + 6 units x 2 + 2 downsample projections
 
-    def __init__(self, enc):
+    def __init__(self, enc, dtype: torch.dtype = torch.float32):
+        """dtype=torch.float16 (InstanceNorm encoders only): activations and filters in fp16, cuDNN tensor-core convolutions
+        with fp32 accumulation, normalisation statistics in fp32/fp64.  fp16 keeps the 11 significant bits TF32 keeps of an
+        fp32 operand, so the arithmetic is TF32-equivalent at half the activation bytes (every activation is normalised,
+        i.e. O(1..100): no range issue); the result is returned in fp32."""
+        self.dtype = dtype
         self.kind = enc.norm_fn
+        if dtype != torch.float32 and self.kind != 'instance':
+            raise ValueError('the fp16 encoder path exists for the InstanceNorm feature encoder only')
         if self.kind not in ('instance', 'batch', 'none'):
             raise ValueError(f'unsupported norm {self.kind}')
         self.stem = self._layer(enc.conv1, enc.norm1)
@@ -74,8 +81,13 @@ class FastEncoder:
             for u in layer:
                 ds = self._layer(u.downsample[0], u.downsample[1]) if u.downsample is not None else None
                 self.units.append((self._layer(u.conv1, u.norm1), self._layer(u.conv2, u.norm2), ds))
-        self.out = (enc.conv2.weight.detach().contiguous(memory_format=CL), enc.conv2.bias.detach(), enc.conv2.stride,
+        self.out = (enc.conv2.weight.detach().to(dtype).contiguous(memory_format=CL), enc.conv2.bias.detach().to(dtype), enc.conv2.stride,
                     enc.conv2.padding)
+        self._out_bias32 = enc.conv2.bias.detach().float().view(1, -1, 1, 1)
+        if dtype != torch.float32:
+            cast = lambda l: None if l is None else (l[0].to(dtype).contiguous(memory_format=CL), l[1].to(dtype), l[2], l[3])
+            self.stem = cast(self.stem)
+            self.units = [tuple(cast(l) for l in u) for u in self.units]
         self._fused_ok = None
         self._max_c = max(l[0].shape[0] for l in [self.stem] + [x for u in self.units for x in u if x is not None])
 
@@ -120,7 +132,7 @@ class FastEncoder:
     def __call__(self, x):
         if x.shape[1] == 3:   # callers on the fast path already hand over 4 channels (ops.normalize_pad_u8(.., channels=4))
             x = F.pad(x, (0, 0, 0, 0, 0, 1))
-        x = x.contiguous(memory_format=CL)
+        x = x.to(self.dtype).contiguous(memory_format=CL)
         if self.kind == 'instance':
             # one zeroed fp64 scratch for the statistics of every norm layer of this pass
             self._stats = torch.zeros((self.N_NORMS, x.shape[0] * self._max_c * 2), dtype=torch.float64, device=x.device)
@@ -132,7 +144,12 @@ class FastEncoder:
                 x = self._conv_norm(x, ds, False)
             x = self._conv_norm(y, c2, True, residual=x)
         w, b, stride, pad = self.out
-        return self._cl(F.conv2d(x, w, b, stride=stride, padding=pad))
+        if self.dtype == torch.float32:
+            return self._cl(F.conv2d(x, w, b, stride=stride, padding=pad))
+        # fp16 path: bias-free convolution, then ONE element-wise kernel that adds the fp32 bias and widens to fp32
+        # (a biased fp16 conv + .float() were a bias kernel of 11 us and a copy of 12 us)
+        y = self._cl(F.conv2d(x, w, None, stride=stride, padding=pad))
+        return self._cl(torch.add(y, self._out_bias32))
 
 
 class KeyFeatures:
@@ -145,7 +162,7 @@ class KeyFeatures:
 
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
-                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False):
+                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True):
         """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
         convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical.
         corr_storage: 'fp16' / 'fp32' pyramid storage (default: fp16 with 16-bit correlation operands, else fp32)."""
@@ -205,8 +222,17 @@ class FastRaft:
         self.cdim = model.context_dim
         self._side = {}
         self._fused_relu_ok = None
-        self.fnet = FastEncoder(model.fnet)
+        # fnet_fp16: the feature encoder's activations / cuDNN convolutions in fp16 (TF32-equivalent operand precision, half
+        # the bytes through the InstanceNorm kernels); its output feeds the correlation, whose operands are fp16 anyway.
+        # Only together with cuDNN's TF32 default: with TF32 switched off the caller wants true fp32 convolutions.
+        self.fnet_fp16 = bool(fnet_fp16) and model.fnet.norm_fn == 'instance'
+        self._fnet32 = FastEncoder(model.fnet)
+        self._fnet16 = FastEncoder(model.fnet, torch.float16) if self.fnet_fp16 else None
         self.cnet = FastEncoder(model.cnet)
+
+    def fnet(self, x):
+        use16 = self._fnet16 is not None and torch.backends.cudnn.allow_tf32
+        return (self._fnet16 if use16 else self._fnet32)(x)
 
     # ---- cuDNN convolutions on dense NHWC buffers ---------------------------------------------------
     @staticmethod

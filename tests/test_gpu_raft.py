@@ -340,3 +340,20 @@ def test_tcgen05_gru_path_equals_cudnn_gru_path(cuda):
     d = (tc.estimate_flow(a, b) - ref.estimate_flow(a, b)).norm(dim=-1)
     print(f'tcgen05 GRU vs cuDNN fp32 GRU: EPE mean {float(d.mean()):.2e} max {float(d.max()):.2e}')
     assert float(d.mean()) <= 2e-3 and float(d.max()) <= 2e-2
+
+
+def test_fp16_feature_encoder_matches_fp32_encoder(cuda):
+    """FastEncoder(fnet, fp16) -- fp16 activations / filters, fp32 accumulation, fp32/fp64 normalisation statistics -- against the
+    fp32 encoder on the same weights: 5e-3 of the feature range (15 conv + norm layers of 2^-11 operand rounding each)."""
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    from sd_animation_optical_flow_b200 import ops
+    eng = RaftEngine(checkpoint=None, iters=2, seed=0, device=cuda, use_cuda_graph=False)
+    assert eng.fast._fnet16 is not None
+    f1, _ = gi.shifted_pair(128, 160, 7)
+    im = ops.normalize_pad_u8(torch.from_numpy(f1).to(cuda)[None], (0, 0, 0, 0), channels=4)
+    a = eng.fast._fnet32(im)
+    b = eng.fast._fnet16(im)
+    assert a.dtype == b.dtype == torch.float32 and a.shape == b.shape
+    rel = float((a - b).abs().max() / a.abs().max())
+    print(f'fp16 vs fp32 feature encoder: max rel diff {rel:.2e}')
+    assert rel <= 5e-3
