@@ -49,10 +49,15 @@ namespace sdof {
 // target patch = 128 pixels; shape chosen at launch (patch_x in {32, 16}; SDOF_RES_PATCHX overrides for experiments)
 constexpr int kRM = 128;                   // target pixels per tile (TMEM lanes)
 constexpr int kRN = 256;                   // resident source pixels (accumulator columns)
-constexpr int kRMaxSlabs = 8;              // C <= 8 * 32 = 256 channels resident
-constexpr int kRAStages = 8;               // ring of 8 KB target-patch slabs
-constexpr int kRAStage = kRM * kSlabBytes;  // 8192
-constexpr int kRBSlab = kRN * kSlabBytes;   // 16384
+// K-slab of THIS kernel: 128-byte rows (64 fp16/bf16 channels, SWIZZLE_128B), four UMMA instructions per slab.  Round 1 used
+// 64-byte slabs: eight mbarrier round trips per tile made the single MMA-issuing thread (and the producer thread) the
+// limiter once the fp16-stored epilogue stopped being one (ablation: 1.9 us per tile with loads, MMA and stores skipped).
+constexpr int kRSlabBytes = 128;
+constexpr int kRMmaPerSlab = kRSlabBytes / 32;
+constexpr int kRMaxSlabs = 4;              // C <= 4 * 64 = 256 channels resident
+constexpr int kRAStages = 5;               // ring of 16 KB target-patch slabs (a tile is 4): what fits beside the 128 KB resident block
+constexpr int kRAStage = kRM * kRSlabBytes;  // 16384
+constexpr int kRBSlab = kRN * kRSlabBytes;   // 32768
 constexpr int kRSmemB = kRMaxSlabs * kRBSlab;     // 131072
 constexpr int kRSmemA = kRAStages * kRAStage;     // 65536
 constexpr int kRMaxTilesPerCta = 512;      // tile table in shared memory (8 bytes per tile)
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
                                                                              const __grid_constant__ ResArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_b = base;                // [kslabs][256 rows][64 B]
-  const uint32_t smem_a = base + kRSmemB;      // [kRAStages][128 rows][64 B]
+  const uint32_t smem_b = base;                // [kslabs][256 rows][128 B]
+  const uint32_t smem_a = base + kRSmemB;      // [kRAStages][128 rows][128 B]
   const uint32_t bars = base + kRSmemB + kRSmemA;
   const uint32_t bar_afull = bars;                      // [kRAStages]
   const uint32_t bar_aempty = bars + 8 * kRAStages;     // [kRAStages]
@@ -237,10 +242,10 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
         for (int k = 0; k < args.kslabs; ++k) {
           mbar_wait(bar_afull + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_a + stage * kRAStage);
-          const uint64_t bdesc = make_smem_desc(smem_b + k * kRBSlab);
+          const uint64_t adesc = make_smem_desc_sw128(smem_a + stage * kRAStage);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_b + k * kRBSlab);
 #pragma unroll
-          for (int j = 0; j < kMmaPerSlab; ++j)
+          for (int j = 0; j < kRMmaPerSlab; ++j)
             if (!(args.debug & 4)) tc_mma<true>(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
           tc_commit(bar_aempty + 8 * stage);
           if (++stage == kRAStages) {
@@ -286,7 +291,10 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
       const int y = (ti.ty << (7 - pxs)) + py, x = (ti.tx << pxs) + px;
       const uint32_t ab = it & 1;
 
-      mbar_wait(bar_tfull + 8 * ab, (it >> 1) & 1);
+      // one lane per warp polls the barrier (512 polling threads slow every other mbarrier operation of the CTA down);
+      // tcgen05.fence::after_thread_sync orders the TMEM loads after the warp-level hand-over
+      if (lane == 0) mbar_wait(bar_tfull + 8 * ab, (it >> 1) & 1);
+      __syncwarp();
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * kRN + cq * kColsPerWarp;
       uint32_t ua[32], ub[32];
@@ -651,7 +659,7 @@ int64_t corr_res_workspace_bytes(int B, int n1, int h2, int w2, int C, int level
   return corr_res_src_bytes(B, n1, C) + corr_res_tgt_bytes(B, h2, w2, C, levels);
 }
 
-bool corr_res_supported(int C, int levels) { return C % 8 == 0 && C <= kRMaxSlabs * 32 && levels >= 1 && levels <= 6; }
+bool corr_res_supported(int C, int levels) { return C % 8 == 0 && C <= kRMaxSlabs * (kRSlabBytes / 2) && levels >= 1 && levels <= 6; }
 
 static int check_ops_ptr(const void* p, const char* what) {
   if (p == nullptr) return fail(SDOF_ERR_INVALID, "%s operand buffer is NULL", what);
@@ -757,12 +765,12 @@ int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, i
   if (used_levels == 0) return SDOF_OK;
 
   const CUtensorMapDataType dt = fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const int slab_elems = kSlabBytes / 2;
+  const int slab_elems = kRSlabBytes / 2;
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)n1, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)n1 * C * 2};
     cuuint32_t box[3] = {(cuuint32_t)slab_elems, (cuuint32_t)kRN, 1};
-    if ((rc = encode_map(&maps.src, dt, 3, src16, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, "fmap1 (16-bit)"))) return rc;
+    if ((rc = encode_map(&maps.src, dt, 3, src16, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap1 (16-bit)"))) return rc;
   }
   ra.B = B;
   ra.n1 = n1;
@@ -788,7 +796,7 @@ int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, i
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)lay.w[l], (cuuint64_t)lay.h[l], (cuuint64_t)B2};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)lay.w[l] * C * 2, (cuuint64_t)lay.h[l] * lay.w[l] * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)patch_x, (cuuint32_t)patch_y, 1};
-    if ((rc = encode_map(&maps.tgt[l], dt, 4, tgt16[l], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B, "pooled fmap2 (16-bit)")))
+    if ((rc = encode_map(&maps.tgt[l], dt, 4, tgt16[l], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "pooled fmap2 (16-bit)")))
       return rc;
     const int tyt = ceil_div(lay.h[l], patch_y), txt = ceil_div(lay.w[l], patch_x);
     if (tyt > 0x3fff || txt > 0x3fff) return SDOF_ERR_UNSUPPORTED;

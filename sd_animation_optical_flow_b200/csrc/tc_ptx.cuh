@@ -133,6 +133,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
+// The same for 128-byte rows with SWIZZLE_128B (8-row atoms 1024 B apart); K advances 32 bytes (+2) per UMMA inside a row.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
 // UMMA instruction descriptor (kind::tf32 / kind::f16): fp32 accumulate, K-major A and B.
 // fmt: 0 = F16, 1 = BF16 (kind::f16); 2 = TF32 (kind::tf32).
 __host__ __device__ constexpr uint32_t make_idesc_fmt(uint32_t fmt, uint32_t M, uint32_t N) {

@@ -75,7 +75,7 @@ else:
     fl = torch.empty((1, 96, 64, 2), device=dev)
     mask = (torch.rand((32, 768, 512), generator=g, device=dev) < 0.3).to(torch.uint8) * 255
     for _ in range(3):
-        pyr = ops.corr_volume_pyramid(f1, f2, 4, prec)
+        pyr = ops.corr_volume_pyramid(f1, f2, 4, prec, 'fp16' if prec in ('fp16', 'bf16') else 'fp32')
         ops.corr_lookup(pyr, coords, 4)
         ops.corr_lookup_nhwc(pyr, coords_nhwc, 4, look_nhwc)
         ops.warp(src, flow)
@@ -84,4 +84,5 @@ else:
         ops.conv7x7_c2_relu(lowflow, w7, b7)
         ops.flowhead2_update(x256, w2, (0.1, 0.2), c1, fl, None, 0, None, 0)
         ops.mask_blur_composite(mask, src, src.flip(0), 4.0)
+        ops.instnorm_nhwc(act.half().contiguous(memory_format=torch.channels_last), torch.zeros((2 * 64 * 2,), dtype=torch.float64, device=dev))
     torch.cuda.synchronize()
