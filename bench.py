@@ -465,7 +465,7 @@ def run_ours(args):
         pyr = src_ops.pyramid(tgt_ops, storage)
         # the dominant kernel alone (operands prepared): replayed inside a CUDA graph, as it runs in the step
         t_corr = time_graphed(lambda: src_ops.pyramid(tgt_ops, storage, out=pyr), 20, torch)
-        t_prep = time_graphed(lambda: (ops.CorrSource(fm1, args.corr_precision), ops.CorrTarget(fm2, 4, args.corr_precision)), 20, torch)
+        t_prep = time_graphed(lambda: ops.prepare_pair(fm1, fm2, 4, args.corr_precision), 20, torch)
         corr_kernel = f'corr_pyramid_resident_kernel<{"fp16" if storage == "fp16" else "fp32"}-stored pyramid>'
         lay = pyr.layout
         pooled = sum(lay.h[l] * lay.w[l] for l in range(4))

@@ -114,6 +114,9 @@ int sdof_corr_prepare_src(const float* fmap1, int B, int h1, int w1, int C, int 
                           sdof_stream_t stream);
 int sdof_corr_prepare_tgt(const float* fmap2, int B2, int h2, int w2, int C, int levels, int precision, void* tgt_ops,
                           int64_t tgt_bytes, sdof_stream_t stream);
+/* Both operands of a pair in ONE abs-max launch and ONE conversion launch (instead of two each). */
+int sdof_corr_prepare_both(const float* fmap1, int B, int h1, int w1, void* src_ops, int64_t src_bytes, const float* fmap2, int B2,
+                           int h2, int w2, int levels, void* tgt_ops, int64_t tgt_bytes, int C, int precision, sdof_stream_t stream);
 int sdof_corr_pyramid_from_parts(const void* src_ops, const void* tgt_ops, int B, int h1, int w1, int B2, int h2, int w2, int C,
                                  int levels, int precision, int elem_bytes, void* pyramid, sdof_stream_t stream);
 

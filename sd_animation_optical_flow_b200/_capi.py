@@ -50,6 +50,7 @@ SIGNATURES = {
     'sdof_corr_tgt_operand_bytes': (c_int64, [c_int] * 5),
     'sdof_corr_prepare_src': (c_int, [_P] + [c_int] * 5 + [_P, c_int64, _P]),
     'sdof_corr_prepare_tgt': (c_int, [_P] + [c_int] * 6 + [_P, c_int64, _P]),
+    'sdof_corr_prepare_both': (c_int, [_P, c_int, c_int, c_int, _P, c_int64, _P, c_int, c_int, c_int, c_int, _P, c_int64, c_int, c_int, _P]),
     'sdof_corr_pyramid_from_parts': (c_int, [_P, _P] + [c_int] * 10 + [_P, _P]),
     'sdof_corr_lookup_ex': (c_int, [_P, c_int, _P] + [c_int] * 7 + [_P, c_int, _P]),
     'sdof_corr_lookup': (c_int, [_P, _P] + [c_int] * 7 + [_P, _P]),

@@ -938,6 +938,22 @@ int sdof_corr_prepare_tgt(const float* fmap2, int B2, int h2, int w2, int C, int
   return rc;
 }
 
+int sdof_corr_prepare_both(const float* fmap1, int B, int h1, int w1, void* src_ops, int64_t src_bytes, const float* fmap2, int B2,
+                           int h2, int w2, int levels, void* tgt_ops, int64_t tgt_bytes, int C, int precision, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(fmap1 && fmap2 && src_ops && tgt_ops, "sdof_corr_prepare_both: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && B2 >= 0 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1 && C >= 8 && C % 8 == 0, "sdof_corr_prepare_both: bad sizes");
+  SDOF_REQUIRE(levels >= 1 && levels <= 6, "sdof_corr_prepare_both: levels must be in [1,6], got %d", levels);
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2)) & 15) == 0, "sdof_corr_prepare_both: feature maps must be 16-byte aligned");
+  if (fmt_of(precision) < 0) return fail(SDOF_ERR_UNSUPPORTED, "sdof_corr_prepare_both: precision must be FP16 or BF16");
+  SDOF_REQUIRE(src_bytes >= corr_res_src_bytes(B, h1 * w1, C) && tgt_bytes >= corr_res_tgt_bytes(B2, h2, w2, C, levels),
+               "sdof_corr_prepare_both: operand buffers too small");
+  if (B == 0 || B2 == 0) return SDOF_OK;
+  int rc = launch_corr_prepare_parts(fmap1, B, h1 * w1, src_ops, fmap2, B2, h2, w2, tgt_ops, C, levels, fmt_of(precision), as_stream(stream));
+  if (rc == SDOF_ERR_UNSUPPORTED) return fail(rc, "sdof_corr_prepare_both: shape not supported by the resident kernel (C %% 8 == 0, C <= 256)");
+  return rc;
+}
+
 int sdof_corr_pyramid_from_parts(const void* src_ops, const void* tgt_ops, int B, int h1, int w1, int B2, int h2, int w2, int C,
                                  int levels, int precision, int elem_bytes, void* pyramid, sdof_stream_t stream) {
   using namespace sdof;

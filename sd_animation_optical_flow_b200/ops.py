@@ -68,7 +68,7 @@ class CorrTarget:
     (sdof_corr_prepare_tgt).  In the key-frame scheme fmap2 belongs to the key frame: build it once (batch 1) and hand it to
     every `corr_volume_pyramid(..., target=...)` / `CorrSource.pyramid` call of the pairs that share the key."""
 
-    def __init__(self, fmap2_nhwc: torch.Tensor, levels: int = 4, precision: str = 'fp16'):
+    def __init__(self, fmap2_nhwc: torch.Tensor, levels: int = 4, precision: str = 'fp16', _prepare: bool = True):
         require_cuda(fmap2_nhwc, 'fmap2', f32)
         if precision not in ('fp16', 'bf16'):
             raise ValueError("prepared operands exist only for precision 'fp16' / 'bf16'")
@@ -79,14 +79,15 @@ class CorrTarget:
         lib = load()
         n = int(lib.sdof_corr_tgt_operand_bytes(self.B2, self.h2, self.w2, self.C, levels))
         self.buf = torch.empty(n, dtype=u8, device=fmap2_nhwc.device)
-        check(lib.sdof_corr_prepare_tgt(ptr(fmap2_nhwc), self.B2, self.h2, self.w2, self.C, levels, PRECISIONS[precision],
-                                        ptr(self.buf), n, stream_ptr(self.buf.device)), 'sdof_corr_prepare_tgt')
+        if _prepare:
+            check(lib.sdof_corr_prepare_tgt(ptr(fmap2_nhwc), self.B2, self.h2, self.w2, self.C, levels, PRECISIONS[precision],
+                                            ptr(self.buf), n, stream_ptr(self.buf.device)), 'sdof_corr_prepare_tgt')
 
 
 class CorrSource:
     """Prepared 16-bit SOURCE operand (fmap1, auto-ranged; sdof_corr_prepare_src)."""
 
-    def __init__(self, fmap1_nhwc: torch.Tensor, precision: str = 'fp16'):
+    def __init__(self, fmap1_nhwc: torch.Tensor, precision: str = 'fp16', _prepare: bool = True):
         require_cuda(fmap1_nhwc, 'fmap1', f32)
         if precision not in ('fp16', 'bf16'):
             raise ValueError("prepared operands exist only for precision 'fp16' / 'bf16'")
@@ -97,8 +98,9 @@ class CorrSource:
         lib = load()
         n = int(lib.sdof_corr_src_operand_bytes(self.B, self.h1, self.w1, self.C))
         self.buf = torch.empty(n, dtype=u8, device=fmap1_nhwc.device)
-        check(lib.sdof_corr_prepare_src(ptr(fmap1_nhwc), self.B, self.h1, self.w1, self.C, PRECISIONS[precision], ptr(self.buf), n,
-                                        stream_ptr(self.buf.device)), 'sdof_corr_prepare_src')
+        if _prepare:
+            check(lib.sdof_corr_prepare_src(ptr(fmap1_nhwc), self.B, self.h1, self.w1, self.C, PRECISIONS[precision], ptr(self.buf), n,
+                                            stream_ptr(self.buf.device)), 'sdof_corr_prepare_src')
 
     def pyramid(self, target: CorrTarget, storage: str = 'fp16', out: CorrPyramid | None = None) -> CorrPyramid:
         """The tcgen05 kernel alone on prepared operands; target.B2 must be B or 1 (shared key frame)."""
@@ -110,6 +112,21 @@ class CorrSource:
                                                   target.w2, self.C, target.levels, PRECISIONS[self.precision], out.elem_bytes,
                                                   ptr(out.buf), stream_ptr(self.buf.device)), 'sdof_corr_pyramid_from_parts')
         return out
+
+
+def prepare_pair(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor, levels: int = 4, precision: str = 'fp16'):
+    """(CorrSource, CorrTarget) of one pair (or B pairs, or B sources against one target) prepared by ONE abs-max launch and
+    ONE conversion launch (sdof_corr_prepare_both) instead of two each."""
+    target = CorrTarget(fmap2_nhwc, levels, precision, _prepare=False)
+    source = CorrSource(fmap1_nhwc, precision, _prepare=False)
+    if source.C != target.C:
+        raise RuntimeError('fmap1 and fmap2 disagree on channels')
+    if source.B and target.B2:
+        check(load().sdof_corr_prepare_both(ptr(fmap1_nhwc), source.B, source.h1, source.w1, ptr(source.buf), source.buf.numel(),
+                                            ptr(fmap2_nhwc), target.B2, target.h2, target.w2, levels, ptr(target.buf),
+                                            target.buf.numel(), source.C, PRECISIONS[precision], stream_ptr(fmap1_nhwc.device)),
+              'sdof_corr_prepare_both')
+    return source, target
 
 
 def corr_volume_pyramid(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor | None, levels: int = 4,
@@ -134,7 +151,8 @@ def corr_volume_pyramid(fmap1_nhwc: torch.Tensor, fmap2_nhwc: torch.Tensor | Non
                 raise RuntimeError(f'fmap1 {tuple(fmap1_nhwc.shape)} and fmap2 {tuple(fmap2_nhwc.shape)} disagree on batch/channels')
             if B == 0:
                 return _new_pyramid(B, h1, w1, fmap2_nhwc.shape[1], fmap2_nhwc.shape[2], levels, storage, fmap1_nhwc.device)
-            target = CorrTarget(fmap2_nhwc, levels, precision)
+            source, target = prepare_pair(fmap1_nhwc, fmap2_nhwc, levels, precision)
+            return source.pyramid(target, storage)
         if B == 0:
             return _new_pyramid(B, h1, w1, target.h2, target.w2, target.levels, storage, fmap1_nhwc.device)
         return CorrSource(fmap1_nhwc, precision).pyramid(target, storage)
