@@ -107,6 +107,15 @@ class RaftEngine:
         finally:
             torch.backends.cudnn.benchmark = prev
 
+    def _capture_stream(self):
+        """Capture stream on THIS engine's device.  torch.cuda.graph's default capture stream is a process-wide singleton
+        created on whichever device captured first; reusing it for an engine on another device switches the current device
+        inside the capture and invalidates it."""
+        st = getattr(self, '_cap_stream', None)
+        if st is None or st.device != self.device:
+            st = self._cap_stream = torch.cuda.Stream(device=self.device)
+        return st
+
     def _graph_get(self, key):
         ent = self._graphs.get(key)
         if ent is not None:
@@ -144,7 +153,7 @@ class RaftEngine:
                     self._forward(s1, s2)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._capture_stream()):
                 out = self._forward(s1, s2)
             ent = (g, s1, s2, out)
             self._graph_put(key, ent)
@@ -177,7 +186,7 @@ class RaftEngine:
                     self._forward_u8(s1, s2, pad, bgr)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._capture_stream()):
                 out = self._forward_u8(s1, s2, pad, bgr)
             ent = (g, s1, s2, out)
             self._graph_put(key, ent)
@@ -249,7 +258,7 @@ class RaftEngine:
                             self._forward_keyed(s1, skey, pad, bgr)
                     torch.cuda.current_stream(self.device).wait_stream(side)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=self._capture_stream()):
                         out = self._forward_keyed(s1, skey, pad, bgr)
                     ent = (g, s1, skey, out, [None])
                     self._graph_put(gk, ent)
