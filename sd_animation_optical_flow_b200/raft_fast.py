@@ -27,6 +27,14 @@ from .corr import _to_nhwc
 CL = torch.channels_last
 
 
+def _warn_fallback(who: str, why: str) -> None:
+    """The fused bias + ReLU convolution is checked once against the plain one; falling back is a performance cliff
+    (one more kernel per convolution), so it is never silent."""
+    import warnings
+    warnings.warn(f'sd_animation_optical_flow_b200.{who}: falling back to separate convolution and ReLU kernels: {why}', RuntimeWarning,
+                  stacklevel=3)
+
+
 def _w(conv, pad_out_to: int | None = None):
     w, b = conv.weight.detach(), conv.bias.detach()
     if pad_out_to is not None and w.shape[0] < pad_out_to:
@@ -67,8 +75,6 @@ class FastEncoder:
         i.e. O(1..100): no range issue); the result is returned in fp32."""
         self.dtype = dtype
         self.kind = enc.norm_fn
-        if dtype != torch.float32 and self.kind != 'instance':
-            raise ValueError('the fp16 encoder path exists for the InstanceNorm feature encoder only')
         if self.kind not in ('instance', 'batch', 'none'):
             raise ValueError(f'unsupported norm {self.kind}')
         self.stem = self._layer(enc.conv1, enc.norm1)
@@ -114,11 +120,14 @@ class FastEncoder:
                     y = torch.cudnn_convolution_relu(x, w, b, tuple(stride), tuple(pad), (1, 1), 1)
                     if self._fused_ok is None:
                         ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=pad))
-                        self._fused_ok = bool(torch.allclose(y, ref, atol=1e-3, rtol=1e-3))
+                        tol = 1e-3 if x.dtype == torch.float32 else 2e-2
+                        self._fused_ok = bool(torch.allclose(y, ref, atol=tol, rtol=tol))
                         if not self._fused_ok:
+                            _warn_fallback('FastEncoder', 'cudnn_convolution_relu disagrees with conv2d + relu')
                             y = ref
-                except RuntimeError:
+                except RuntimeError as ex:
                     self._fused_ok = False
+                    _warn_fallback('FastEncoder', f'cudnn_convolution_relu is unavailable ({ex})')
                     y = None
             if y is None:
                 y = F.relu_(F.conv2d(x, w, b, stride=stride, padding=pad))
@@ -126,7 +135,10 @@ class FastEncoder:
             y = F.conv2d(x, w, b, stride=stride, padding=pad)
         y = self._cl(y)
         if residual is not None:
-            ops.add_relu_(y, residual)
+            if y.dtype == torch.float32:
+                ops.add_relu_(y, residual)
+            else:
+                y = torch.relu_(y.add_(residual))
         return y
 
     def __call__(self, x):
@@ -162,7 +174,7 @@ class KeyFeatures:
 
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
-                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True):
+                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True, cnet_fp16: bool = True):
         """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
         convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical.
         corr_storage: 'fp16' / 'fp32' pyramid storage (default: fp16 with 16-bit correlation operands, else fp32)."""
@@ -228,7 +240,14 @@ class FastRaft:
         self.fnet_fp16 = bool(fnet_fp16) and model.fnet.norm_fn == 'instance'
         self._fnet32 = FastEncoder(model.fnet)
         self._fnet16 = FastEncoder(model.fnet, torch.float16) if self.fnet_fp16 else None
-        self.cnet = FastEncoder(model.cnet)
+        # the context encoder the same way (BatchNorm folded into fp16 filters): its output only passes through tanh / relu
+        self.cnet_fp16 = bool(cnet_fp16) and model.cnet.norm_fn == 'batch'
+        self._cnet32 = FastEncoder(model.cnet)
+        self._cnet16 = FastEncoder(model.cnet, torch.float16) if self.cnet_fp16 else None
+
+    def cnet(self, x):
+        use16 = self._cnet16 is not None and torch.backends.cudnn.allow_tf32
+        return (self._cnet16 if use16 else self._cnet32)(x)
 
     def fnet(self, x):
         use16 = self._fnet16 is not None and torch.backends.cudnn.allow_tf32
@@ -255,9 +274,11 @@ class FastRaft:
                     ref = F.relu(F.conv2d(x, w, b, padding=pad))
                     self._fused_relu_ok = bool(torch.allclose(y, ref, atol=1e-3, rtol=1e-3))
                     if not self._fused_relu_ok:
+                        _warn_fallback('FastRaft', 'cudnn_convolution_relu disagrees with conv2d + relu')
                         y = ref
-            except RuntimeError:
+            except RuntimeError as ex:
                 self._fused_relu_ok = False
+                _warn_fallback('FastRaft', f'cudnn_convolution_relu is unavailable ({ex})')
                 y = F.relu_(F.conv2d(x, w, b, padding=pad))
         else:
             y = F.relu_(F.conv2d(x, w, b, padding=pad))
