@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Per-iteration glue of the RAFT update loop on dense channels-last (NHWC) buffers.
 //
 // The reference's update block (RAFT/core/update.py:79-136) runs ~100 small kernels per GRU iteration
@@ -676,11 +677,11 @@ __device__ __forceinline__ float warp_reduce_transpose32(float (&v)[32], int lan
 //                  across the pixels, two transposing butterflies reduce the 36 partials)
 //   gather kernel: delta[p][co] = bias[co] + sum_tap y[p + off(tap)][tap][co] (zero padding), then the
 //                  coords / flow update of RAFT.forward (raft.py:128-131).
-constexpr int kFhPx = 2;                           // pixels per warp
-constexpr int kFhGroups = (kFhPx * 18 + 31) / 32;  // butterflies per warp
 
+template <int kFhPx>   // pixels per warp
 __global__ void __launch_bounds__(256) flowhead2_taps_kernel(const float* __restrict__ x, const float* __restrict__ w2,
                                                              float* __restrict__ y, int64_t npix) {
+  constexpr int kFhGroups = (kFhPx * 18 + 31) / 32;  // butterflies per warp
   __shared__ __align__(16) float ws[18 * 256];
   for (int i = threadIdx.x; i < 18 * 256 / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
   __syncthreads();
@@ -787,9 +788,26 @@ int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float b
                "sdof_flowhead2_update: strides/offsets must be even (float2 stores)");
   const int64_t npix = (int64_t)B * h * w;
   if (npix == 0) return SDOF_OK;
-  const int64_t want = ceil_div64(ceil_div64(npix, kFhPx), 8);
-  const int64_t cap = (int64_t)sm_count() * 2;
-  flowhead2_taps_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(x, w2, scratch, npix);
+  {
+    // one CTA per SM: every CTA first stages the 18 KB of filters, which is the kernel's main fixed cost (in-graph at
+    // 96x64, taps + gather: 1 CTA/SM 8.0 us, 2/SM 9.6, 3/SM 11.2, 6/SM with one pixel per warp 16.7); SDOF_FH_PX / SDOF_FH_CAP
+    // are the experiment switches behind those numbers
+    static int px_mode = -1, cap_mode = 1;
+    if (px_mode < 0) {
+      const char* e = getenv("SDOF_FH_PX");
+      px_mode = e ? atoi(e) : 2;
+      const char* c = getenv("SDOF_FH_CAP");
+      cap_mode = c && atoi(c) > 0 ? atoi(c) : 1;
+    }
+    const int px = px_mode == 1 ? 1 : 2;
+    const int64_t want = ceil_div64(ceil_div64(npix, px), 8);
+    const int64_t cap = (int64_t)sm_count() * cap_mode;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (px == 1)
+      flowhead2_taps_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, w2, scratch, npix);
+    else
+      flowhead2_taps_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, w2, scratch, npix);
+  }
   SDOF_LAUNCH_CHECK("flowhead2_taps_kernel");
   flowhead2_gather_update_kernel<<<grid_for(npix, 256, 8), 256, 0, as_stream(stream)>>>(
       scratch, make_float2(bias_x, bias_y), reinterpret_cast<float2*>(coords1), reinterpret_cast<float2*>(flow), hx, hx_stride, hx_off, rhx,
