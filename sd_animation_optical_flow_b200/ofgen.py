@@ -50,7 +50,15 @@ class namespace:
 
 class RAFT_2:
     """ofgen.py:55-79.  `model_path=None` keeps seeded random-init weights (no checkpoint ships with
-    the reference); otherwise the raft-things checkpoint at `model_path` is loaded."""
+    the reference); otherwise the raft-things checkpoint at `model_path` is loaded (the public files' `module.` key prefix
+    is accepted, like the reference's DataParallel wrapper, ofgen.py:67-68).
+
+    Two deliberate differences from the script's literal arithmetic, both documented in DESIGN.md §2: (1) the model runs in
+    eval mode (BatchNorm running statistics, folded into the convolutions) as upstream RAFT's demo does -- the reference never
+    calls `.eval()`, so its context encoder normalises with batch statistics and mutates its running stats on every call;
+    (2) the all-pairs correlation runs on auto-ranged fp16 operands with fp32 accumulation (11 significant bits like the TF32
+    convolutions around it, per-tensor power-of-two scaling so feature magnitude does not matter) instead of an fp32 SGEMM;
+    pass `corr_precision='3xtf32'` for an fp32-faithful volume."""
 
     def __init__(self, model_path: str | None = 'RAFT/models/raft-things.pth', iters: int = 20, device=None, **engine_kw) -> None:
         ckpt = model_path if (model_path is not None and os.path.exists(model_path)) else None
@@ -235,6 +243,30 @@ class PDCNetAux:
                 ret[i, 0] = self.load_cached(s, target_index)
         self.cached_pair.update(todo)
         return ret
+
+    @torch.no_grad()
+    def calculate_multiple_to_one_device(self, source_frames_rgb: torch.Tensor, target_frame_rgb: torch.Tensor,
+                                         identity: List[bool] | None = None) -> torch.Tensor:
+        """Device-resident form of `calculate_multiple_to_one` for callers that already hold the frames on the GPU: RGB uint8
+        sources [n,H,W,3] and one target [H,W,3] (CUDA) -> flow_mat [n,1,H,W,3] fp32 on the device (flow x, flow y, confidence),
+        the layout `composite_references` / `ops.greedy_composite` consume -- no PNG decode, H2D, D2H or `.npy` file per pair
+        (ofgen_keyframe_inpaint.py:585-625 does all four).  `identity[i]` marks a source that IS the target (flow 0,
+        confidence 1, :621-623).  Pairs run through `calc_batch_device` in chunks of `batch_size`."""
+        n, H, W, _ = source_frames_rgb.shape
+        dev = self.device
+        out = torch.zeros((n, 1, H, W, 3), dtype=torch.float32, device=dev)
+        todo = [i for i in range(n) if not (identity and identity[i])]
+        tgt1 = target_frame_rgb.to(dev)[None]
+        for chunk in chunks(todo, self.batch_size):
+            idx = torch.tensor(chunk, device=dev)
+            src = source_frames_rgb.to(dev).index_select(0, idx).contiguous()
+            flow, conf = self.pdcnet_model.calc_batch_device(src, tgt1.expand(len(chunk), -1, -1, -1).contiguous())
+            out[idx, 0, :, :, 0:2] = flow
+            out[idx, 0, :, :, 2] = conf
+        for i in range(n):
+            if identity and identity[i]:
+                out[i, 0, :, :, 2] = 1.0
+        return out
 
     def calculate_pairwise(self, video, indices) -> np.ndarray:
         """[n, n, H, W, 3] for every ordered pair of `indices`."""

@@ -112,3 +112,28 @@ def test_raft_flow_confidence_adapter_and_clip_path(cuda):
     warped = ops.warp(stylised, flow)
     keep = mask <= 127
     assert torch.equal(out[keep], warped[keep]) and torch.equal(out[~keep], tgt[~keep])
+
+
+def test_pdcnet_aux_device_resident_multiple_to_one(cuda, tmp_path):
+    """PDCNetAux.calculate_multiple_to_one_device == the numpy / `.npy`-cache path of calculate_multiple_to_one on the same
+    frames (ofgen_keyframe_inpaint.py:602-625), without leaving the device."""
+    from sd_animation_optical_flow_b200 import ofgen, pdcnet_of
+    from sd_animation_optical_flow_b200.engine import RaftEngine, RaftFlowConfidence
+    from tests import golden_inputs as gi
+    eng = RaftEngine(checkpoint=None, iters=3, seed=0, flow_head_scale=0.02, device=cuda, use_cuda_graph=False)
+    algo = pdcnet_of.PDCNetPlus(network=RaftFlowConfidence(eng))
+    aux = ofgen.PDCNetAux(algo, str(tmp_path), batch_size=2, device=cuda)
+    canvas = gi.texture(96 + 16, 128 + 16, 5)
+    frames = [np.ascontiguousarray(canvas[2 * i:2 * i + 96, 3 * i:3 * i + 128]) for i in range(4)]     # RGB
+
+    class Video:
+        size_hw = (96, 128)
+
+        def get_raw_frame(self, i):
+            return frames[i][:, :, ::-1]                                                               # BGR like cv2.imread
+
+    ref = aux.calculate_multiple_to_one(Video(), [0, 1, 3], 3)                                        # [3,1,H,W,3] numpy
+    dev_frames = torch.from_numpy(np.stack([frames[0], frames[1], frames[3]])).to(cuda)
+    got = aux.calculate_multiple_to_one_device(dev_frames, torch.from_numpy(frames[3]).to(cuda), identity=[False, False, True])
+    assert got.is_cuda and tuple(got.shape) == ref.shape
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=2e-4)
