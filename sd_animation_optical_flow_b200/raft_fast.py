@@ -183,7 +183,8 @@ class FastRaft:
         # tc_gru: the SepConvGRU on tcgen05 (csrc/conv_tc.cu: fp16 operands, gate arithmetic in the epilogue) instead of
         # cuDNN TF32 convolutions + element-wise glue kernels.  Correct and parity-tested, but OFF by default: measured on the
         # B200 (tools/gru_bench.py, in-graph, 768x512 batch 1) gru_zr_tc 18.4 us vs cuDNN 11.8 + gru_rh 3.2, gru_q_tc 12.1 vs
-        # 6.2 + 3.9, whole step 4.40 vs 3.91 ms; at batch 8 146 vs 82 us.  cuDNN's kernels for these shapes are 2-SM
+        # 6.2 + 3.9, whole step 4.40 vs 3.91 ms (inside the step, warm-cache ncu: 25.6 / 18.7 us vs 13.2 + 5.0 / 9.1 + 5.6);
+        # at batch 8 146 vs 82 us.  cuDNN's kernels for these shapes are 2-SM
         # (cta_group::2) tiles with cluster multicast, which halve the L2 -> SM operand traffic this one-CTA-per-tile kernel
         # pays in full (26 B/clk/SM through TMA); profiles/README.md has the numbers and what closing the gap needs.
         self.tc_gru = bool(tc_gru)

@@ -17,7 +17,8 @@ prec = sys.argv[2] if len(sys.argv) > 2 else 'tf32'
 g = torch.Generator(device=dev).manual_seed(0)
 if mode == 'step':
     cl = len(sys.argv) > 3 and sys.argv[3] == 'cl'
-    eng = RaftEngine(iters=20, device=dev, corr_precision=prec, channels_last=cl)
+    tcg = len(sys.argv) > 3 and sys.argv[3] == 'tcgru'
+    eng = RaftEngine(iters=20, device=dev, corr_precision=prec, channels_last=cl and not tcg, flow_head_scale=0.02, fast_options=dict(tc_gru=tcg))
     a = torch.randint(0, 256, (1, 768, 512, 3), dtype=torch.uint8, device=dev)
     b = a.roll(3, 1)
     sty = torch.randint(0, 256, (1, 768, 512, 3), dtype=torch.uint8, device=dev)
