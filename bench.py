@@ -248,7 +248,7 @@ def run_ours(args):
                      mixed_precision=args.mixed_precision, channels_last=args.channels_last, device=dev, seed=WEIGHT_SEED,
                      flow_head_scale=FLOW_HEAD_SCALE, cudnn_benchmark=not args.no_cudnn_benchmark,
                      fast_options=dict(side_streams=not args.no_side_streams, own_convf1=not args.cudnn_convf1, own_fh2=not args.cudnn_fh2,
-                                       corr_storage=args.corr_storage, tc_gru=args.tc_gru, fnet_fp16=not args.no_fnet_fp16, cnet_fp16=not args.no_cnet_fp16))
+                                       corr_storage=args.corr_storage, tc_gru=args.tc_gru, fnet_fp16=not args.no_fnet_fp16, cnet_fp16=not args.no_cnet_fp16, loop_fp16=not args.no_loop_fp16))
 
     def step():
         flow = eng.estimate_flow(d1, d2)                 # [1,768,512,2]
@@ -598,7 +598,7 @@ def run_ours(args):
                        'H': H, 'W': W, 'iters': ITERS,
                        'weights': f'random-init, name-seeded (seed {WEIGHT_SEED}), flow-head output convolution x{FLOW_HEAD_SCALE} so the flow stays a few px (RAFT_FULL_CASES S_calm)',
                        'corr_precision': args.corr_precision, 'corr_storage': storage,
-                       'conv_precision': 'bf16 autocast' if args.mixed_precision else ('cuDNN tensor cores, fp32 accumulate: TF32 (torch default = what the reference runs on this GPU) for the context encoder and the update block' + ('; fp16 activations / filters (the same 11-bit operand precision) for the feature encoder' if not args.no_fnet_fp16 else '')),
+                       'conv_precision': 'bf16 autocast' if args.mixed_precision else ('cuDNN tensor cores, fp32 accumulate: TF32 (torch default = what the reference runs on this GPU) for what is left in fp32 activations (per-pair context maps)' + ('; fp16 activations / filters (the same 11-bit operand precision, fp32 accumulation) for the encoders and the update block, fp32 hidden-state master copy / coordinates / flow' if not args.no_loop_fp16 else '; fp16 encoders')),
                        'precision_note': 'dtype names the arithmetic of the bulk of the step (TF32 convolutions); the correlation volume uses '
                                          f'auto-ranged {args.corr_precision} operands (11-bit significand like TF32, per-tensor power-of-two scale) with fp32 accumulation and a {storage}-stored pyramid, '
                                          'the thin convolutions and all glue fp32, the warp exact integer (u8)',
@@ -638,6 +638,7 @@ def main():
     ap.add_argument('--tc-gru', action='store_true', help='SepConvGRU on the tcgen05 kernels of csrc/conv_tc.cu instead of cuDNN + glue (A/B switch)')
     ap.add_argument('--no-fnet-fp16', action='store_true', help='feature encoder in TF32 (fp32 activations) instead of fp16 (A/B switch)')
     ap.add_argument('--no-cnet-fp16', action='store_true', help='context encoder in TF32 instead of fp16 (A/B switch)')
+    ap.add_argument('--no-loop-fp16', action='store_true', help='update block in TF32 with fp32 activations instead of fp16 (A/B switch)')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-on-this-GPU leg')
     ap.add_argument('--quick', action='store_true', help='step timing only: skip e2e, roofline, config and CPU legs')
     ap.add_argument('--cpu-budget-s', type=float, default=10.0)

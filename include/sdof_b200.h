@@ -338,6 +338,30 @@ int sdof_gru_zr_tc(const void* hx16, const void* w_zr16, const float* zrmap, con
 int sdof_gru_q_tc(const void* rh16, const void* w_q16, const float* qmap, const float* qx, const float* z, int B, int hh, int ww,
                   int horizontal, float* h, void* hx16, int hx16_stride, sdof_stream_t stream);
 
+/* The update block with fp16 activations (csrc/raft_glue16.cu): the glue kernels above for an update block whose cuDNN
+ * convolutions run in fp16 (tensor-op, fp32 accumulation; 11-bit operands like TF32) -- the twelve convolutions of one
+ * iteration take 93 us instead of 113 us at 768x512 batch 1.  fp16 buffers are dense channels-last, 8-byte aligned; the hidden
+ * state's master copy, coordinates, flow and the per-pair bias maps stay fp32.  hidden = 128 (the basic model).
+ *   sdof_corr_lookup_h       : sdof_corr_lookup_ex (channels-last) with fp16 output rows padded to out_channels (zeros)
+ *   sdof_conv7x7_c2_relu_h   : sdof_conv7x7_c2_relu with fp16 output
+ *   sdof_motion_tail16_h     : sdof_motion_tail16 reading fp16 partial sums
+ *   sdof_gru_rh_h            : rh16 = sigmoid(zr16[:, 128:256] + zrmap[:, 128:256]) * h          (zr16 [npix, zr_channels])
+ *   sdof_gru_update_h        : h = (1-z) h + z tanh(q16 + zr16[:, 256:384] + qmap), z = sigmoid(zr16[:, :128] + zrmap[:, :128]);
+ *                              writes h (fp32, in place), hx16[:, :128] and the dense copy h16 (may be NULL)
+ *   sdof_flowhead2_taps_h    : the tap products of sdof_flowhead2_update from fp16 activations, then
+ *   sdof_flowhead2_gather_update : its 9-neighbour gather + coords / flow update                                        */
+int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels, int radius,
+                       void* out16, int out_channels, sdof_stream_t stream);
+int sdof_conv7x7_c2_relu_h(const float* flow, const float* wT, const float* bias, void* out16, int B, int h, int w, sdof_stream_t stream);
+int sdof_motion_tail16_h(const void* mc16, const void* mf16, const float* bias, const float* flow, int64_t npix, void* hx16, int hx16_stride,
+                         sdof_stream_t stream);
+int sdof_gru_rh_h(const void* zr16, int zr_channels, const float* zrmap, const float* h, void* rh16, int64_t npix, sdof_stream_t stream);
+int sdof_gru_update_h(const void* zr16, const float* zrmap, const void* q16, const float* qmap, float* h, void* hx16, int hx16_stride, void* h16,
+                      int64_t npix, sdof_stream_t stream);
+int sdof_flowhead2_taps_h(const void* x16, const float* w2, int64_t npix, float* scratch, sdof_stream_t stream);
+int sdof_flowhead2_gather_update(const float* scratch, float bias_x, float bias_y, float* coords1, float* flow, float* hx, int hx_stride,
+                                 int hx_off, int B, int h, int w, sdof_stream_t stream);
+
 /* ---------------------------------------------------------------- before the path: key-frame detector
  * frame_generator's edge-change detector (ofgen_pixel_inpaint.py:127-176, 300-312), bit-exact to OpenCV:
  *   sdof_detect_edges   : edges = cv2.dilate(cv2.Canny(V(frame), low, high), ones(k,k)) with V = max(B,G,R) (8-bit HSV

@@ -58,6 +58,13 @@ SIGNATURES = {
     'sdof_relu_scatter': (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, _P]),
     'sdof_gru_rh': (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     'sdof_gru_update': (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    'sdof_corr_lookup_h': (c_int, [_P, c_int, _P] + [c_int] * 7 + [_P, c_int, _P]),
+    'sdof_conv7x7_c2_relu_h': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    'sdof_motion_tail16_h': (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, _P]),
+    'sdof_gru_rh_h': (c_int, [_P, c_int, _P, _P, _P, c_int64, _P]),
+    'sdof_gru_update_h': (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, c_int64, _P]),
+    'sdof_flowhead2_taps_h': (c_int, [_P, _P, c_int64, _P, _P]),
+    'sdof_flowhead2_gather_update': (c_int, [_P, c_float, c_float, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     'sdof_motion_tail16': (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, _P]),
     'sdof_gru_zr_tc': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     'sdof_gru_q_tc': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P]),

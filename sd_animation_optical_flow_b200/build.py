@@ -20,7 +20,7 @@ LIB_DIR = os.path.join(PKG_DIR, 'lib')
 OBJ_DIR = os.path.join(PKG_DIR, 'build')
 LIB_PATH = os.path.join(LIB_DIR, 'libsdof_b200.so')
 
-SOURCES = ['sdof_core.cu', 'warp.cu', 'mask.cu', 'fused.cu', 'corr_simt.cu', 'corr_lookup.cu', 'corr_tc.cu', 'corr_tc_res.cu', 'raft_glue.cu', 'blur.cu', 'keyframe.cu', 'resize.cu', 'conv_tc.cu']
+SOURCES = ['sdof_core.cu', 'warp.cu', 'mask.cu', 'fused.cu', 'corr_simt.cu', 'corr_lookup.cu', 'corr_tc.cu', 'corr_tc_res.cu', 'raft_glue.cu', 'blur.cu', 'keyframe.cu', 'resize.cu', 'conv_tc.cu', 'raft_glue16.cu']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

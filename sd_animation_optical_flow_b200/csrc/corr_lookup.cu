@@ -82,16 +82,19 @@ struct BlendMap {
   }
 };
 
-template <int D>
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__half* p, float v) { *p = __float2half_rn(v); }
+
+template <int D, typename OT>
 __device__ __forceinline__ void blend_fast(const float* __restrict__ win, const BlendMap<D>& bm, int WS, float fx, float fy, float scale,
-                                           float* __restrict__ dst, int stride, int lane) {
+                                           OT* __restrict__ dst, int stride, int lane) {
   const float w00 = (1.f - fx) * (1.f - fy) * scale, w01 = fx * (1.f - fy) * scale, w10 = (1.f - fx) * fy * scale, w11 = fx * fy * scale;
 #pragma unroll
   for (int t = 0; t < BlendMap<D>::kTrips; ++t) {
     const int k = lane + 32 * t;
     if (k < D * D) {
       const float* q = win + bm.off[t];
-      dst[k * stride] = q[0] * w00 + q[1] * w01 + q[WS] * w10 + q[WS + 1] * w11;
+      store_out(dst + k * stride, q[0] * w00 + q[1] * w01 + q[WS] * w10 + q[WS + 1] * w11);
     }
   }
 }
@@ -114,7 +117,8 @@ constexpr int kLookupPxNhwc = 8;
 // as 2r/2+2 aligned 32-bit words (two taps each), half the load instructions and half the sectors of the fp32 form.
 template <int R_T, int L_T, int PX, typename ET>
 __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
-                                                              int N1, int r_rt, float* __restrict__ out) {
+                                                              int N1, int r_rt, float* __restrict__ out, __half* __restrict__ out16 = nullptr,
+                                                              int out16_channels = 0) {
   constexpr bool nhwc = PX != kLookupPx;   // the 8-warp CTA shape is the channels-last form (no stage tile)
   extern __shared__ __align__(16) float smem[];
   constexpr bool kHalf = sizeof(ET) == 2;
@@ -193,11 +197,15 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
 #pragma unroll
       for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
         if (l >= L) break;
-        if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
+        if (nhwc && out16)  // fp16 channels-last output, rows padded to out16_channels (the cuDNN fp16 convc1 needs C % 8 == 0)
+          blend_fast<2 * R_T + 1>(win + l * T + xos[l], bm, WS, fxs[l], fys[l], factor, out16 + ((int64_t)b * N1 + p) * out16_channels + l * DD, 1, lane);
+        else if (nhwc)  // the pixel's channels are contiguous: write them straight out (stride 1 between channels)
           blend_fast<2 * R_T + 1>(win + l * T + xos[l], bm, WS, fxs[l], fys[l], factor, out + ((int64_t)b * N1 + p) * (L * DD) + l * DD, 1, lane);
         else
           blend_fast<2 * R_T + 1>(win + l * T + xos[l], bm, WS, fxs[l], fys[l], factor, stage + l * DD * kStagePitch + warp, kStagePitch, lane);
       }
+      if (nhwc && out16 && lane < out16_channels - L * DD)   // zero the padding channels
+        out16[((int64_t)b * N1 + p) * out16_channels + L * DD + lane] = __float2half_rn(0.f);
     } else {
 #pragma unroll
       for (int l = 0; l < (L_T ? L_T : SDOF_MAX_LEVELS); ++l) {
@@ -401,6 +409,48 @@ int sdof_corr_lookup(const float* pyramid, const float* coords, int B, int h1, i
 int sdof_corr_lookup_nhwc(const float* pyramid, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,
                           int radius, float* out, sdof_stream_t stream) {
   return corr_lookup_impl("sdof_corr_lookup_nhwc", pyramid, 4, coords, B, h1, w1, h2, w2, levels, radius, out, 1, stream);
+}
+
+// fp16 channels-last output for the fp16 update block: out16 [B,h1,w1,out_channels] halves, out_channels >= levels*(2r+1)^2 a
+// multiple of 8 (padding channels are written as zeros); radius 4, 4 levels only (RAFT's configuration).
+int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels, int radius,
+                       void* out16, int out_channels, sdof_stream_t stream) {
+  using namespace sdof;
+  const char* name = "sdof_corr_lookup_h";
+  SDOF_REQUIRE(pyramid && coords && out16, "%s: NULL pointer", name);
+  SDOF_REQUIRE(B >= 0 && B <= 65535 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "%s: bad sizes", name);
+  SDOF_REQUIRE(radius == 4 && levels == 4, "%s: radius 4 / 4 levels only", name);
+  SDOF_REQUIRE(out_channels >= 324 && out_channels <= 356 && out_channels % 8 == 0, "%s: out_channels must be a multiple of 8 in [328, 352]", name);
+  SDOF_REQUIRE(elem_bytes == 4 || elem_bytes == 2, "%s: elem_bytes must be 4 or 2", name);
+  sdof_pyramid_layout lay;
+  const int N1 = h1 * w1;
+  int rc = sdof_corr_pyramid_layout_ex((int64_t)B * N1, h2, w2, levels, elem_bytes, &lay);
+  if (rc) return rc;
+  if (B == 0) return SDOF_OK;
+  LookupLevels lv;
+  lv.levels = levels;
+  lv.header = pyramid;
+  for (int l = 0; l < SDOF_MAX_LEVELS; ++l) {
+    const int ll = l < levels ? l : 0;
+    lv.base[l] = reinterpret_cast<const uint8_t*>(pyramid) + lay.offset[ll] * elem_bytes;
+    lv.pitch[l] = lay.pitch[ll];
+    lv.h[l] = lay.h[ll];
+    lv.w[l] = lay.w[ll];
+    lv.wp[l] = lay.wp[ll];
+  }
+  const int T1 = 10;
+  const int T = (elem_bytes == 2 ? T1 + 2 : T1) * T1;
+  const size_t smem = (size_t)kLookupPxNhwc * levels * T * sizeof(float);
+  dim3 grid(ceil_div(N1, kLookupPxNhwc), B);
+  cudaStream_t st = as_stream(stream);
+  if (elem_bytes == 2)
+    corr_lookup_kernel<4, 4, kLookupPxNhwc, __half><<<grid, kLookupPxNhwc * 32, smem, st>>>(lv, coords, N1, radius, nullptr,
+                                                                                           reinterpret_cast<__half*>(out16), out_channels);
+  else
+    corr_lookup_kernel<4, 4, kLookupPxNhwc, float><<<grid, kLookupPxNhwc * 32, smem, st>>>(lv, coords, N1, radius, nullptr,
+                                                                                          reinterpret_cast<__half*>(out16), out_channels);
+  SDOF_LAUNCH_CHECK("corr_lookup_kernel");
+  return SDOF_OK;
 }
 
 int sdof_corr_lookup_ex(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,

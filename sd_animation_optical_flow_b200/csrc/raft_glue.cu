@@ -816,6 +816,22 @@ int sdof_flowhead2_update(const float* x, const float* w2, float bias_x, float b
   return SDOF_OK;
 }
 
+// The second half of sdof_flowhead2_update alone (the tap products come from sdof_flowhead2_taps_h on fp16 activations).
+int sdof_flowhead2_gather_update(const float* scratch, float bias_x, float bias_y, float* coords1, float* flow, float* hx, int hx_stride,
+                                 int hx_off, int B, int h, int w, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(scratch && coords1 && flow, "sdof_flowhead2_gather_update: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h >= 1 && w >= 1, "sdof_flowhead2_gather_update: bad sizes");
+  SDOF_REQUIRE((hx_stride % 2 == 0) && (hx_off % 2 == 0), "sdof_flowhead2_gather_update: strides/offsets must be even (float2 stores)");
+  const int64_t npix = (int64_t)B * h * w;
+  if (npix == 0) return SDOF_OK;
+  flowhead2_gather_update_kernel<<<grid_for(npix, 256, 8), 256, 0, as_stream(stream)>>>(
+      scratch, make_float2(bias_x, bias_y), reinterpret_cast<float2*>(coords1), reinterpret_cast<float2*>(flow), hx, hx_stride, hx_off, nullptr,
+      0, 0, npix, h, w);
+  SDOF_LAUNCH_CHECK("flowhead2_gather_update_kernel");
+  return SDOF_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------

@@ -565,6 +565,50 @@ def gru_q_tc(rh16: torch.Tensor, w_q16: torch.Tensor, qmap: torch.Tensor, qx: to
                                hx16.shape[-1], stream_ptr(rh16.device)), 'sdof_gru_q_tc')
 
 
+# ---- fp16-activation forms (csrc/raft_glue16.cu) for the update block run with cuDNN fp16 convolutions
+def corr_lookup_nhwc_h(pyr: 'CorrPyramid', coords_nhwc: torch.Tensor, out16: torch.Tensor) -> torch.Tensor:
+    """coords [B,h1,w1,2] -> out16 [B,h1,w1,Cpad] fp16, Cpad >= 324 a multiple of 8 (padding channels zeroed); radius 4, 4 levels."""
+    check(load().sdof_corr_lookup_h(ptr(pyr.buf), pyr.elem_bytes, ptr(coords_nhwc), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2, pyr.levels, 4,
+                                    ptr(out16), out16.shape[-1], stream_ptr(out16.device)), 'sdof_corr_lookup_h')
+    return out16
+
+
+def conv7x7_c2_relu_h(flow_nhwc: torch.Tensor, wT: torch.Tensor, bias: torch.Tensor, out16: torch.Tensor) -> torch.Tensor:
+    B, h, w, _ = flow_nhwc.shape
+    check(load().sdof_conv7x7_c2_relu_h(ptr(flow_nhwc), ptr(wT), ptr(bias), ptr(out16), B, h, w, stream_ptr(out16.device)),
+          'sdof_conv7x7_c2_relu_h')
+    return out16
+
+
+def motion_tail16_h(mc16: torch.Tensor, mf16: torch.Tensor, bias: torch.Tensor, flow: torch.Tensor, hx16: torch.Tensor) -> None:
+    check(load().sdof_motion_tail16_h(ptr(mc16), ptr(mf16), ptr(bias), ptr(flow), flow.numel() // 2, ptr(hx16), hx16.shape[-1],
+                                      stream_ptr(hx16.device)), 'sdof_motion_tail16_h')
+
+
+def gru_rh_h(zr16: torch.Tensor, zrmap: torch.Tensor, h: torch.Tensor, rh16: torch.Tensor) -> None:
+    check(load().sdof_gru_rh_h(ptr(zr16), zr16.shape[-1], ptr(zrmap), ptr(h), ptr(rh16), h.numel() // 128, stream_ptr(h.device)),
+          'sdof_gru_rh_h')
+
+
+def gru_update_h(zr16: torch.Tensor, zrmap: torch.Tensor, q16: torch.Tensor, qmap: torch.Tensor, h: torch.Tensor, hx16: torch.Tensor,
+                 h16: torch.Tensor | None) -> None:
+    if zr16.shape[-1] != 384:
+        raise RuntimeError('gru_update_h: zr16 must carry [z | r | q_x] = 384 channels')
+    check(load().sdof_gru_update_h(ptr(zr16), ptr(zrmap), ptr(q16), ptr(qmap), ptr(h), ptr(hx16), hx16.shape[-1], ptr(h16),
+                                   h.numel() // 128, stream_ptr(h.device)), 'sdof_gru_update_h')
+
+
+def flowhead2_update_h(x16: torch.Tensor, w2: torch.Tensor, bias, coords1: torch.Tensor, flow: torch.Tensor, scratch: torch.Tensor) -> None:
+    """flowhead2_update on fp16 activations x16 [B,h,w,256]: tap products, then the 9-neighbour gather + coords / flow update."""
+    B, h, w, C = x16.shape
+    if C != 256 or x16.dtype != f16:
+        raise RuntimeError('flowhead2_update_h: x16 must be fp16 [B,h,w,256]')
+    lib = load()
+    check(lib.sdof_flowhead2_taps_h(ptr(x16), ptr(w2), B * h * w, ptr(scratch), stream_ptr(x16.device)), 'sdof_flowhead2_taps_h')
+    check(lib.sdof_flowhead2_gather_update(ptr(scratch), float(bias[0]), float(bias[1]), ptr(coords1), ptr(flow), None, 0, 0, B, h, w,
+                                           stream_ptr(x16.device)), 'sdof_flowhead2_gather_update')
+
+
 def flow_update(delta: torch.Tensor | None, coords1: torch.Tensor, flow: torch.Tensor, hx: torch.Tensor | None, hx_off: int,
                 rhx: torch.Tensor | None, rhx_off: int, delta_bias=(0.0, 0.0)) -> None:
     B, h, w, _ = coords1.shape

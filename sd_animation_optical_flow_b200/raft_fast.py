@@ -174,7 +174,7 @@ class KeyFeatures:
 
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
-                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True, cnet_fp16: bool = True):
+                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True, cnet_fp16: bool = True, loop_fp16: bool = True):
         """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
         convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical.
         corr_storage: 'fp16' / 'fp32' pyramid storage (default: fp16 with 16-bit correlation operands, else fp32)."""
@@ -231,6 +231,26 @@ class FastRaft:
         self.fh2_t = fh.conv2.weight.detach().permute(2, 3, 0, 1).contiguous()         # [3,3,2,256] for flowhead2_update
         self._fh2_bias = tuple(float(v) for v in fh.conv2.bias.detach().cpu().tolist())
         self.mask0, self.mask2 = _w(ub.mask[0]), _w(ub.mask[2])
+        # loop_fp16: the update block's cuDNN convolutions in fp16 (tensor-op, fp32 accumulation), activations between them in
+        # fp16 through the glue kernels of csrc/raft_glue16.cu; hidden-state master copy, coordinates, flow and the per-pair
+        # bias maps stay fp32.  Same 11-bit operand precision as the TF32 path, 93 instead of 113 us of convolutions per
+        # iteration at 768x512.  Only under cuDNN's TF32 default (with TF32 off the caller wants fp32 convolutions).
+        self.loop_fp16 = bool(loop_fp16)
+        if self.loop_fp16:
+            h16 = lambda t: t.to(torch.float16)
+            def half_wbp(wbp, pad_in_to=None):
+                w, b, pad = wbp
+                if pad_in_to is not None and w.shape[1] < pad_in_to:
+                    w = torch.cat([w, w.new_zeros((w.shape[0], pad_in_to - w.shape[1], *w.shape[2:]))], 1)
+                return (h16(w).contiguous(memory_format=CL), None if b is None else h16(b), pad)
+            self.corr_ch16 = 328                                           # 324 lookup channels padded to a multiple of 8
+            self.convc1_16 = half_wbp(self.convc1, self.corr_ch16)
+            self.convc2_16, self.convf2_16 = half_wbp(self.convc2), half_wbp(self.convf2)
+            self.conv_cor_16, self.conv_flo_16 = half_wbp(self.conv_cor), half_wbp(self.conv_flo)
+            self.zr_w16 = [half_wbp((w, None, pad)) for (w, _, pad) in self.zr]
+            self.q_w16 = [half_wbp((w, None, pad)) for (w, _, pad) in self.q]
+            self.fh1_16 = half_wbp(self.fh1)
+            self.mask0_16, self.mask2_16 = half_wbp(self.mask0), half_wbp((self.mask2[0], None, self.mask2[2]))
         self.hidden = model.hidden_dim
         self.cdim = model.context_dim
         self._side = {}
@@ -286,6 +306,48 @@ class FastRaft:
         if not y.is_contiguous(memory_format=CL):
             y = y.contiguous(memory_format=CL)
         return y.permute(0, 2, 3, 1)
+
+    def _conv16_relu(self, x16_nhwc: torch.Tensor, wbp) -> torch.Tensor:
+        """fp16 cuDNN convolution + bias + ReLU on a dense NHWC fp16 buffer (fused by cuDNN)."""
+        w, b, pad = wbp
+        y = torch.cudnn_convolution_relu(x16_nhwc.permute(0, 3, 1, 2), w, b, (1, 1), tuple(pad), (1, 1), 1)
+        if not y.is_contiguous(memory_format=CL):
+            y = y.contiguous(memory_format=CL)
+        return y.permute(0, 2, 3, 1)
+
+    @torch.no_grad()
+    def _iterate_fp16(self, iters, B, h, w, dev, main, side, pyr, coords1, flow, H, ZRMAP, QMAP, fh_scratch):
+        """The update loop with fp16 activations (see loop_fp16 in __init__): same schedule as the fp32 loop in forward()."""
+        hd = self.hidden
+        f16 = torch.float16
+        HX16 = torch.empty((B, h, w, hd + 128), device=dev, dtype=f16)    # [h | motion | flow], the GRU input
+        RH16 = torch.empty((B, h, w, hd), device=dev, dtype=f16)          # r*h
+        H16 = torch.empty((B, h, w, hd), device=dev, dtype=f16)           # dense fp16 copy of h for the flow / mask heads
+        MF16 = torch.empty((B, h, w, 128), device=dev, dtype=f16)
+        F1_16 = torch.empty((B, h, w, 128), device=dev, dtype=f16)
+        corr16 = torch.empty((B, h, w, self.corr_ch16), device=dev, dtype=f16)
+        H16.copy_(H)
+        HX16[..., :hd] = H16
+        for _ in range(iters):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):                                 # flow branch (update.py:93-94)
+                ops.conv7x7_c2_relu_h(flow, self.convf1_t, self.convf1[1], F1_16)
+                f2 = self._conv16_relu(F1_16, self.convf2_16)
+                MF16.copy_(self._conv(f2, self.conv_flo_16))
+                del f2
+            ops.corr_lookup_nhwc_h(pyr, coords1, corr16)                  # correlation branch (update.py:91-92)
+            c2 = self._conv16_relu(self._conv16_relu(corr16, self.convc1_16), self.convc2_16)
+            mc = self._conv(c2, self.conv_cor_16)
+            main.wait_stream(side)
+            ops.motion_tail16_h(mc, MF16, self.conv[1], flow, HX16)
+            for p in (0, 1):                                              # SepConvGRU: 1x5 then 5x1 (update.py:45-60)
+                zr = self._conv(HX16, self.zr_w16[p])                     # [z | r | x-share of q] fp16
+                ops.gru_rh_h(zr, ZRMAP[p], H, RH16)
+                q = self._conv(RH16, self.q_w16[p])
+                ops.gru_update_h(zr, ZRMAP[p], q, QMAP[p], H, HX16, H16 if p == 1 else None)
+            ops.flowhead2_update_h(self._conv16_relu(H16, self.fh1_16), self.fh2_t, self._fh2_bias, coords1, flow, fh_scratch)
+        mask = self._conv(self._conv16_relu(H16, self.mask0_16), self.mask2_16).float()
+        return flow, ops.convex_upsample(mask.contiguous(), flow, 0.25, mask_bias=self.mask2[1])
 
     def _side_stream(self, dev):
         st = self._side.get(dev)
@@ -377,6 +439,8 @@ class FastRaft:
         del fmaps
         main.wait_stream(side)
 
+        if self.loop_fp16 and not tc and torch.backends.cudnn.allow_tf32:
+            return self._iterate_fp16(iters, B, h, w, dev, main, side, pyr, coords1, flow, H, ZRMAP, QMAP, fh_scratch)
         for _ in range(iters):
             side.wait_stream(main)
             with torch.cuda.stream(side):                                 # flow branch (update.py:93-94)

@@ -357,3 +357,62 @@ def test_fp16_feature_encoder_matches_fp32_encoder(cuda):
     rel = float((a - b).abs().max() / a.abs().max())
     print(f'fp16 vs fp32 feature encoder: max rel diff {rel:.2e}')
     assert rel <= 5e-3
+
+
+def test_fp16_glue_kernels_vs_fp32_glue(cuda):
+    """csrc/raft_glue16.cu against the fp32 glue kernels on the same (fp16-representable) inputs: results agree to fp16 output
+    rounding (2^-11 relative)."""
+    from sd_animation_optical_flow_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(11)
+    rnd = lambda *s: torch.randn(s, generator=g, device=cuda)
+    B, h, w = 2, 13, 21
+    npix = B * h * w
+    H = torch.tanh(rnd(B, h, w, 128))
+    zr16 = rnd(B, h, w, 384).half()
+    q16 = rnd(B, h, w, 128).half()
+    zrmap, qmap = rnd(B, h, w, 256), rnd(B, h, w, 128)
+    # gru_rh
+    rh32 = torch.empty((B, h, w, 128), device=cuda)
+    ops.gru_rh(zr16.float(), H, rh32, bias_zr=zrmap)
+    rh16 = torch.empty((B, h, w, 128), device=cuda, dtype=torch.float16)
+    ops.gru_rh_h(zr16, zrmap, H, rh16)
+    assert float((rh16.float() - rh32).abs().max()) <= 1e-3
+    # gru_update
+    H32, HX32 = H.clone(), torch.zeros((B, h, w, 256), device=cuda)
+    ops.gru_update(zr16.float(), q16.float(), H32, HX32, bias_zr=zrmap, bias_q=qmap)
+    Hh, HX16, H16 = H.clone(), torch.zeros((B, h, w, 256), device=cuda, dtype=torch.float16), torch.zeros((B, h, w, 128), device=cuda, dtype=torch.float16)
+    ops.gru_update_h(zr16, zrmap, q16, qmap, Hh, HX16, H16)
+    assert float((Hh - H32).abs().max()) <= 1e-5
+    assert torch.equal(HX16[..., :128], Hh.half()) and torch.equal(H16, Hh.half()) and float(HX16[..., 128:].abs().max()) == 0
+    # motion tail
+    mc, mf, bias, flow = rnd(B, h, w, 128).half(), rnd(B, h, w, 128).half(), rnd(128), 5 * rnd(B, h, w, 2)
+    hx = torch.zeros((B, h, w, 256), dtype=torch.float16, device=cuda)
+    ops.motion_tail16_h(mc, mf, bias, flow, hx)
+    want = torch.cat([torch.relu(mc.float() + mf.float() + bias)[..., :126], flow], -1).half()
+    assert torch.equal(hx[..., 128:], want)
+    # conv7x7 -> fp16, flow-head taps from fp16
+    wt = (rnd(7, 7, 2, 128) * 0.1).contiguous()
+    b7 = rnd(128)
+    o32 = ops.conv7x7_c2_relu(flow, wt, b7)
+    o16 = torch.empty((B, h, w, 128), device=cuda, dtype=torch.float16)
+    ops.conv7x7_c2_relu_h(flow, wt, b7, o16)
+    assert torch.equal(o16, o32.half())
+    x16 = torch.relu(rnd(B, h, w, 256)).half()
+    w2 = (rnd(3, 3, 2, 256) * 0.05).contiguous()
+    ys, xs = torch.meshgrid(torch.arange(h, device=cuda), torch.arange(w, device=cuda), indexing='ij')
+    grid = torch.stack([xs, ys], -1).float()[None].repeat(B, 1, 1, 1)
+    c_a, c_b = (grid + 0.5).contiguous(), (grid + 0.5).contiguous()
+    f_a, f_b = torch.empty((B, h, w, 2), device=cuda), torch.empty((B, h, w, 2), device=cuda)
+    ops.flowhead2_update(x16.float(), w2, (0.3, -0.7), c_a, f_a, None, 0, None, 0)
+    ops.flowhead2_update_h(x16, w2, (0.3, -0.7), c_b, f_b, torch.empty((npix * 18,), device=cuda))
+    assert float((c_a - c_b).abs().max()) <= 1e-5 and float((f_a - f_b).abs().max()) <= 1e-5
+    # lookup -> fp16, padded channels
+    from sd_animation_optical_flow_b200.raft import coords_grid
+    f1, f2 = rnd(1, 16, 24, 64), rnd(1, 16, 24, 64)
+    pyr = ops.corr_volume_pyramid(f1, f2, 4, 'fp16', 'fp16')
+    cn = (coords_grid(1, 16, 24, cuda) + 2 * rnd(1, 2, 16, 24)).permute(0, 2, 3, 1).contiguous()
+    l32 = torch.empty((1, 16, 24, 324), device=cuda)
+    ops.corr_lookup_nhwc(pyr, cn, 4, l32)
+    l16 = torch.full((1, 16, 24, 328), 7.0, device=cuda, dtype=torch.float16)
+    ops.corr_lookup_nhwc_h(pyr, cn, l16)
+    assert torch.equal(l16[..., :324], l32.half()) and float(l16[..., 324:].abs().max()) == 0
