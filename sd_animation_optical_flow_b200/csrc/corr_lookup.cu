@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
   const int p0 = blockIdx.x * PX;
   const int p = p0 + warp;
   float* win = win_all + warp * L * T;
+  pdl_wait();      // no-op unless launched with the PDL attribute (sdof_corr_lookup_h: overlaps the tail of the coords update)
+  pdl_trigger();
   // fp16 pyramid: stored values are raw accumulators of the auto-ranged operands; the header holds the factor back to
   // correlation units (sdof_corr_pyramid_layout_ex).  levels share one header, lv.base[0] is 128 bytes behind it.
   const float factor = kHalf ? __ldg(reinterpret_cast<const float*>(lv.header)) : 1.0f;
@@ -444,11 +446,11 @@ int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords,
   dim3 grid(ceil_div(N1, kLookupPxNhwc), B);
   cudaStream_t st = as_stream(stream);
   if (elem_bytes == 2)
-    corr_lookup_kernel<4, 4, kLookupPxNhwc, __half><<<grid, kLookupPxNhwc * 32, smem, st>>>(lv, coords, N1, radius, nullptr,
-                                                                                           reinterpret_cast<__half*>(out16), out_channels);
+    SDOF_CUDA(launch_pdl(corr_lookup_kernel<4, 4, kLookupPxNhwc, __half>, grid, dim3(kLookupPxNhwc * 32), smem, st, lv, coords, N1, radius,
+                         static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
   else
-    corr_lookup_kernel<4, 4, kLookupPxNhwc, float><<<grid, kLookupPxNhwc * 32, smem, st>>>(lv, coords, N1, radius, nullptr,
-                                                                                          reinterpret_cast<__half*>(out16), out_channels);
+    SDOF_CUDA(launch_pdl(corr_lookup_kernel<4, 4, kLookupPxNhwc, float>, grid, dim3(kLookupPxNhwc * 32), smem, st, lv, coords, N1, radius,
+                         static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
   SDOF_LAUNCH_CHECK("corr_lookup_kernel");
   return SDOF_OK;
 }

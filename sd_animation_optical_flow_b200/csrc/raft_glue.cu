@@ -726,6 +726,8 @@ __global__ void __launch_bounds__(256) flowhead2_gather_update_kernel(const floa
                                                                       float2* __restrict__ flow, float* __restrict__ hx, int hx_stride,
                                                                       int hx_off, float* __restrict__ rhx, int rhx_stride, int rhx_off,
                                                                       int64_t npix, int h, int w) {
+  pdl_wait();      // no-op unless launched with the PDL attribute (sdof_flowhead2_gather_update)
+  pdl_trigger();
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
     const int rem = (int)(p % ((int64_t)h * w));
     const int yy = rem / w, xx = rem - yy * w;
@@ -825,9 +827,9 @@ int sdof_flowhead2_gather_update(const float* scratch, float bias_x, float bias_
   SDOF_REQUIRE((hx_stride % 2 == 0) && (hx_off % 2 == 0), "sdof_flowhead2_gather_update: strides/offsets must be even (float2 stores)");
   const int64_t npix = (int64_t)B * h * w;
   if (npix == 0) return SDOF_OK;
-  flowhead2_gather_update_kernel<<<grid_for(npix, 256, 8), 256, 0, as_stream(stream)>>>(
-      scratch, make_float2(bias_x, bias_y), reinterpret_cast<float2*>(coords1), reinterpret_cast<float2*>(flow), hx, hx_stride, hx_off, nullptr,
-      0, 0, npix, h, w);
+  SDOF_CUDA(launch_pdl(flowhead2_gather_update_kernel, dim3(grid_for(npix, 256, 8)), dim3(256), 0, as_stream(stream), scratch,
+                       make_float2(bias_x, bias_y), reinterpret_cast<float2*>(coords1), reinterpret_cast<float2*>(flow), hx, hx_stride, hx_off,
+                       static_cast<float*>(nullptr), 0, 0, npix, h, w));
   SDOF_LAUNCH_CHECK("flowhead2_gather_update_kernel");
   return SDOF_OK;
 }

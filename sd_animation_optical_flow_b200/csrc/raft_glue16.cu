@@ -32,6 +32,8 @@ __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x
 __global__ void __launch_bounds__(256) motion_tail16_h_kernel(const __half* __restrict__ mc, const __half* __restrict__ mf,
                                                               const float4* __restrict__ bias, const float2* __restrict__ flow,
                                                               __half* __restrict__ hx16, int hx16_stride, int64_t npix) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = npix * 32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i >> 5;
@@ -49,6 +51,8 @@ __global__ void __launch_bounds__(256) motion_tail16_h_kernel(const __half* __re
 
 __global__ void __launch_bounds__(256) gru_rh_h_kernel(const __half* __restrict__ zr, int zr_stride, const float4* __restrict__ zrmap,
                                                        const float4* __restrict__ h, __half* __restrict__ rh16, int64_t npix) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = npix * 32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i >> 5;
@@ -62,6 +66,8 @@ __global__ void __launch_bounds__(256) gru_update_h_kernel(const __half* __restr
                                                            const __half* __restrict__ q, const float4* __restrict__ qmap,
                                                            float4* __restrict__ h, __half* __restrict__ hx16, int hx16_stride,
                                                            __half* __restrict__ h16, int64_t npix) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = npix * 32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i >> 5;
@@ -96,6 +102,8 @@ __global__ void __launch_bounds__(kH7Threads) conv7x7_c2_relu_h_kernel(const flo
   const int trem = tile - b * tiles_x * tiles_y;
   const int ty0 = (trem / tiles_x) * kH7Tile, tx0 = (trem % tiles_x) * kH7Tile;
   for (int i = threadIdx.x; i < kH7K * 128 / 4; i += kH7Threads) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wT) + i);
+  pdl_wait();        // the 50 KB of filters above are staged while the kernel that produces `flow` drains
+  pdl_trigger();
   const float2* fb = flow + (int64_t)b * h * w;
   for (int i = threadIdx.x; i < kH7Patch * kH7Patch; i += kH7Threads) {
     const int py = i / kH7Patch, pxx = i - py * kH7Patch;
@@ -167,6 +175,8 @@ __global__ void __launch_bounds__(256) flowhead2_taps_h_kernel(const __half* __r
                                                                int64_t npix) {
   __shared__ __align__(16) float ws[18 * 256];
   for (int i = threadIdx.x; i < 18 * 256 / 4; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
+  pdl_wait();        // filter staging (the kernel's main fixed cost) overlaps the tail of the flow head's first convolution
+  pdl_trigger();
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ngroups = (npix + 1) / 2;
@@ -220,9 +230,9 @@ int sdof_motion_tail16_h(const void* mc16, const void* mf16, const float* bias, 
                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(flow) & 7) == 0,
                "sdof_motion_tail16_h: misaligned pointer");
   if (npix <= 0) return SDOF_OK;
-  motion_tail16_h_kernel<<<grid_for(npix * 32, 256, 8), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(mc16), reinterpret_cast<const __half*>(mf16), reinterpret_cast<const float4*>(bias),
-      reinterpret_cast<const float2*>(flow), reinterpret_cast<__half*>(hx16), hx16_stride, npix);
+  SDOF_CUDA(launch_pdl(motion_tail16_h_kernel, dim3(grid_for(npix * 32, 256, 8)), dim3(256), 0, as_stream(stream),
+                       reinterpret_cast<const __half*>(mc16), reinterpret_cast<const __half*>(mf16), reinterpret_cast<const float4*>(bias),
+                       reinterpret_cast<const float2*>(flow), reinterpret_cast<__half*>(hx16), hx16_stride, npix));
   SDOF_LAUNCH_CHECK("motion_tail16_h_kernel");
   return SDOF_OK;
 }
@@ -234,9 +244,9 @@ int sdof_gru_rh_h(const void* zr16, int zr_channels, const float* zrmap, const f
   SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(zr16) | reinterpret_cast<uintptr_t>(rh16)) & 7) == 0 &&
                    ((reinterpret_cast<uintptr_t>(zrmap) | reinterpret_cast<uintptr_t>(h)) & 15) == 0, "sdof_gru_rh_h: misaligned pointer");
   if (npix <= 0) return SDOF_OK;
-  gru_rh_h_kernel<<<grid_for(npix * 32, 256, 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(zr16), zr_channels,
-                                                                             reinterpret_cast<const float4*>(zrmap),
-                                                                             reinterpret_cast<const float4*>(h), reinterpret_cast<__half*>(rh16), npix);
+  SDOF_CUDA(launch_pdl(gru_rh_h_kernel, dim3(grid_for(npix * 32, 256, 8)), dim3(256), 0, as_stream(stream),
+                       reinterpret_cast<const __half*>(zr16), zr_channels, reinterpret_cast<const float4*>(zrmap),
+                       reinterpret_cast<const float4*>(h), reinterpret_cast<__half*>(rh16), npix));
   SDOF_LAUNCH_CHECK("gru_rh_h_kernel");
   return SDOF_OK;
 }
@@ -251,10 +261,10 @@ int sdof_gru_update_h(const void* zr16, const float* zrmap, const void* q16, con
                    ((reinterpret_cast<uintptr_t>(zrmap) | reinterpret_cast<uintptr_t>(qmap) | reinterpret_cast<uintptr_t>(h)) & 15) == 0,
                "sdof_gru_update_h: misaligned pointer");
   if (npix <= 0) return SDOF_OK;
-  gru_update_h_kernel<<<grid_for(npix * 32, 256, 8), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(zr16), 384, reinterpret_cast<const float4*>(zrmap), reinterpret_cast<const __half*>(q16),
-      reinterpret_cast<const float4*>(qmap), reinterpret_cast<float4*>(h), reinterpret_cast<__half*>(hx16), hx16_stride,
-      reinterpret_cast<__half*>(h16), npix);
+  SDOF_CUDA(launch_pdl(gru_update_h_kernel, dim3(grid_for(npix * 32, 256, 8)), dim3(256), 0, as_stream(stream),
+                       reinterpret_cast<const __half*>(zr16), 384, reinterpret_cast<const float4*>(zrmap), reinterpret_cast<const __half*>(q16),
+                       reinterpret_cast<const float4*>(qmap), reinterpret_cast<float4*>(h), reinterpret_cast<__half*>(hx16), hx16_stride,
+                       reinterpret_cast<__half*>(h16), npix));
   SDOF_LAUNCH_CHECK("gru_update_h_kernel");
   return SDOF_OK;
 }
@@ -276,8 +286,8 @@ int sdof_conv7x7_c2_relu_h(const float* flow, const float* wT, const float* bias
   const int tx = ceil_div(w, kH7Tile), ty = ceil_div(h, kH7Tile);
   const int64_t tiles = (int64_t)tx * ty * B;
   SDOF_REQUIRE(tiles < 0x7fffffffLL, "sdof_conv7x7_c2_relu_h: too many tiles");
-  conv7x7_c2_relu_h_kernel<<<(unsigned)tiles, kH7Threads, kH7Smem, as_stream(stream)>>>(reinterpret_cast<const float2*>(flow), wT, bias,
-                                                                                       reinterpret_cast<__half*>(out16), h, w, tx, ty);
+  SDOF_CUDA(launch_pdl(conv7x7_c2_relu_h_kernel, dim3((unsigned)tiles), dim3(kH7Threads), kH7Smem, as_stream(stream),
+                       reinterpret_cast<const float2*>(flow), wT, bias, reinterpret_cast<__half*>(out16), h, w, tx, ty));
   SDOF_LAUNCH_CHECK("conv7x7_c2_relu_h_kernel");
   return SDOF_OK;
 }
@@ -290,7 +300,8 @@ int sdof_flowhead2_taps_h(const void* x16, const float* w2, int64_t npix, float*
   if (npix <= 0) return SDOF_OK;
   const int64_t want = ceil_div64(ceil_div64(npix, 2), 8);
   const int64_t cap = sm_count();
-  flowhead2_taps_h_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x16), w2, scratch, npix);
+  SDOF_CUDA(launch_pdl(flowhead2_taps_h_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, as_stream(stream),
+                       reinterpret_cast<const __half*>(x16), w2, scratch, npix));
   SDOF_LAUNCH_CHECK("flowhead2_taps_h_kernel");
   return SDOF_OK;
 }

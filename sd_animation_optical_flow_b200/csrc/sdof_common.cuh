@@ -53,6 +53,31 @@ inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
   return (int)(need < cap ? need : cap);
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may be scheduled while its predecessor in the
+// stream (or CUDA-graph chain) is still draining; it must call pdl_wait() before touching anything the predecessor wrote
+// (a no-op when the launch carries no PDL attribute).  Work that does not depend on the predecessor -- staging filters into
+// shared memory, index arithmetic -- goes BEFORE pdl_wait() and overlaps the predecessor's tail.  pdl_trigger() lets the NEXT
+// kernel's launch begin early in the same way.  SDOF_PDL=0 in the environment switches the attribute off (A/B).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // host-side tables (cubic_table.cpp)
 const int16_t* cubic_table_i16_host();  // [1024][16]
 const float* cubic_table_f32_host();    // [1024][16]
