@@ -188,6 +188,10 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  // everything above (barrier init, TMEM allocation, tile table, descriptor prefetch) touched nothing the operand pre-pass
+  // writes: with a programmatic dependent launch it overlapped that kernel's tail
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == kREpiWarps) {
     // ===================================================================== TMA producer
@@ -418,6 +422,8 @@ struct PrepArgs {
 // NaNs are ignored by fmaxf, an infinity switches the scaling off).  blockIdx.y selects the tensor.
 __global__ void __launch_bounds__(256) corr_absmax_kernel(const float4* __restrict__ a, long long na4, float* __restrict__ pa,
                                                           const float4* __restrict__ b, long long nb4, float* __restrict__ pb) {
+  pdl_wait();
+  pdl_trigger();
   const float4* x = blockIdx.y == 0 ? a : b;
   const long long n4 = blockIdx.y == 0 ? na4 : nb4;
   float* part = blockIdx.y == 0 ? pa : pb;
@@ -519,6 +525,8 @@ __device__ __forceinline__ uint2 pack16(float4 v, int fmt) {
 constexpr int kPrepSrcPerThread = 4;   // float4 items per thread in the fmap1 section (independent loads in flight)
 
 __global__ void __launch_bounds__(256, 4) corr_prep16_kernel(const __grid_constant__ PrepArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int C4 = a.C4;
   int blk = blockIdx.x;
   // every CTA derives its tensor's scale from the abs-max partials (128 floats from L2); the first CTA of a tensor's
@@ -716,11 +724,11 @@ int launch_corr_prepare_parts(const float* fmap1, int B, int n1, void* src_ops, 
   const int nb_deep = (int)ceil_div64(deep_items, 256);
   const int nb = pa.nb_src + pa.nb_cells + pa.nb_l2 + nb_deep;
   if (nb == 0) return SDOF_OK;
-  corr_absmax_kernel<<<dim3(kAmaxBlocks, 2), 256, 0, st>>>(reinterpret_cast<const float4*>(fmap1), pa.src_items, pa.src_hdr,
-                                                            reinterpret_cast<const float4*>(fmap2),
-                                                            fmap2 ? (int64_t)B2 * h2 * w2 * (C / 4) : 0, pa.tgt_hdr);
+  SDOF_CUDA(launch_pdl(corr_absmax_kernel, dim3(kAmaxBlocks, 2), dim3(256), 0, st, reinterpret_cast<const float4*>(fmap1),
+                       (long long)pa.src_items, pa.src_hdr, reinterpret_cast<const float4*>(fmap2),
+                       (long long)(fmap2 ? (int64_t)B2 * h2 * w2 * (C / 4) : 0), pa.tgt_hdr));
   SDOF_LAUNCH_CHECK("corr_absmax_kernel");
-  corr_prep16_kernel<<<nb, 256, 0, st>>>(pa);
+  SDOF_CUDA(launch_pdl(corr_prep16_kernel, dim3(nb), dim3(256), 0, st, pa));
   SDOF_LAUNCH_CHECK("corr_prep16_kernel");
   return SDOF_OK;
 }
@@ -818,10 +826,10 @@ int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, i
   if (ceil_div64(total, grid) + 1 > kRMaxTilesPerCta) return SDOF_ERR_UNSUPPORTED;  // tile table would not fit
   if (out_half) {
     SDOF_CUDA(cudaFuncSetAttribute(corr_pyramid_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemTotal));
-    corr_pyramid_resident_kernel<true><<<grid, kRThreads, kRSmemTotal, st>>>(maps, ra);
+    SDOF_CUDA(launch_pdl(corr_pyramid_resident_kernel<true>, dim3(grid), dim3(kRThreads), (size_t)kRSmemTotal, st, maps, ra));
   } else {
     SDOF_CUDA(cudaFuncSetAttribute(corr_pyramid_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemTotal));
-    corr_pyramid_resident_kernel<false><<<grid, kRThreads, kRSmemTotal, st>>>(maps, ra);
+    SDOF_CUDA(launch_pdl(corr_pyramid_resident_kernel<false>, dim3(grid), dim3(kRThreads), (size_t)kRSmemTotal, st, maps, ra));
   }
   SDOF_LAUNCH_CHECK("corr_pyramid_resident_kernel");
   return SDOF_OK;

@@ -371,6 +371,8 @@ __global__ void __launch_bounds__(kStThreads, 2) instnorm_stats_nhwc_kernel(cons
                                                                         int64_t hw, int C, int px_per_cta) {
   constexpr int kCh = StatLoad<ST>::kCh;
   extern __shared__ float st_red[];            // [2][kStThreads][kCh]
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y;
   const int G = C / kCh;                        // 16-byte groups per pixel
   const int npl = kStThreads / G;               // pixel lanes
@@ -438,6 +440,8 @@ __global__ void __launch_bounds__(kInThreads) instnorm_apply_nhwc_kernel(const S
                                                                         const ST* __restrict__ res, ST* __restrict__ y,
                                                                         int64_t hw, int C4, int px_per_cta, float eps, int relu) {
   __shared__ float mean_s[512], rstd_s[512];
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y;
   const int C = C4 * 4;
   for (int c = threadIdx.x; c < C; c += kInThreads) {
@@ -525,11 +529,11 @@ static int instnorm_stats_impl(const void* x, int elem_bytes, int N, int64_t hw,
     dim3 sgrid((unsigned)ceil_div64(hw, sppc), N);
     if (elem_bytes == 2) {
       SDOF_REQUIRE(C % 8 == 0, "sdof_instnorm_stats_nhwc_h: C must be a multiple of 8");
-      instnorm_stats_nhwc_kernel<uint2><<<sgrid, kStThreads, 2 * kStThreads * 8 * sizeof(float), as_stream(stream)>>>(
-          reinterpret_cast<const uint2*>(x), stats, hw, C, sppc);
+      SDOF_CUDA(launch_pdl(instnorm_stats_nhwc_kernel<uint2>, sgrid, dim3(kStThreads), 2 * kStThreads * 8 * sizeof(float), as_stream(stream),
+                           reinterpret_cast<const uint2*>(x), stats, hw, C, sppc));
     } else {
-      instnorm_stats_nhwc_kernel<float4><<<sgrid, kStThreads, 2 * kStThreads * 4 * sizeof(float), as_stream(stream)>>>(
-          reinterpret_cast<const float4*>(x), stats, hw, C, sppc);
+      SDOF_CUDA(launch_pdl(instnorm_stats_nhwc_kernel<float4>, sgrid, dim3(kStThreads), 2 * kStThreads * 4 * sizeof(float), as_stream(stream),
+                           reinterpret_cast<const float4*>(x), stats, hw, C, sppc));
     }
   }
   SDOF_LAUNCH_CHECK("instnorm_stats_nhwc_kernel");
@@ -547,13 +551,11 @@ static int instnorm_apply_impl(const void* x, int elem_bytes, const double* stat
   const int ppc = instnorm_px_per_cta(N, hw);
   dim3 grid((unsigned)ceil_div64(hw, ppc), N);
   if (elem_bytes == 2)
-    instnorm_apply_nhwc_kernel<uint2><<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const uint2*>(x), stats,
-                                                                                 reinterpret_cast<const uint2*>(residual),
-                                                                                 reinterpret_cast<uint2*>(y), hw, C / 4, ppc, eps, relu);
+    SDOF_CUDA(launch_pdl(instnorm_apply_nhwc_kernel<uint2>, grid, dim3(kInThreads), 0, as_stream(stream), reinterpret_cast<const uint2*>(x),
+                         stats, reinterpret_cast<const uint2*>(residual), reinterpret_cast<uint2*>(y), hw, C / 4, ppc, eps, relu));
   else
-    instnorm_apply_nhwc_kernel<float4><<<grid, kInThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), stats,
-                                                                                  reinterpret_cast<const float4*>(residual),
-                                                                                  reinterpret_cast<float4*>(y), hw, C / 4, ppc, eps, relu);
+    SDOF_CUDA(launch_pdl(instnorm_apply_nhwc_kernel<float4>, grid, dim3(kInThreads), 0, as_stream(stream), reinterpret_cast<const float4*>(x),
+                         stats, reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(y), hw, C / 4, ppc, eps, relu));
   SDOF_LAUNCH_CHECK("instnorm_apply_nhwc_kernel");
   return SDOF_OK;
 }

@@ -286,6 +286,56 @@ static void gru_tc_case(int B, int h, int w) {
   printf("ok tcgen05 GRU B=%d %dx%d\n", B, h, w);
 }
 
+// fp16 update-loop glue (csrc/raft_glue16.cu), the fp16 lookup output and fp16 instance norm -- all launched with the
+// programmatic-dependent-launch attribute, back to back on one stream like an iteration of the update block
+static uint16_t* dhalves(size_t n, uint16_t v) {
+  std::vector<uint16_t> h(n, v);
+  uint16_t* d = dalloc<uint16_t>(n);
+  CK(cudaMemcpy(d, h.data(), n * 2, cudaMemcpyHostToDevice));
+  return d;
+}
+static void glue16_case(int B, int h, int w) {
+  const int levels = 4, r = 4;
+  const size_t npix = (size_t)B * h * w;
+  sdof_pyramid_layout lay;
+  SD(sdof_corr_pyramid_layout_ex((int64_t)npix, h, w, levels, 2, &lay));
+  uint16_t* pyr = dhalves((size_t)lay.total_floats, 0x3000);
+  float* coords = dfloats(npix * 2, 10.f);
+  uint16_t* corr16 = dalloc<uint16_t>(npix * 328);
+  float* flow = dfloats(npix * 2, 3.f);
+  float* wT = dfloats(7 * 7 * 2 * 128, 0.1f);
+  float* bias = dfloats(128, 0.1f);
+  uint16_t* f1 = dalloc<uint16_t>(npix * 128);
+  uint16_t* mc = dhalves(npix * 128, 0x3800);
+  uint16_t* mf = dhalves(npix * 128, 0x3400);
+  uint16_t* hx16 = dalloc<uint16_t>(npix * 256);
+  uint16_t* zr16 = dhalves(npix * 384, 0x3000);
+  uint16_t* q16 = dhalves(npix * 128, 0x3000);
+  uint16_t* rh16 = dalloc<uint16_t>(npix * 128);
+  uint16_t* h16 = dalloc<uint16_t>(npix * 128);
+  float* zrmap = dfloats(npix * 256, 0.5f);
+  float* qmap = dfloats(npix * 128, 0.5f);
+  float* hid = dfloats(npix * 128, 0.9f);
+  uint16_t* x16 = dhalves(npix * 256, 0x3400);
+  float* w2 = dfloats(3 * 3 * 2 * 256, 0.05f);
+  float* scratch = dalloc<float>(npix * 18);
+  for (int it = 0; it < 2; ++it) {
+    SD(sdof_corr_lookup_h(pyr, 2, coords, B, h, w, h, w, levels, r, corr16, 328, nullptr));
+    SD(sdof_conv7x7_c2_relu_h(flow, wT, bias, f1, B, h, w, nullptr));
+    SD(sdof_motion_tail16_h(mc, mf, bias, flow, (int64_t)npix, hx16, 256, nullptr));
+    SD(sdof_gru_rh_h(zr16, 384, zrmap, hid, rh16, (int64_t)npix, nullptr));
+    SD(sdof_gru_update_h(zr16, zrmap, q16, qmap, hid, hx16, 256, h16, (int64_t)npix, nullptr));
+    SD(sdof_flowhead2_taps_h(x16, w2, (int64_t)npix, scratch, nullptr));
+    SD(sdof_flowhead2_gather_update(scratch, 0.1f, -0.1f, coords, flow, nullptr, 0, 0, B, h, w, nullptr));
+  }
+  double* stats = dalloc<double>((size_t)B * 256 * 2);
+  CK(cudaMemset(stats, 0, (size_t)B * 256 * 2 * sizeof(double)));
+  SD(sdof_instnorm_stats_nhwc_h(x16, B, (int64_t)h * w, 256, stats, nullptr));
+  SD(sdof_instnorm_apply_nhwc_h(x16, stats, nullptr, x16, B, (int64_t)h * w, 256, 1e-5f, 1, nullptr));
+  CK(cudaDeviceSynchronize());
+  printf("ok fp16 update-loop glue (PDL launches) B=%d %dx%d\n", B, h, w);
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
   const bool all = !strcmp(what, "all");
@@ -305,6 +355,10 @@ int main(int argc, char** argv) {
   }
   if (all || !strcmp(what, "mask")) mask_case(1, 90, 124);
   if (all || !strcmp(what, "glue")) glue_case(2, 12, 20);
+  if (all || !strcmp(what, "glue")) {
+    glue16_case(2, 12, 20);
+    glue16_case(1, 23, 37);     // sizes no vector width divides
+  }
   if (all || !strcmp(what, "gru")) {
     gru_tc_case(1, 24, 64);     // full 32x4 patches
     gru_tc_case(2, 11, 20);     // partial tiles on both axes, B > 1
