@@ -17,7 +17,7 @@ import torch
 SDOF_MAX_LEVELS = 8
 PRECISIONS = {'tf32': 0, '3xtf32': 1, 'bf16': 2, 'fp32': 3, 'fp16': 4}
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libsdof_b200.so')
+_LIB_PATH = os.environ.get('SDOF_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libsdof_b200.so')   # SDOF_B200_LIB: A/B runs against another build
 
 
 class PyramidLayout(ctypes.Structure):

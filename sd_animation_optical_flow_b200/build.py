@@ -29,6 +29,8 @@ NVCC_FLAGS = [
     '-Xcompiler', '-fPIC,-ffp-contract=off',
     '-Xptxas', '-v',
 ]
+# experiments: SDOF_NVCC_EXTRA="-DSDOF_RES_TRACE" python -m sd_animation_optical_flow_b200.build   (tools/corr_trace.py)
+NVCC_FLAGS += os.environ.get('SDOF_NVCC_EXTRA', '').split()
 
 
 def _nvcc() -> str:

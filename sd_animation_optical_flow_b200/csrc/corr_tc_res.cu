@@ -42,6 +42,8 @@
 #include <string.h>
 
 #include "corr.cuh"
+#include <vector>
+
 #include "tc_ptx.cuh"
 
 namespace sdof {
@@ -96,7 +98,21 @@ struct ResArgs {
   int fmt;  // 0 = fp16, 1 = bf16
   int tgt_shared;                      // the target operand has batch 1 and serves every pair of the call
   int debug;             // SDOF_RES_DEBUG: 1 skip stores, 4 skip MMA, 8 skip A loads, 16 skip TMEM loads (experiments only)
+  long long* trace;      // built with -DSDOF_RES_TRACE and run with SDOF_RES_TRACE=<file>: clock64 stamps [cta][tile of the cta < kRTraceTiles][kRTraceSlots] (experiments only)
 };
+constexpr int kRTraceTiles = 64, kRTraceSlots = 16;
+// slots: 0 MMA warp owns the accumulator | 1 first slab landed | 2 tile's MMAs issued + committed | 3 epilogue warp 0 saw the
+// accumulator full | 4 all 64 columns in registers, buffer handed back | 5 stores of columns 0-31 issued | 7 of columns 32-63 |
+// 8 producer issued the tile's last slab load | 9 producer started (re)loading the resident block | 10 MMA thread saw it landed
+#ifndef SDOF_RES_TRACE   // compiled out of the product build: the stamps cost ~1.8 us of a 32 us kernel even when switched off
+#define RES_TRACE(it_, slot_) do { } while (0)
+#else
+#define RES_TRACE(it_, slot_)                                                                                          \
+  do {                                                                                                                 \
+    if (args.trace != nullptr && (it_) < kRTraceTiles)                                                                 \
+      args.trace[((long long)blockIdx.x * kRTraceTiles + (it_)) * kRTraceSlots + (slot_)] = clock64();                 \
+  } while (0)
+#endif
 
 struct TileInfo {
   int blk;  // b * m_tiles + mt
@@ -203,6 +219,7 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
         if (ti.blk != cur_blk) {
           // (re)load the resident block once every tensor-core read of the previous one has retired
           mbar_wait(bar_bempty, bphase ^ 1);
+          RES_TRACE(t - t_begin, 9);
           mbar_expect_tx(bar_bfull, (uint32_t)args.kslabs * kRBSlab);
           for (int k = 0; k < args.kslabs; ++k)
             tma_load_3d(smem_b + k * kRBSlab, &maps.src, bar_bfull, k * args.slab_elems, ti.mt * kRN, ti.b);
@@ -223,46 +240,74 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
             phase ^= 1;
           }
         }
+        RES_TRACE(t - t_begin, 8);
       }
     }
   } else if (warp == kREpiWarps + 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_fmt((uint32_t)args.fmt, kRM, kRN);
-      uint32_t stage = 0, phase = 0, bphase = 0;
-      int cur_blk = -1;
-      int it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const TileInfo ti = unpack_tile(args, table[t - t_begin]);
-        if (ti.blk != cur_blk) {
-          mbar_wait(bar_bfull, bphase);
-          bphase ^= 1;
-          cur_blk = ti.blk;
-        }
-        const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * ab, aphase ^ 1);
+    // The WHOLE warp walks the loop and one elected lane issues: every operand of the tensor-core instructions is then
+    // warp-uniform and lives in uniform registers.  (Round 2 finding, tools/corr_trace.py + tools/microbench/mma_rate.cu: with
+    // the loop under `if (lane == 0)` the compiler moves each descriptor through R2UR and wraps each tcgen05 instruction in
+    // an ELECT loop -- ~300 cycles of single-lane work per 128-byte slab, more than the tensor pipe's short queue hides:
+    // 176 instead of 128 cycles per MMA and ~900 idle cycles per tile.)  No shared-memory reads on this path either: the
+    // resident-block boundaries follow from the tile index.
+    const uint32_t idesc = make_idesc_fmt((uint32_t)args.fmt, kRM, kRN);
+    const int per_block = args.tile_begin_level[args.levels];
+    const bool skip_mma = (args.debug & 4) != 0;
+    const int kslabs = args.kslabs;
+    uint32_t stage = 0, phase = 0, bphase = 0;
+    int r = t_begin % per_block;      // position of the tile inside its source block
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      // (one lane polls: thirty-two polling lanes slow every other mbarrier operation of the CTA down)
+      if (it == 0 || r == 0) {
+        if (lane == 0) mbar_wait(bar_bfull, bphase);
+        __syncwarp();
+        if (lane == 0) RES_TRACE(it, 10);
+        bphase ^= 1;
+      }
+      const uint32_t ab = it & 1;
+      if (lane == 0) mbar_wait(bar_tempty + 8 * ab, ((it >> 1) & 1) ^ 1);
+      __syncwarp();
+      tc_fence_after();
+      if (lane == 0) RES_TRACE(it, 0);
+      const uint32_t tmem_d = tmem_base + ab * kRN;
+      for (int k = 0; k < kslabs; ++k) {
+        if (lane == 0) mbar_wait(bar_afull + 8 * stage, phase);
+        __syncwarp();
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + ab * kRN;
-        for (int k = 0; k < args.kslabs; ++k) {
-          mbar_wait(bar_afull + 8 * stage, phase);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_a + stage * kRAStage);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_b + k * kRBSlab);
+        if (k == 0 && lane == 0) RES_TRACE(it, 1);
+        const uint64_t adesc = make_smem_desc_sw128(smem_a + stage * kRAStage);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_b + k * kRBSlab);
+        if (elect_one()) {
+          if (!skip_mma) {
 #pragma unroll
-          for (int j = 0; j < kRMmaPerSlab; ++j)
-            if (!(args.debug & 4)) tc_mma<true>(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
-          tc_commit(bar_aempty + 8 * stage);
-          if (++stage == kRAStages) {
-            stage = 0;
-            phase ^= 1;
+            for (int j = 0; j < kRMmaPerSlab; ++j) tc_mma<true>(tmem_d, adesc + 2 * j, bdesc + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
           }
+          tc_commit(bar_aempty + 8 * stage);
         }
+        __syncwarp();
+        if (++stage == kRAStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      // last tile that reads this resident block: release it to the producer
+      const bool last_of_block = (t + 1 == t_end) || (r + 1 == per_block);
+      if (elect_one()) {
         tc_commit(bar_tfull + 8 * ab);
-        // last tile that reads this resident block: release it to the producer
-        bool last_of_block = (t + 1 == t_end);
-        if (!last_of_block) last_of_block = (int)table[t + 1 - t_begin].blk != cur_blk;
         if (last_of_block) tc_commit(bar_bempty);
       }
+      __syncwarp();
+      if (lane == 0) {
+        RES_TRACE(it, 2);
+        if (args.trace != nullptr && it < kRTraceTiles) {   // wall clock beside the cycle counter: the SM clock of this run
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          args.trace[((long long)blockIdx.x * kRTraceTiles + it) * kRTraceSlots + 11] = (long long)gt;
+        }
+      }
+      if (++r == per_block) r = 0;
     }
   } else {
     // ===================================================================== epilogue: 16 warps on EVERY tile
@@ -283,6 +328,21 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
       const float f = __ldg(args.src_hdr + kHdrInvScale) * __ldg(args.tgt_hdr + kHdrInvScale);
       *args.out_factor = use_div ? __fdiv_rn(f, divisor) : f * args.rsqrt_c;
     }
+    // Drain, release, store: TMEM -> registers is fast (470-890 B/clk per SM, tools/microbench/tmem_ld.cu: ~150 ns for this
+    // warp's 64 columns), so both halves are loaded at once and the accumulator goes back to the tensor core before the first
+    // store.  (Measured and dropped in round 2: software-pipelining the two halves against the stores, with the hand-over in
+    // between -- 33.5 vs 31.5 us; the tile time is the memory system accepting this store pattern, see profiles/README.md.)
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + cq * kColsPerWarp;
+    uint32_t ua[32], ub[32];
+    const bool skip_ld = (args.debug & 16) != 0;
+    auto issue_ld = [&](uint32_t (&u)[32], uint32_t addr) {
+      if (!skip_ld) {
+        tmem_ld32(addr, u);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) u[i] = 0;
+      }
+    };
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const TileInfo ti = unpack_tile(args, table[t - t_begin]);
@@ -294,23 +354,16 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
       const long long pitch = args.pitch[l];
       const int y = (ti.ty << (7 - pxs)) + py, x = (ti.tx << pxs) + px;
       const uint32_t ab = it & 1;
-
       // one lane per warp polls the barrier (512 polling threads slow every other mbarrier operation of the CTA down);
       // tcgen05.fence::after_thread_sync orders the TMEM loads after the warp-level hand-over
       if (lane == 0) mbar_wait(bar_tfull + 8 * ab, (it >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * kRN + cq * kColsPerWarp;
-      uint32_t ua[32], ub[32];
-      if (!(args.debug & 16)) {
-        tmem_ld32(taddr, ua);
-        tmem_ld32(taddr + 32, ub);
-        tmem_ld_wait(ua, ub);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ua[i] = ub[i] = 0;
-      }
-      // this warp's share of the accumulator is in registers: hand the TMEM buffer back
+      if (threadIdx.x == 0) RES_TRACE(it, 3);
+      issue_ld(ua, taddr0 + ab * kRN);
+      issue_ld(ub, taddr0 + ab * kRN + 32);
+      tmem_ld_wait(ua, ub);
+      if (threadIdx.x == 0) RES_TRACE(it, 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
@@ -327,60 +380,69 @@ __global__ void __launch_bounds__(kRThreads, 1) corr_pyramid_resident_kernel(con
         const bool do_store = !(args.debug & 1);
         __half2* p = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(args.out[l]) +
                                                 ((long long)ti.b * args.n1 + m0 + (odd ? 1 : 0)) * pitch + (long long)y * args.wp[l] + xe);
-        const long long pstep = pitch;  // two columns further, in half2 units
+        // Instruction diet (the epilogue is ALU-pipe bound: 2 issue cycles per ALU instruction and quarter-SM): each lane
+        // first packs ITS pixel's (column j, column j+1) into one half2, the pair of lanes swaps the packed words, and one
+        // PRMT picks (x, x+1) of the lane's column; the address is base + constant * pitch in one IMAD.WIDE.  5
+        // instructions per 4-byte store where the select-shuffle-select-convert-add64 sequence took 9.
+        const uint32_t pstep = (uint32_t)pitch;                 // two columns further, in half2 units (pitch < 2^31 halves)
+        const uint32_t sel = odd ? 0x3276u : 0x5410u;           // odd: (partner's hi, my hi) = column j+1; even: (my lo, partner's lo) = column j
         auto store_chunk = [&](const uint32_t (&u)[32], int chunk) {
           const int ncols = mcount - chunk * 32;
+          __half2* pc = p + (size_t)(chunk * 16) * pstep;
           if (ncols >= 32 && all_in) {
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 2) {
-              const uint32_t mine = odd ? u[jj + 1] : u[jj];
-              const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? u[jj] : u[jj + 1], 1);
-              const __half2 v = __floats2half2_rn(__uint_as_float(odd ? recv : mine), __uint_as_float(odd ? mine : recv));
-              if (do_store) *p = v;
-              p += pstep;
+            for (int i = 0; i < 16; ++i) {
+              const __half2 h = __floats2half2_rn(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
+              const uint32_t mine = *reinterpret_cast<const uint32_t*>(&h);
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, mine, 1);
+              const uint32_t v = __byte_perm(mine, recv, sel);
+              if (do_store) *reinterpret_cast<uint32_t*>(pc + (size_t)i * pstep) = v;
             }
           } else if (ncols > 0) {
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 2) {
-              if (jj < ncols) {  // warp-uniform
-                const uint32_t mine = odd ? u[jj + 1] : u[jj];
-                const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? u[jj] : u[jj + 1], 1);
-                const __half2 v = __floats2half2_rn(__uint_as_float(odd ? recv : mine), __uint_as_float(odd ? mine : recv));
-                if (do_store && in && jj + (odd ? 1 : 0) < ncols) *p = v;
-                p += pstep;
+            for (int i = 0; i < 16; ++i) {
+              if (2 * i < ncols) {  // warp-uniform
+                const __half2 h = __floats2half2_rn(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
+                const uint32_t mine = *reinterpret_cast<const uint32_t*>(&h);
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, mine, 1);
+                const uint32_t v = __byte_perm(mine, recv, sel);
+                if (do_store && in && 2 * i + (odd ? 1 : 0) < ncols) *reinterpret_cast<uint32_t*>(pc + (size_t)i * pstep) = v;
               }
             }
           }
         };
         store_chunk(ua, 0);
+        if (threadIdx.x == 0) RES_TRACE(it, 5);
         store_chunk(ub, 1);
+        if (threadIdx.x == 0) RES_TRACE(it, 7);
       } else {
         const bool in = y < args.lh[l] && x < args.lw[l];
         const bool all_in = __all_sync(0xffffffffu, in);
         const bool do_store = !(args.debug & 1);
         float* p = reinterpret_cast<float*>(args.out[l]) + ((long long)ti.b * args.n1 + m0) * pitch + (long long)y * args.wp[l] + x;
+        const uint32_t pstep = (uint32_t)pitch;
         auto store_chunk = [&](const uint32_t (&u)[32], int chunk) {
           const int ncols = mcount - chunk * 32;
+          float* pc = p + (size_t)(chunk * 32) * pstep;
           if (ncols >= 32 && all_in && !use_div) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              if (do_store) *p = __uint_as_float(u[jj]) * mul;
-              p += pitch;
-            }
+            for (int jj = 0; jj < 32; ++jj)
+              if (do_store) pc[(size_t)jj * pstep] = __uint_as_float(u[jj]) * mul;
           } else if (ncols > 0) {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
               if (jj < ncols) {  // warp-uniform
                 float v = __uint_as_float(u[jj]) * mul;
                 if (use_div) v = __fdiv_rn(v, divisor);
-                if (in && do_store) *p = v;
-                p += pitch;
+                if (in && do_store) pc[(size_t)jj * pstep] = v;
               }
             }
           }
         };
         store_chunk(ua, 0);
+        if (threadIdx.x == 0) RES_TRACE(it, 5);
         store_chunk(ub, 1);
+        if (threadIdx.x == 0) RES_TRACE(it, 7);
       }
     }
   }
@@ -797,6 +859,17 @@ int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, i
     const char* d = getenv("SDOF_RES_DEBUG");
     ra.debug = d ? atoi(d) : 0;
   }
+  ra.trace = nullptr;
+#ifdef SDOF_RES_TRACE
+  const char* trace_path = getenv("SDOF_RES_TRACE");
+#else
+  const char* trace_path = nullptr;
+#endif
+  const size_t trace_bytes = (size_t)sm_count() * kRTraceTiles * kRTraceSlots * sizeof(long long);
+  if (trace_path && *trace_path) {
+    SDOF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ra.trace), trace_bytes));
+    SDOF_CUDA(cudaMemsetAsync(ra.trace, 0, trace_bytes, st));
+  }
   ra.tile_begin_level[0] = 0;
   for (int l = 0; l < used_levels; ++l) {
     const int pxs = pick_patch_shift(lay.h[l], lay.w[l]);
@@ -832,6 +905,19 @@ int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, i
     SDOF_CUDA(launch_pdl(corr_pyramid_resident_kernel<false>, dim3(grid), dim3(kRThreads), (size_t)kRSmemTotal, st, maps, ra));
   }
   SDOF_LAUNCH_CHECK("corr_pyramid_resident_kernel");
+  if (ra.trace) {
+    // experiments only: synchronises and dumps the stamps (header: ctas, tiles, slots, total tiles)
+    std::vector<long long> host(trace_bytes / sizeof(long long));
+    SDOF_CUDA(cudaStreamSynchronize(st));
+    SDOF_CUDA(cudaMemcpy(host.data(), ra.trace, trace_bytes, cudaMemcpyDeviceToHost));
+    SDOF_CUDA(cudaFree(ra.trace));
+    if (FILE* f = fopen(trace_path, "wb")) {
+      const long long hdr[4] = {grid, kRTraceTiles, kRTraceSlots, total};
+      fwrite(hdr, sizeof(hdr), 1, f);
+      fwrite(host.data(), 1, trace_bytes, f);
+      fclose(f);
+    }
+  }
   return SDOF_OK;
 }
 
