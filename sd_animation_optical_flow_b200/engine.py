@@ -196,6 +196,53 @@ class RaftEngine:
         g.replay()
         return out  # overwritten by the next replay: estimate_flow copies (unpad / contiguous) before returning
 
+    # ---------------------------------------------------------------- consecutive frames of a clip
+    def _forward_seq(self, frames: torch.Tensor, pad, bgr: bool) -> torch.Tensor:
+        im = ops.normalize_pad_u8(frames, pad, channels=4, bgr=bgr)
+        _, flow_up = self.fast.forward(im, None, self.iters, normalized=True, sequence=True)
+        return flow_up
+
+    @torch.no_grad()
+    def estimate_flow_sequence(self, frames: torch.Tensor, unpad: bool = True, bgr: bool = False) -> torch.Tensor:
+        """Flows of the consecutive pairs of a clip: frames [n,H,W,3] (uint8 CUDA) -> [n-1,H,W,2] fp32, pair i = RAFT(image1 =
+        frame i, image2 = frame i+1) -- the loop of ofgen.py (`calc(prev, cur)` for every frame).  Equal to
+        estimate_flow(frames[:-1], frames[1:]) but the feature encoder runs once per frame instead of twice (frame i+1 is
+        image2 of pair i and image1 of pair i+1).  One CUDA graph per shape."""
+        if self.fast is None:
+            raise RuntimeError('estimate_flow_sequence needs the fast path (basic model, fast=True)')
+        if frames.dim() != 4 or frames.shape[-1] != 3 or frames.dtype != torch.uint8 or not frames.is_cuda or frames.shape[0] < 2:
+            raise RuntimeError(f'frames must be a uint8 CUDA tensor [n >= 2,H,W,3], got {tuple(frames.shape)} {frames.dtype}')
+        with self._scope():
+            n, H, W, _ = frames.shape
+            pad = InputPadder((H, W))._pad
+            frames = frames.contiguous()
+            if self.use_cuda_graph:
+                gk = ('seq', tuple(frames.shape), self.iters, bool(bgr))
+                ent = self._graph_get(gk)
+                if ent is None:
+                    s1 = frames.clone()
+                    side = torch.cuda.Stream(device=self.device)
+                    side.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            self._forward_seq(s1, pad, bgr)
+                    torch.cuda.current_stream(self.device).wait_stream(side)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self._capture_stream()):
+                        out = self._forward_seq(s1, pad, bgr)
+                    ent = (g, s1, out)
+                    self._graph_put(gk, ent)
+                g, s1, out = ent
+                s1.copy_(frames)
+                g.replay()
+                flow_up = out
+            else:
+                flow_up = self._forward_seq(frames, pad, bgr)
+            if unpad and any(pad):
+                Hp, Wp = flow_up.shape[1:3]
+                flow_up = flow_up[:, pad[2]:Hp - pad[3], pad[0]:Wp - pad[1]]
+            return flow_up.clone(memory_format=torch.contiguous_format) if self.use_cuda_graph else flow_up.contiguous()
+
     # ---------------------------------------------------------------- key-frame scheme
     @torch.no_grad()
     def encode_key(self, key_img: torch.Tensor, bgr: bool = False):

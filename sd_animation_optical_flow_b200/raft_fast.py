@@ -366,11 +366,14 @@ class FastRaft:
 
     @torch.no_grad()
     def forward(self, image1: torch.Tensor, image2: torch.Tensor | None, iters: int = 20, normalized: bool = False,
-                key: KeyFeatures | None = None):
+                key: KeyFeatures | None = None, sequence: bool = False):
         """image1/2: [B,3,H,W] float 0..255 (H, W multiples of 8), or with normalized=True already 2*(x/255)-1 (any memory
         format; ops.normalize_pad_u8 hands over channels-last).  Returns (flow_low [B,h,w,2], flow_up [B,H,W,2]).
         key: the encoded key frame serving as image2 of all B pairs (then `image2` is ignored): fnet(key) and the pooled
         correlation operands are not recomputed per pair.
+        sequence: image1 holds the B+1 frames of a clip and the pairs are (frame i, frame i+1) -- the loop of ofgen.py, where
+        frame i+1 is image2 of one pair and image1 of the next: the feature encoder runs once per FRAME (B+1 images
+        instead of 2B), the context encoder on frames 0..B-1.  `image2` is ignored.
 
         Two independent chains run on a side stream (fork/join with events, so a CUDA-graph capture records them as
         parallel branches): the context encoder next to the feature encoder + correlation pyramid, and in every
@@ -378,6 +381,10 @@ class FastRaft:
         buffer that crosses the streams is allocated before the fork on the main stream; the side stream's own
         temporaries are allocated and freed in stream order on that stream."""
         B, _, Hh, Ww = image1.shape
+        if sequence:
+            if key is not None or B < 2:
+                raise RuntimeError('sequence mode takes the B+1 >= 2 frames of a clip in image1 and no key')
+            B -= 1
         h, w = Hh // 8, Ww // 8
         hd = self.hidden
         dev = image1.device
@@ -389,7 +396,10 @@ class FastRaft:
             im1, im2 = image1, image2
         else:
             im1 = (2 * (image1 / 255.0) - 1.0).contiguous()
-            im2 = (2 * (image2 / 255.0) - 1.0).contiguous() if key is None else None
+            im2 = (2 * (image2 / 255.0) - 1.0).contiguous() if key is None and not sequence else None
+        frames = im1
+        if sequence:
+            im1 = frames[:B]
         tc = self.tc_gru
         H = torch.empty((B, h, w, hd), device=dev)                        # hidden state, dense [B,h,w,128] (fp32 master copy)
         if tc:                                                            # tcgen05 GRU: the conv operands exist only in fp16
@@ -426,7 +436,10 @@ class FastRaft:
                 ZRMAP[p].copy_(self._conv(inp, self.zr_ctx[p], bias=True))
                 QMAP[p].copy_(self._conv(inp, self.q_ctx[p], bias=True))
             del cn, inp
-        if key is None:                                                   # ---- feature encoder + all-pairs volume
+        if sequence:                                                      # ---- feature encoder once per frame
+            fmaps = _to_nhwc(self.fnet(frames))
+            pyr = ops.corr_volume_pyramid(fmaps[:B], fmaps[1:], 4, self.corr_precision, self.corr_storage)
+        elif key is None:                                                 # ---- feature encoder + all-pairs volume
             fmaps = self.fnet(torch.cat([im1, im2], 0))
             pyr = ops.corr_volume_pyramid(_to_nhwc(fmaps[:B]), _to_nhwc(fmaps[B:]), 4, self.corr_precision, self.corr_storage)
         else:                                                             # key frame: its features / operands exist already

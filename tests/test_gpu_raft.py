@@ -261,6 +261,29 @@ def test_keyed_flow_equals_pairwise_flow(cuda):
         assert torch.allclose(eng.estimate_flow_keyed(k, fr[1:]), flow_k, atol=1e-5)
 
 
+def test_sequence_flow_equals_pairwise_flow(cuda):
+    """estimate_flow_sequence(frames) == estimate_flow(frames[:-1], frames[1:]): the feature encoder runs once per frame
+    (InstanceNorm is per image, so a frame's features do not depend on the batch it is encoded in)."""
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    canvas = gi.texture(128 + 32, 160 + 32, 777)
+    frames = np.stack([canvas[5 * i:5 * i + 128, 4 * i:4 * i + 160] for i in range(5)])
+    fr = torch.from_numpy(frames).to(cuda)
+    for graph in (False, True):
+        eng = RaftEngine(checkpoint=None, iters=4, seed=0, device=cuda, use_cuda_graph=graph)
+        flow_s = eng.estimate_flow_sequence(fr)
+        flow_p = eng.estimate_flow(fr[:-1].contiguous(), fr[1:].contiguous())
+        assert flow_s.shape == flow_p.shape == (4, 128, 160, 2)
+        d = (flow_s - flow_p).norm(dim=-1)
+        print(f'sequence vs pairwise (graph={graph}): EPE mean {float(d.mean()):.2e} max {float(d.max()):.2e}')
+        assert float(d.max()) <= 1e-3
+        # same graph, other frames; and the first result was a copy
+        flow_r = eng.estimate_flow_sequence(fr.flip(0).contiguous())
+        assert flow_r.data_ptr() != flow_s.data_ptr()
+        assert float((flow_r - eng.estimate_flow(fr.flip(0)[:-1].contiguous(), fr.flip(0)[1:].contiguous())).norm(dim=-1).max()) <= 1e-3
+    with pytest.raises(RuntimeError):
+        eng.estimate_flow_sequence(fr[:1])
+
+
 def test_engine_on_a_device_that_is_not_current(cuda):
     """engine, warp and masks on cuda:1 while cuda:0 is current (PDCNetAux(device=cuda:N))."""
     if torch.cuda.device_count() < 2:
