@@ -44,6 +44,7 @@ UNIT = 'frame-pairs/s'
 # flow is committed (tests/golden/raft_full.npz): bench.py measures its EPE against it live (config.parity_epe).
 WEIGHT_SEED, FLOW_HEAD_SCALE = 0, 0.02
 MIN_TIMED_S = 1.0
+NCU_CORR_TRAFFIC = 8025088 + 48935936   # bytes; see roofline.traffic_note
 
 
 def synthetic_pair(seed: int):
@@ -512,13 +513,14 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = old_tf32
     del ma, mb
     step_flops = 946e9           # reference RAFT at 768x512, iters=20 (torch.utils.flop_counter)
+    fp16_step = not (args.no_loop_fp16 or args.tc_gru or args.mixed_precision)
 
     hbm = peaks['hbm_gbs']
     corr_gbs = (in_bytes + out_bytes) / t_corr / 1e9
     roofline = {'kernel': corr_kernel + ', 1 pair, N=6144, C=256, 4 levels', 'bound': 'hbm',
                 'achieved': corr_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': corr_gbs / hbm,
-                'traffic': None,
-                'traffic_note': 'not measured in this run; one ncu --set full capture of the same kernel: profiles/r2_kernels_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum)',
+                'traffic': NCU_CORR_TRAFFIC if (args.corr_precision == 'fp16' and ebytes == 2) else None,
+                'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel at this size (8.03 MB read + 48.94 MB written; profiles/r2_kernels_ncu_summary.txt), not measured in this run: less than the algorithmic bytes because about half of the 100 MB pyramid is still dirty in the 126 MB L2 when the kernel ends (the first lookups read it from there)',
                 'peak_source': peaks['source'], 'us_per_launch': t_corr * 1e6, 'us_operand_prepass': t_prep * 1e6,
                 'frac_with_prepass': (in_bytes + out_bytes + 2 * n1 * C * 4) / (t_corr + t_prep) / 1e9 / hbm,
                 'algorithmic_bytes': in_bytes + out_bytes,
@@ -538,9 +540,11 @@ def run_ours(args):
          'tiles_staged': w32_staged, 'tiles_fallback': w32_fallback},
         {'kernel': 'warp_mask_composite_kernel, 32 frames, same flows, N(0,3) logits, thres 0.95, 7x7 ellipse', 'bound': 'hbm', 'achieved': 26.0 * 32 * H * W / t_fused / 1e9, 'peak': hbm,
          'unit': 'GB/s', 'frac': 26.0 * 32 * H * W / t_fused / 1e9 / hbm, 'us_per_launch': t_fused * 1e6},
-        {'kernel': 'whole step (cuDNN TF32 convolutions dominate)', 'bound': 'tensor', 'achieved': step_flops / (dt / timed_steps) / 1e12, 'peak': tf32_peak,
-         'unit': 'TFLOP/s', 'frac': step_flops / (dt / timed_steps) / 1e12 / tf32_peak,
-         'note': '946 GFLOP per pair (reference RAFT, 768x512, iters=20) / step time vs the TF32 matmul peak measured in this run (torch.matmul 8192^3, allow_tf32)'},
+        {'kernel': 'whole step (cuDNN tensor-op convolutions dominate: fp16 operands in the encoders and the update block)', 'bound': 'tensor',
+         'achieved': step_flops / (dt / timed_steps) / 1e12, 'peak': peaks['bf16_tflops'] if fp16_step else tf32_peak,
+         'unit': 'TFLOP/s', 'frac': step_flops / (dt / timed_steps) / 1e12 / (peaks['bf16_tflops'] if fp16_step else tf32_peak),
+         'frac_of_tf32_peak': step_flops / (dt / timed_steps) / 1e12 / tf32_peak,
+         'note': '946 GFLOP per pair (reference RAFT, 768x512, iters=20) / step time vs the measured 16-bit dense peak (MEASURED_PEAKS.json) when the convolutions run on fp16 operands, else vs the TF32 matmul peak measured in this run (torch.matmul 8192^3, allow_tf32); at 6144 pixels per pair every convolution of the update loop is a sub-wave GEMM bound by launch latency and L2 -> SM operand traffic, not by the tensor pipe'},
     ]
 
     # ---- the same path with 8 pairs per call (how configs[2..4] feed it: PDCNetAux batches 16 pairs,
@@ -591,7 +595,7 @@ def run_ours(args):
     cpu = cpu_baseline_leg(args.cpu_budget_s) if args.cpu_budget_s > 0 else None
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': dt / timed_steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'tf32', 'data': 'synthetic',
+            'dtype': 'tf32' if (args.no_loop_fp16 or args.tc_gru) else 'fp16', 'data': 'synthetic',
             'timed_steps': timed_steps, 'timed_region_s': dt,
             'timed_note': f'the {args.steps} steps are repeated {reps}x back to back so that the timed region is >= {MIN_TIMED_S} s; every repetition is inside the timed region',
             'config': {'workload': 'configs[1]: RAFT all-pairs correlation + warp, single 512x768 frame pair per GPU',
@@ -599,7 +603,7 @@ def run_ours(args):
                        'weights': f'random-init, name-seeded (seed {WEIGHT_SEED}), flow-head output convolution x{FLOW_HEAD_SCALE} so the flow stays a few px (RAFT_FULL_CASES S_calm)',
                        'corr_precision': args.corr_precision, 'corr_storage': storage,
                        'conv_precision': 'bf16 autocast' if args.mixed_precision else ('cuDNN tensor cores, fp32 accumulate: TF32 (torch default = what the reference runs on this GPU) for what is left in fp32 activations (per-pair context maps)' + ('; fp16 activations / filters (the same 11-bit operand precision, fp32 accumulation) for the encoders and the update block, fp32 hidden-state master copy / coordinates / flow' if not args.no_loop_fp16 else '; fp16 encoders')),
-                       'precision_note': 'dtype names the arithmetic of the bulk of the step (TF32 convolutions); the correlation volume uses '
+                       'precision_note': 'dtype names the operand type of the bulk of the step: fp16 activations and filters with fp32 accumulation (11-bit significand, what TF32 - the arithmetic the reference itself gets on this GPU from torch defaults - rounds its operands to), fp32 recurrent state; config.parity_epe is the measured distance to the fp32 reference.  The correlation volume uses '
                                          f'auto-ranged {args.corr_precision} operands (11-bit significand like TF32, per-tensor power-of-two scale) with fp32 accumulation and a {storage}-stored pyramid, '
                                          'the thin convolutions and all glue fp32, the warp exact integer (u8)',
                        'parity_epe': parity,

@@ -75,6 +75,20 @@ else:
     c1 = coords_nhwc.clone()
     fl = torch.empty((1, 96, 64, 2), device=dev)
     mask = (torch.rand((32, 768, 512), generator=g, device=dev) < 0.3).to(torch.uint8) * 255
+    # the fp16 update-loop kernels (csrc/raft_glue16.cu, fp16 lookup output) at the batch-1 size
+    hf = lambda *sh: (torch.randn(sh, generator=g, device=dev) * 0.5).half()
+    corr16 = torch.empty((1, 96, 64, 328), dtype=torch.float16, device=dev)
+    f1_16 = torch.empty((1, 96, 64, 128), dtype=torch.float16, device=dev)
+    mc16, mf16 = hf(1, 96, 64, 128), hf(1, 96, 64, 128)
+    hx16 = torch.empty((1, 96, 64, 256), dtype=torch.float16, device=dev)
+    zr16, q16 = hf(1, 96, 64, 384), hf(1, 96, 64, 128)
+    zrmap, qmap = torch.randn((1, 96, 64, 256), generator=g, device=dev), torch.randn((1, 96, 64, 128), generator=g, device=dev)
+    hid = torch.tanh(torch.randn((1, 96, 64, 128), generator=g, device=dev))
+    rh16 = torch.empty((1, 96, 64, 128), dtype=torch.float16, device=dev)
+    h16 = torch.empty((1, 96, 64, 128), dtype=torch.float16, device=dev)
+    x16 = torch.relu(hf(1, 96, 64, 256))
+    bias128 = torch.randn((128,), generator=g, device=dev)
+    scratch = torch.empty((96 * 64 * 18,), device=dev)
     for _ in range(3):
         pyr = ops.corr_volume_pyramid(f1, f2, 4, prec, 'fp16' if prec in ('fp16', 'bf16') else 'fp32')
         ops.corr_lookup(pyr, coords, 4)
@@ -86,4 +100,11 @@ else:
         ops.flowhead2_update(x256, w2, (0.1, 0.2), c1, fl, None, 0, None, 0)
         ops.mask_blur_composite(mask, src, src.flip(0), 4.0)
         ops.instnorm_nhwc(act.half().contiguous(memory_format=torch.channels_last), torch.zeros((2 * 64 * 2,), dtype=torch.float64, device=dev))
+        if pyr.elem_bytes == 2:
+            ops.corr_lookup_nhwc_h(pyr, coords_nhwc, corr16)
+        ops.conv7x7_c2_relu_h(lowflow, w7, b7, f1_16)
+        ops.motion_tail16_h(mc16, mf16, bias128, lowflow, hx16)
+        ops.gru_rh_h(zr16, zrmap, hid, rh16)
+        ops.gru_update_h(zr16, zrmap, q16, qmap, hid, hx16, h16)
+        ops.flowhead2_update_h(x16, w2, (0.1, 0.2), c1, fl, scratch)
     torch.cuda.synchronize()
