@@ -44,7 +44,6 @@ UNIT = 'frame-pairs/s'
 # flow is committed (tests/golden/raft_full.npz): bench.py measures its EPE against it live (config.parity_epe).
 WEIGHT_SEED, FLOW_HEAD_SCALE = 0, 0.02
 MIN_TIMED_S = 1.0
-NCU_CORR_TRAFFIC = 8025088 + 48935936   # bytes; see roofline.traffic_note
 
 
 def synthetic_pair(seed: int):
@@ -519,8 +518,8 @@ def run_ours(args):
     corr_gbs = (in_bytes + out_bytes) / t_corr / 1e9
     roofline = {'kernel': corr_kernel + ', 1 pair, N=6144, C=256, 4 levels', 'bound': 'hbm',
                 'achieved': corr_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': corr_gbs / hbm,
-                'traffic': NCU_CORR_TRAFFIC if (args.corr_precision == 'fp16' and ebytes == 2) else None,
-                'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel at this size (8.03 MB read + 48.94 MB written; profiles/r2_kernels_ncu_summary.txt), not measured in this run: less than the algorithmic bytes because about half of the 100 MB pyramid is still dirty in the 126 MB L2 when the kernel ends (the first lookups read it from there)',
+                'traffic': None,
+                'traffic_note': 'not measured in this run (VERDICT r1: no constants here); one ncu --set full capture of the same kernel at this size is committed as profiles/r2_kernels_ncu_summary.txt: dram__bytes_read.sum 8.03 MB + dram__bytes_write.sum 48.94 MB -- below the algorithmic bytes because about half of the 100 MB pyramid is still dirty in the 126 MB L2 when the kernel ends; inside a step (profiles/r2_lookup_dram_in_step.txt) 0.45 MB read + 101.9 MB written',
                 'peak_source': peaks['source'], 'us_per_launch': t_corr * 1e6, 'us_operand_prepass': t_prep * 1e6,
                 'frac_with_prepass': (in_bytes + out_bytes + 2 * n1 * C * 4) / (t_corr + t_prep) / 1e9 / hbm,
                 'algorithmic_bytes': in_bytes + out_bytes,
