@@ -445,12 +445,20 @@ int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords,
   const size_t smem = (size_t)kLookupPxNhwc * levels * T * sizeof(float);
   dim3 grid(ceil_div(N1, kLookupPxNhwc), B);
   cudaStream_t st = as_stream(stream);
+  // the pyramid is read 20 times per pair: its leading bytes (level 0 first) may stay in the persisting part of L2
+  L2Window win;
+  win.ptr = pyramid;
+  win.bytes = (size_t)lay.total_floats * elem_bytes;
+  {
+    const size_t cap = l2_persist_bytes();
+    if (cap > 0 && win.bytes > cap) win.bytes = cap;   // a window that fits entirely: level 0 (and what follows it) up to the cap
+  }
   if (elem_bytes == 2)
-    SDOF_CUDA(launch_pdl(corr_lookup_kernel<4, 4, kLookupPxNhwc, __half>, grid, dim3(kLookupPxNhwc * 32), smem, st, lv, coords, N1, radius,
-                         static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
+    SDOF_CUDA(launch_pdl_win(corr_lookup_kernel<4, 4, kLookupPxNhwc, __half>, grid, dim3(kLookupPxNhwc * 32), smem, st, win, lv, coords, N1,
+                             radius, static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
   else
-    SDOF_CUDA(launch_pdl(corr_lookup_kernel<4, 4, kLookupPxNhwc, float>, grid, dim3(kLookupPxNhwc * 32), smem, st, lv, coords, N1, radius,
-                         static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
+    SDOF_CUDA(launch_pdl_win(corr_lookup_kernel<4, 4, kLookupPxNhwc, float>, grid, dim3(kLookupPxNhwc * 32), smem, st, win, lv, coords, N1,
+                             radius, static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
   SDOF_LAUNCH_CHECK("corr_lookup_kernel");
   return SDOF_OK;
 }

@@ -899,7 +899,14 @@ int launch_corr_pyramid_parts(const void* src_ops, const void* tgt_ops, int B, i
   if (ceil_div64(total, grid) + 1 > kRMaxTilesPerCta) return SDOF_ERR_UNSUPPORTED;  // tile table would not fit
   if (out_half) {
     SDOF_CUDA(cudaFuncSetAttribute(corr_pyramid_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemTotal));
-    SDOF_CUDA(launch_pdl(corr_pyramid_resident_kernel<true>, dim3(grid), dim3(kRThreads), (size_t)kRSmemTotal, st, maps, ra));
+    L2Window win;   // written once, read by 20 lookups: same window as sdof_corr_lookup_h
+    win.ptr = pyramid;
+    win.bytes = (size_t)lay.total_floats * 2;
+    {
+      const size_t cap = l2_persist_bytes();
+      if (cap > 0 && win.bytes > cap) win.bytes = cap;
+    }
+    SDOF_CUDA(launch_pdl_win(corr_pyramid_resident_kernel<true>, dim3(grid), dim3(kRThreads), (size_t)kRSmemTotal, st, win, maps, ra));
   } else {
     SDOF_CUDA(cudaFuncSetAttribute(corr_pyramid_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemTotal));
     SDOF_CUDA(launch_pdl(corr_pyramid_resident_kernel<false>, dim3(grid), dim3(kRThreads), (size_t)kRSmemTotal, st, maps, ra));

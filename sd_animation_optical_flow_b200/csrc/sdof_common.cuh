@@ -63,19 +63,44 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 bool pdl_enabled();
+// L2 residency of a buffer read many times (the correlation pyramid: 20 lookups per pair): bytes of L2 this device sets aside
+// for persisting lines (0 = unsupported or switched off with SDOF_L2_PERSIST=0; the limit is raised once per device).
+size_t l2_persist_bytes();
+struct L2Window {        // accesses to [ptr, ptr + bytes) keep their lines in the persisting part of L2
+  const void* ptr = nullptr;
+  size_t bytes = 0;
+};
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl_win(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, L2Window win, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  const size_t persist = win.ptr ? l2_persist_bytes() : 0;
+  if (persist > 0 && win.bytes > 0) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = const_cast<void*>(win.ptr);
+    attr[n].val.accessPolicyWindow.num_bytes = win.bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = win.bytes <= persist ? 1.0f : (float)((double)persist / (double)win.bytes);
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  return launch_pdl_win(kernel, grid, block, smem, st, L2Window{}, args...);
 }
 
 // host-side tables (cubic_table.cpp)

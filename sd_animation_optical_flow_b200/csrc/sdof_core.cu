@@ -40,6 +40,28 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+size_t l2_persist_bytes() {
+  static long long cached[64];
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!done[dev]) {
+    long long v = 0;
+    const char* e = getenv("SDOF_L2_PERSIST");
+    if (e && e[0] == '1') {   // opt-in (experiment): see profiles/README.md
+      int max_persist = 0, max_window = 0;
+      if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess &&
+          cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess && max_persist > 0 &&
+          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess)
+        v = max_persist < max_window ? max_persist : max_window;
+    }
+    (void)cudaGetLastError();
+    cached[dev] = v;
+    done[dev] = true;
+  }
+  return (size_t)cached[dev];
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
