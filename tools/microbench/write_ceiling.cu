@@ -38,6 +38,26 @@ __global__ void __launch_bounds__(512, 1) pyr16_kernel(__half* out, int rows, in
   }
 }
 
+// patch-blocked layout [source block][patch ty][patch tx][map (256)][py (4)][px (32)]: a tile is one contiguous 64 KB run
+__global__ void __launch_bounds__(512, 1) pyr16_blocked_kernel(__half* out, int rows, int h, int w) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cq = warp >> 2, q = warp & 3;
+  const bool odd = lane & 1;
+  const int txt = w / 32, tyt = h / 4, per_block = txt * tyt;
+  const int total = (rows / 256) * per_block;
+  const int t_begin = (int)((long long)total * blockIdx.x / gridDim.x), t_end = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+  const __half2 v = __floats2half2_rn((float)lane, 1.f);
+  for (int t = t_begin; t < t_end; ++t) {
+    // tile t = 32768 halves; map m of the tile at m * 128, row q at + q * 32, x at + (lane & ~1)
+    __half2* p = reinterpret_cast<__half2*>(out + (long long)t * 32768 + (cq * 64 + (odd ? 1 : 0)) * 128 + q * 32 + (lane & ~1));
+#pragma unroll 16
+    for (int j = 0; j < 32; ++j) {
+      *p = v;
+      p += 128;   // two maps further (2 * 128 halves), in half2 units
+    }
+  }
+}
+
 static float time_us(void (*launch)(void*, long long, int, int, int), void* buf, long long bytes, int rows, int h, int w) {
   cudaEvent_t s, e;
   cudaEventCreate(&s);
@@ -64,8 +84,10 @@ int main() {
     const float t_set = time_us([](void* b, long long n, int, int, int) { cudaMemsetAsync(b, 1, n); }, buf, bytes, 0, 0, 0);
     const float t_pyr = time_us([](void* b, long long, int rows, int h, int w) { pyr16_kernel<<<148, 512>>>((__half*)b, rows, h, w); }, buf, bytes,
                                 c.rows, c.h, c.w);
-    printf("%-28s fill %7.1f us %5.0f GB/s | memset %7.1f us %5.0f GB/s | pyramid pattern %7.1f us %5.0f GB/s\n", c.name, t_fill,
-           bytes / t_fill / 1e3, t_set, bytes / t_set / 1e3, t_pyr, bytes / t_pyr / 1e3);
+    const float t_blk = time_us([](void* b, long long, int rows, int h, int w) { pyr16_blocked_kernel<<<148, 512>>>((__half*)b, rows, h, w); }, buf, bytes,
+                                c.rows, c.h, c.w);
+    printf("%-28s fill %7.1f us %5.0f GB/s | memset %7.1f us %5.0f GB/s | pyramid pattern %7.1f us %5.0f GB/s | patch-blocked layout %7.1f us %5.0f GB/s\n",
+           c.name, t_fill, bytes / t_fill / 1e3, t_set, bytes / t_set / 1e3, t_pyr, bytes / t_pyr / 1e3, t_blk, bytes / t_blk / 1e3);
     cudaFree(buf);
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
