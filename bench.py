@@ -373,7 +373,9 @@ def run_ours(args):
     gather = None
     if world > 1:
         local = local_stack                                 # [pairs of this rank, H, W, 2] fp32
-        shard.gather_stack(local[:1], world)                # NCCL warm-up (communicator, buffers)
+        shard.gather_stack(local[:1], world)                # NCCL warm-up (communicator, channels)
+        del_me = shard.gather_stack(local, n_frames4 - 1)   # and one full-size call: the 2 x 0.8 GB of buffers come from cudaMalloc the first time
+        del del_me
         barrier()
         sg, eg = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sg.record()
