@@ -353,6 +353,19 @@ int sdof_gru_q_tc(const void* rh16, const void* w_q16, const float* qmap, const 
 int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels, int radius,
                        void* out16, int out_channels, sdof_stream_t stream);
 int sdof_conv7x7_c2_relu_h(const float* flow, const float* wT, const float* bias, void* out16, int B, int h, int w, sdof_stream_t stream);
+/* Deferred coords update of the update loop (RAFT/core/raft.py:128-131 `coords1 = coords1 + delta_flow`): the flow head of iteration i
+ * only leaves its tap products (sdof_flowhead2_taps_h); iteration i+1 applies coords = coords_in + (bias + sum of the 9 neighbours'
+ * taps) where the coordinates are consumed, one launch and one dependency less per iteration:
+ *   sdof_corr_lookup_gather_h     : sdof_corr_lookup_h on the updated coordinates; also writes them to coords_out (must not alias
+ *                                   coords_in) and flow_out = coords_out - pixel grid.  taps == NULL: coordinates pass through.
+ *   sdof_conv7x7_c2_relu_coords_h : sdof_conv7x7_c2_relu_h (BasicMotionEncoder.convf1, update.py:85,93) on flow = updated
+ *                                   coordinates - pixel grid, reading coords_in and the taps only (it runs beside the lookup).
+ * Both use the summation order of sdof_flowhead2_gather_update: identical bits. */
+int sdof_corr_lookup_gather_h(const void* pyramid, int elem_bytes, const float* coords_in, const float* taps, float bias_x, float bias_y,
+                              float* coords_out, float* flow_out, int B, int h1, int w1, int h2, int w2, int levels, int radius, void* out16,
+                              int out_channels, sdof_stream_t stream);
+int sdof_conv7x7_c2_relu_coords_h(const float* coords, const float* taps, float tap_bias_x, float tap_bias_y, const float* wT, const float* bias,
+                                  void* out16, int B, int h, int w, sdof_stream_t stream);
 int sdof_motion_tail16_h(const void* mc16, const void* mf16, const float* bias, const float* flow, int64_t npix, void* hx16, int hx16_stride,
                          sdof_stream_t stream);
 int sdof_gru_rh_h(const void* zr16, int zr_channels, const float* zrmap, const float* h, void* rh16, int64_t npix, sdof_stream_t stream);

@@ -115,10 +115,22 @@ constexpr int kLookupPxNhwc = 8;
 
 // ET = float: the fp32 pyramid (window taps gathered one by one).  ET = __half: the fp16 pyramid -- a window row is gathered
 // as 2r/2+2 aligned 32-bit words (two taps each), half the load instructions and half the sectors of the fp32 form.
+// Deferred coords update (channels-last form only): the previous iteration's flow head left its tap products in `taps`
+// (sdof_flowhead2_taps_h); instead of a separate kernel that sums them into coords1, the lookup does
+// coords = coords_in + gather(taps) itself (every lane computes the same scalar sum: broadcast loads) and lane 0 writes the new
+// coordinates / flow for the kernels after it.  coords_out == nullptr: plain lookup.
+struct LookupGather {
+  const float* taps = nullptr;     // [B*h1*w1][18]; nullptr with coords_out set: coords pass through (first iteration)
+  float2 bias = {0.f, 0.f};
+  float2* coords_out = nullptr;    // [B,h1,w1,2]   (must not alias coords_in: the flow branch reads coords_in concurrently)
+  float2* flow_out = nullptr;      // [B,h1,w1,2] = coords_out - pixel grid
+  int w1 = 0;
+};
+
 template <int R_T, int L_T, int PX, typename ET>
 __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords,
                                                               int N1, int r_rt, float* __restrict__ out, __half* __restrict__ out16 = nullptr,
-                                                              int out16_channels = 0) {
+                                                              int out16_channels = 0, LookupGather g = LookupGather()) {
   constexpr bool nhwc = PX != kLookupPx;   // the 8-warp CTA shape is the channels-last form (no stage tile)
   extern __shared__ __align__(16) float smem[];
   constexpr bool kHalf = sizeof(ET) == 2;
@@ -142,9 +154,23 @@ __global__ void __launch_bounds__(PX * 32) corr_lookup_kernel(LookupLevels lv, c
   if (p < N1) {
     // nhwc: coords [B,h,w,2] and out [B,h,w,CH] (channels-last, for the NHWC update loop); else the
     // reference's planar layouts coords [B,2,h,w] / out [B,CH,h,w]
-    const float cx = nhwc ? coords[((int64_t)b * N1 + p) * 2] : coords[((int64_t)b * 2 + 0) * N1 + p];
-    const float cy = nhwc ? coords[((int64_t)b * N1 + p) * 2 + 1] : coords[((int64_t)b * 2 + 1) * N1 + p];
+    float cx = nhwc ? coords[((int64_t)b * N1 + p) * 2] : coords[((int64_t)b * 2 + 0) * N1 + p];
+    float cy = nhwc ? coords[((int64_t)b * N1 + p) * 2 + 1] : coords[((int64_t)b * 2 + 1) * N1 + p];
     const int64_t row = (int64_t)b * N1 + p;
+    if constexpr (nhwc) {
+      if (g.coords_out != nullptr) {
+        const int yy = p / g.w1, xx = p - yy * g.w1;
+        if (g.taps != nullptr) {
+          const float2 d = flowhead2_gather(g.taps, g.bias, row, yy, xx, N1 / g.w1, g.w1);
+          cx += d.x;
+          cy += d.y;
+        }
+        if (lane == 0) {
+          g.coords_out[row] = make_float2(cx, cy);
+          g.flow_out[row] = make_float2(cx - (float)xx, cy - (float)yy);
+        }
+      }
+    }
     float fxs[L_T ? L_T : SDOF_MAX_LEVELS], fys[L_T ? L_T : SDOF_MAX_LEVELS];
     int xos[L_T ? L_T : SDOF_MAX_LEVELS];
     // gather: with compile-time (r, L) every level's loads are issued before any is consumed
@@ -415,10 +441,9 @@ int sdof_corr_lookup_nhwc(const float* pyramid, const float* coords, int B, int 
 
 // fp16 channels-last output for the fp16 update block: out16 [B,h1,w1,out_channels] halves, out_channels >= levels*(2r+1)^2 a
 // multiple of 8 (padding channels are written as zeros); radius 4, 4 levels only (RAFT's configuration).
-int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels, int radius,
-                       void* out16, int out_channels, sdof_stream_t stream) {
+static int corr_lookup_h_impl(const char* name, const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2,
+                              int levels, int radius, void* out16, int out_channels, sdof::LookupGather g, sdof_stream_t stream) {
   using namespace sdof;
-  const char* name = "sdof_corr_lookup_h";
   SDOF_REQUIRE(pyramid && coords && out16, "%s: NULL pointer", name);
   SDOF_REQUIRE(B >= 0 && B <= 65535 && h1 >= 1 && w1 >= 1 && h2 >= 1 && w2 >= 1, "%s: bad sizes", name);
   SDOF_REQUIRE(radius == 4 && levels == 4, "%s: radius 4 / 4 levels only", name);
@@ -455,12 +480,36 @@ int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords,
   }
   if (elem_bytes == 2)
     SDOF_CUDA(launch_pdl_win(corr_lookup_kernel<4, 4, kLookupPxNhwc, __half>, grid, dim3(kLookupPxNhwc * 32), smem, st, win, lv, coords, N1,
-                             radius, static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
+                             radius, static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels, g));
   else
     SDOF_CUDA(launch_pdl_win(corr_lookup_kernel<4, 4, kLookupPxNhwc, float>, grid, dim3(kLookupPxNhwc * 32), smem, st, win, lv, coords, N1,
-                             radius, static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels));
+                             radius, static_cast<float*>(nullptr), reinterpret_cast<__half*>(out16), out_channels, g));
   SDOF_LAUNCH_CHECK("corr_lookup_kernel");
   return SDOF_OK;
+}
+
+int sdof_corr_lookup_h(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels, int radius,
+                       void* out16, int out_channels, sdof_stream_t stream) {
+  return corr_lookup_h_impl("sdof_corr_lookup_h", pyramid, elem_bytes, coords, B, h1, w1, h2, w2, levels, radius, out16, out_channels,
+                            sdof::LookupGather(), stream);
+}
+
+int sdof_corr_lookup_gather_h(const void* pyramid, int elem_bytes, const float* coords_in, const float* taps, float bias_x, float bias_y,
+                              float* coords_out, float* flow_out, int B, int h1, int w1, int h2, int w2, int levels, int radius, void* out16,
+                              int out_channels, sdof_stream_t stream) {
+  using namespace sdof;
+  const char* name = "sdof_corr_lookup_gather_h";
+  SDOF_REQUIRE(coords_in && coords_out && flow_out, "%s: NULL pointer", name);
+  SDOF_REQUIRE(coords_out != coords_in, "%s: coords_out must not alias coords_in (the flow branch reads coords_in concurrently)", name);
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(coords_out) | reinterpret_cast<uintptr_t>(flow_out) | reinterpret_cast<uintptr_t>(taps)) & 7) == 0,
+               "%s: misaligned pointer", name);
+  LookupGather g;
+  g.taps = taps;
+  g.bias = make_float2(bias_x, bias_y);
+  g.coords_out = reinterpret_cast<float2*>(coords_out);
+  g.flow_out = reinterpret_cast<float2*>(flow_out);
+  g.w1 = w1;
+  return corr_lookup_h_impl(name, pyramid, elem_bytes, coords_in, B, h1, w1, h2, w2, levels, radius, out16, out_channels, g, stream);
 }
 
 int sdof_corr_lookup_ex(const void* pyramid, int elem_bytes, const float* coords, int B, int h1, int w1, int h2, int w2, int levels,

@@ -733,19 +733,10 @@ __global__ void __launch_bounds__(256) flowhead2_gather_update_kernel(const floa
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
     const int rem = (int)(p % ((int64_t)h * w));
     const int yy = rem / w, xx = rem - yy * w;
-    float s0 = bias.x, s1 = bias.y;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int ny = yy + t / 3 - 1, nx = xx + t % 3 - 1;
-      if ((unsigned)ny < (unsigned)h && (unsigned)nx < (unsigned)w) {
-        const float2 q = *reinterpret_cast<const float2*>(y + (p + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * 18 + t * 2);
-        s0 += q.x;
-        s1 += q.y;
-      }
-    }
+    const float2 d = flowhead2_gather(y, bias, p, yy, xx, h, w);
     float2 c = coords1[p];
-    c.x += s0;
-    c.y += s1;
+    c.x += d.x;
+    c.y += d.y;
     coords1[p] = c;
     const float2 f = make_float2(c.x - (float)xx, c.y - (float)yy);
     flow[p] = f;

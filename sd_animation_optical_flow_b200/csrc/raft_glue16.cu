@@ -91,9 +91,13 @@ __global__ void __launch_bounds__(256) gru_update_h_kernel(const __half* __restr
 constexpr int kH7Tile = 8, kH7Threads = 256, kH7Patch = kH7Tile + 6, kH7K = 98;
 constexpr size_t kH7Smem = (size_t)kH7K * 128 * 4 + (size_t)kH7Patch * kH7Patch * 8;
 
+// coords != nullptr: the input is flow = coords + gather(taps) - pixel grid, computed while the patch is staged (the deferred coords
+// update of sdof_corr_lookup_gather_h: this kernel runs beside the lookup and must not read what the lookup writes); `flow` unused.
 __global__ void __launch_bounds__(kH7Threads) conv7x7_c2_relu_h_kernel(const float2* __restrict__ flow, const float* __restrict__ wT,
                                                                       const float* __restrict__ bias, __half* __restrict__ out, int h, int w,
-                                                                      int tiles_x, int tiles_y) {
+                                                                      int tiles_x, int tiles_y, const float2* __restrict__ coords = nullptr,
+                                                                      const float* __restrict__ taps = nullptr,
+                                                                      float2 tap_bias = make_float2(0.f, 0.f)) {
   extern __shared__ __align__(16) unsigned char h7_smem[];
   float* ws = reinterpret_cast<float*>(h7_smem);                                   // [98][128]
   float2* patch = reinterpret_cast<float2*>(h7_smem + (size_t)kH7K * 128 * 4);     // [14][14]
@@ -104,11 +108,24 @@ __global__ void __launch_bounds__(kH7Threads) conv7x7_c2_relu_h_kernel(const flo
   for (int i = threadIdx.x; i < kH7K * 128 / 4; i += kH7Threads) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wT) + i);
   pdl_wait();        // the 50 KB of filters above are staged while the kernel that produces `flow` drains
   pdl_trigger();
-  const float2* fb = flow + (int64_t)b * h * w;
+  const float2* fb = (coords ? coords : flow) + (int64_t)b * h * w;
   for (int i = threadIdx.x; i < kH7Patch * kH7Patch; i += kH7Threads) {
     const int py = i / kH7Patch, pxx = i - py * kH7Patch;
     const int y = ty0 + py - 3, x = tx0 + pxx - 3;
-    patch[i] = ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) ? fb[y * w + x] : make_float2(0.f, 0.f);
+    float2 v = make_float2(0.f, 0.f);
+    if ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) {
+      v = fb[y * w + x];
+      if (coords) {
+        if (taps) {
+          const float2 d = flowhead2_gather(taps, tap_bias, (int64_t)b * h * w + y * w + x, y, x, h, w);
+          v.x += d.x;
+          v.y += d.y;
+        }
+        v.x -= (float)x;
+        v.y -= (float)y;
+      }
+    }
+    patch[i] = v;
   }
   __syncthreads();
   const int cg = threadIdx.x & 15, pg = threadIdx.x >> 4;
@@ -269,7 +286,23 @@ int sdof_gru_update_h(const void* zr16, const float* zrmap, const void* q16, con
   return SDOF_OK;
 }
 
+static int conv7x7_c2_relu_h_impl(const float* flow, const float* wT, const float* bias, void* out16, int B, int h, int w, const float* coords,
+                                  const float* taps, float tap_bias_x, float tap_bias_y, sdof_stream_t stream);
+
 int sdof_conv7x7_c2_relu_h(const float* flow, const float* wT, const float* bias, void* out16, int B, int h, int w, sdof_stream_t stream) {
+  SDOF_REQUIRE(flow, "sdof_conv7x7_c2_relu_h: NULL pointer");
+  return conv7x7_c2_relu_h_impl(flow, wT, bias, out16, B, h, w, nullptr, nullptr, 0.f, 0.f, stream);
+}
+
+int sdof_conv7x7_c2_relu_coords_h(const float* coords, const float* taps, float tap_bias_x, float tap_bias_y, const float* wT, const float* bias,
+                                  void* out16, int B, int h, int w, sdof_stream_t stream) {
+  SDOF_REQUIRE(coords, "sdof_conv7x7_c2_relu_coords_h: NULL pointer");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(coords) | reinterpret_cast<uintptr_t>(taps)) & 7) == 0, "sdof_conv7x7_c2_relu_coords_h: misaligned pointer");
+  return conv7x7_c2_relu_h_impl(coords, wT, bias, out16, B, h, w, coords, taps, tap_bias_x, tap_bias_y, stream);
+}
+
+static int conv7x7_c2_relu_h_impl(const float* flow, const float* wT, const float* bias, void* out16, int B, int h, int w, const float* coords,
+                                  const float* taps, float tap_bias_x, float tap_bias_y, sdof_stream_t stream) {
   using namespace sdof;
   SDOF_REQUIRE(flow && wT && bias && out16, "sdof_conv7x7_c2_relu_h: NULL pointer");
   SDOF_REQUIRE(B >= 0 && h >= 1 && w >= 1, "sdof_conv7x7_c2_relu_h: bad sizes");
@@ -287,7 +320,8 @@ int sdof_conv7x7_c2_relu_h(const float* flow, const float* wT, const float* bias
   const int64_t tiles = (int64_t)tx * ty * B;
   SDOF_REQUIRE(tiles < 0x7fffffffLL, "sdof_conv7x7_c2_relu_h: too many tiles");
   SDOF_CUDA(launch_pdl(conv7x7_c2_relu_h_kernel, dim3((unsigned)tiles), dim3(kH7Threads), kH7Smem, as_stream(stream),
-                       reinterpret_cast<const float2*>(flow), wT, bias, reinterpret_cast<__half*>(out16), h, w, tx, ty));
+                       reinterpret_cast<const float2*>(flow), wT, bias, reinterpret_cast<__half*>(out16), h, w, tx, ty,
+                       reinterpret_cast<const float2*>(coords), taps, make_float2(tap_bias_x, tap_bias_y)));
   SDOF_LAUNCH_CHECK("conv7x7_c2_relu_h_kernel");
   return SDOF_OK;
 }

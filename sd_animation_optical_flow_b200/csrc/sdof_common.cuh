@@ -103,6 +103,26 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return launch_pdl_win(kernel, grid, block, smem, st, L2Window{}, args...);
 }
 
+// FlowHead.conv2 as "taps first" (raft_glue.cu): y[p][t] (t = 3*(dy+1) + (dx+1), two floats each) = <x[p,:], w[t][:, :]>; the 3x3
+// convolution at pixel p is bias + the sum over the in-image neighbours q = p + (dy, dx) of y[q][t].  ONE definition of that sum
+// (order: bias, then t = 0..8) for the coords-update kernel and for the kernels that apply the update on the fly (lookup, convf1),
+// so that all of them produce bit-identical coordinates.
+#ifdef __CUDACC__
+__device__ __forceinline__ float2 flowhead2_gather(const float* __restrict__ y, float2 bias, int64_t p, int yy, int xx, int h, int w) {
+  float s0 = bias.x, s1 = bias.y;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int ny = yy + t / 3 - 1, nx = xx + t % 3 - 1;
+    if ((unsigned)ny < (unsigned)h && (unsigned)nx < (unsigned)w) {
+      const float2 q = *reinterpret_cast<const float2*>(y + (p + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * 18 + t * 2);
+      s0 += q.x;
+      s1 += q.y;
+    }
+  }
+  return make_float2(s0, s1);
+}
+#endif
+
 // host-side tables (cubic_table.cpp)
 const int16_t* cubic_table_i16_host();  // [1024][16]
 const float* cubic_table_f32_host();    // [1024][16]

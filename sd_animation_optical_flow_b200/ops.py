@@ -573,6 +573,27 @@ def corr_lookup_nhwc_h(pyr: 'CorrPyramid', coords_nhwc: torch.Tensor, out16: tor
     return out16
 
 
+def corr_lookup_gather_nhwc_h(pyr: 'CorrPyramid', coords_in: torch.Tensor, taps: torch.Tensor | None, tap_bias, coords_out: torch.Tensor,
+                              flow_out: torch.Tensor, out16: torch.Tensor) -> torch.Tensor:
+    """corr_lookup_nhwc_h on coords = coords_in + gather(taps) (the deferred coords update, see include/sdof_b200.h); writes the new
+    coordinates to coords_out (a different tensor) and flow_out = coords_out - grid.  taps None: coordinates pass through."""
+    if coords_out.data_ptr() == coords_in.data_ptr():
+        raise RuntimeError('corr_lookup_gather_nhwc_h: coords_out must not alias coords_in')
+    check(load().sdof_corr_lookup_gather_h(ptr(pyr.buf), pyr.elem_bytes, ptr(coords_in), ptr(taps), float(tap_bias[0]), float(tap_bias[1]),
+                                           ptr(coords_out), ptr(flow_out), pyr.B, pyr.h1, pyr.w1, pyr.h2, pyr.w2, pyr.levels, 4, ptr(out16),
+                                           out16.shape[-1], stream_ptr(out16.device)), 'sdof_corr_lookup_gather_h')
+    return out16
+
+
+def conv7x7_c2_relu_coords_h(coords: torch.Tensor, taps: torch.Tensor | None, tap_bias, wT: torch.Tensor, bias: torch.Tensor,
+                             out16: torch.Tensor) -> torch.Tensor:
+    """conv7x7_c2_relu_h on flow = coords + gather(taps) - grid, computed on the fly from coords [B,h,w,2] and the taps."""
+    B, h, w, _ = coords.shape
+    check(load().sdof_conv7x7_c2_relu_coords_h(ptr(coords), ptr(taps), float(tap_bias[0]), float(tap_bias[1]), ptr(wT), ptr(bias), ptr(out16),
+                                               B, h, w, stream_ptr(out16.device)), 'sdof_conv7x7_c2_relu_coords_h')
+    return out16
+
+
 def conv7x7_c2_relu_h(flow_nhwc: torch.Tensor, wT: torch.Tensor, bias: torch.Tensor, out16: torch.Tensor) -> torch.Tensor:
     B, h, w, _ = flow_nhwc.shape
     check(load().sdof_conv7x7_c2_relu_h(ptr(flow_nhwc), ptr(wT), ptr(bias), ptr(out16), B, h, w, stream_ptr(out16.device)),
@@ -607,6 +628,22 @@ def flowhead2_update_h(x16: torch.Tensor, w2: torch.Tensor, bias, coords1: torch
     check(lib.sdof_flowhead2_taps_h(ptr(x16), ptr(w2), B * h * w, ptr(scratch), stream_ptr(x16.device)), 'sdof_flowhead2_taps_h')
     check(lib.sdof_flowhead2_gather_update(ptr(scratch), float(bias[0]), float(bias[1]), ptr(coords1), ptr(flow), None, 0, 0, B, h, w,
                                            stream_ptr(x16.device)), 'sdof_flowhead2_gather_update')
+
+
+def flowhead2_taps_h(x16: torch.Tensor, w2: torch.Tensor, scratch: torch.Tensor) -> None:
+    """First half of flowhead2_update_h alone: the 18 tap products per pixel into scratch [B*h*w*18] (the consumers of the
+    coordinates apply them: corr_lookup_gather_nhwc_h, conv7x7_c2_relu_coords_h, and flowhead2_gather_update after the loop)."""
+    B, h, w, C = x16.shape
+    if C != 256 or x16.dtype != f16:
+        raise RuntimeError('flowhead2_taps_h: x16 must be fp16 [B,h,w,256]')
+    check(load().sdof_flowhead2_taps_h(ptr(x16), ptr(w2), B * h * w, ptr(scratch), stream_ptr(x16.device)), 'sdof_flowhead2_taps_h')
+
+
+def flowhead2_gather_update(scratch: torch.Tensor, bias, coords1: torch.Tensor, flow: torch.Tensor) -> None:
+    """coords1 += bias + 9-neighbour sum of the taps in scratch (in place); flow = coords1 - grid."""
+    B, h, w, _ = coords1.shape
+    check(load().sdof_flowhead2_gather_update(ptr(scratch), float(bias[0]), float(bias[1]), ptr(coords1), ptr(flow), None, 0, 0, B, h, w,
+                                              stream_ptr(coords1.device)), 'sdof_flowhead2_gather_update')
 
 
 def flow_update(delta: torch.Tensor | None, coords1: torch.Tensor, flow: torch.Tensor, hx: torch.Tensor | None, hx_off: int,

@@ -174,7 +174,8 @@ class KeyFeatures:
 
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
-                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True, cnet_fp16: bool = True, loop_fp16: bool = True):
+                 own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True, cnet_fp16: bool = True, loop_fp16: bool = True,
+                 defer_coords: bool = True):
         """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
         convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical.
         corr_storage: 'fp16' / 'fp32' pyramid storage (default: fp16 with 16-bit correlation operands, else fp32)."""
@@ -254,6 +255,7 @@ class FastRaft:
         self.hidden = model.hidden_dim
         self.cdim = model.context_dim
         self._side = {}
+        self.defer_coords = bool(defer_coords)
         self._fused_relu_ok = None
         # fnet_fp16: the feature encoder's activations / cuDNN convolutions in fp16 (TF32-equivalent operand precision, half
         # the bytes through the InstanceNorm kernels); its output feeds the correlation, whose operands are fp16 anyway.
@@ -328,14 +330,29 @@ class FastRaft:
         corr16 = torch.empty((B, h, w, self.corr_ch16), device=dev, dtype=f16)
         H16.copy_(H)
         HX16[..., :hd] = H16
-        for _ in range(iters):
+        # Deferred coords update: the flow head leaves its tap products in fh_scratch and the NEXT iteration's consumers of the
+        # coordinates (lookup on this stream, convf1 on the side stream) add bias + the 9-neighbour sum themselves -- one kernel
+        # and one dependency less per iteration.  The coordinates ping-pong between two buffers because convf1 reads the old
+        # ones while the lookup writes the new ones.
+        defer = self.defer_coords and iters > 0
+        cbuf = [coords1, torch.empty_like(coords1)] if defer else None
+        for it in range(iters):
+            if defer:
+                cin, cout = cbuf[it % 2], cbuf[(it + 1) % 2]
+                taps = fh_scratch if it > 0 else None
             side.wait_stream(main)
             with torch.cuda.stream(side):                                 # flow branch (update.py:93-94)
-                ops.conv7x7_c2_relu_h(flow, self.convf1_t, self.convf1[1], F1_16)
+                if defer:
+                    ops.conv7x7_c2_relu_coords_h(cin, taps, self._fh2_bias, self.convf1_t, self.convf1[1], F1_16)
+                else:
+                    ops.conv7x7_c2_relu_h(flow, self.convf1_t, self.convf1[1], F1_16)
                 f2 = self._conv16_relu(F1_16, self.convf2_16)
                 MF16.copy_(self._conv(f2, self.conv_flo_16))
                 del f2
-            ops.corr_lookup_nhwc_h(pyr, coords1, corr16)                  # correlation branch (update.py:91-92)
+            if defer:                                                     # correlation branch (update.py:91-92)
+                ops.corr_lookup_gather_nhwc_h(pyr, cin, taps, self._fh2_bias, cout, flow, corr16)
+            else:
+                ops.corr_lookup_nhwc_h(pyr, coords1, corr16)
             c2 = self._conv16_relu(self._conv16_relu(corr16, self.convc1_16), self.convc2_16)
             mc = self._conv(c2, self.conv_cor_16)
             main.wait_stream(side)
@@ -345,7 +362,12 @@ class FastRaft:
                 ops.gru_rh_h(zr, ZRMAP[p], H, RH16)
                 q = self._conv(RH16, self.q_w16[p])
                 ops.gru_update_h(zr, ZRMAP[p], q, QMAP[p], H, HX16, H16 if p == 1 else None)
-            ops.flowhead2_update_h(self._conv16_relu(H16, self.fh1_16), self.fh2_t, self._fh2_bias, coords1, flow, fh_scratch)
+            if defer:
+                ops.flowhead2_taps_h(self._conv16_relu(H16, self.fh1_16), self.fh2_t, fh_scratch)
+            else:
+                ops.flowhead2_update_h(self._conv16_relu(H16, self.fh1_16), self.fh2_t, self._fh2_bias, coords1, flow, fh_scratch)
+        if defer:                                                         # the last iteration's update
+            ops.flowhead2_gather_update(fh_scratch, self._fh2_bias, cbuf[iters % 2], flow)
         mask = self._conv(self._conv16_relu(H16, self.mask0_16), self.mask2_16).float()
         return flow, ops.convex_upsample(mask.contiguous(), flow, 0.25, mask_bias=self.mask2[1])
 

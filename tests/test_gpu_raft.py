@@ -284,6 +284,57 @@ def test_sequence_flow_equals_pairwise_flow(cuda):
         eng.estimate_flow_sequence(fr[:1])
 
 
+def test_deferred_coords_update_is_bit_identical(cuda):
+    """The flow head's coords update applied inside the next lookup / convf1 (sdof_corr_lookup_gather_h,
+    sdof_conv7x7_c2_relu_coords_h) instead of by its own kernel: same summation order, so the flow must not change by a bit."""
+    from sd_animation_optical_flow_b200.engine import RaftEngine
+    canvas = gi.texture(136 + 24, 152 + 24, 99)
+    a = torch.from_numpy(np.stack([canvas[:136, :152], canvas[7:143, 3:155]])).to(cuda)
+    b = torch.from_numpy(np.stack([canvas[4:140, 6:158], canvas[2:138, 9:161]])).to(cuda)
+    flows = []
+    for defer in (True, False):
+        eng = RaftEngine(checkpoint=None, iters=5, seed=1, device=cuda, use_cuda_graph=False, fast_options=dict(defer_coords=defer))
+        flows.append(eng.estimate_flow(a, b))
+    assert flows[0].shape == (2, 136, 152, 2)
+    assert torch.equal(flows[0], flows[1])
+    assert float(flows[0].abs().max()) > 0.1
+
+
+def test_deferred_coords_kernels_vs_separate_update(cuda):
+    """The two consumers of the deferred update against the separate kernel on the same taps: coordinates, flow, lookup rows and
+    convf1 output identical."""
+    from sd_animation_optical_flow_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(5)
+    B, h, w = 2, 13, 21
+    f1 = torch.randn((B, h, w, 64), generator=g, device=cuda)
+    f2 = torch.randn((B, h, w, 64), generator=g, device=cuda)
+    pyr = ops.corr_volume_pyramid(f1, f2, 4, 'fp16', 'fp16')
+    ys, xs = torch.meshgrid(torch.arange(h, device=cuda), torch.arange(w, device=cuda), indexing='ij')
+    grid = torch.stack([xs, ys], -1).float()[None].repeat(B, 1, 1, 1).contiguous()
+    cin = (grid + 2 * torch.randn((B, h, w, 2), generator=g, device=cuda)).contiguous()
+    taps = torch.randn((B * h * w * 18,), generator=g, device=cuda) * 0.3
+    bias = (0.25, -0.5)
+    wT = torch.randn((7, 7, 2, 128), generator=g, device=cuda) * 0.1
+    b7 = torch.randn((128,), generator=g, device=cuda) * 0.1
+    # reference: separate update kernel, then the plain consumers
+    c_ref, fl_ref = cin.clone(), torch.empty_like(cin)
+    ops.flowhead2_gather_update(taps, bias, c_ref, fl_ref)
+    look_ref = ops.corr_lookup_nhwc_h(pyr, c_ref, torch.empty((B, h, w, 328), dtype=torch.float16, device=cuda))
+    conv_ref = ops.conv7x7_c2_relu_h(fl_ref, wT, b7, torch.empty((B, h, w, 128), dtype=torch.float16, device=cuda))
+    # deferred
+    cout, fl = torch.empty_like(cin), torch.empty_like(cin)
+    look = ops.corr_lookup_gather_nhwc_h(pyr, cin, taps, bias, cout, fl, torch.empty((B, h, w, 328), dtype=torch.float16, device=cuda))
+    conv = ops.conv7x7_c2_relu_coords_h(cin, taps, bias, wT, b7, torch.empty((B, h, w, 128), dtype=torch.float16, device=cuda))
+    assert torch.equal(cout, c_ref) and torch.equal(fl, fl_ref)
+    assert torch.equal(look, look_ref) and torch.equal(conv, conv_ref)
+    # no taps: coordinates pass through
+    look0 = ops.corr_lookup_gather_nhwc_h(pyr, cin, None, bias, cout, fl, torch.empty((B, h, w, 328), dtype=torch.float16, device=cuda))
+    assert torch.equal(cout, cin) and torch.equal(fl, cin - grid)
+    assert torch.equal(look0, ops.corr_lookup_nhwc_h(pyr, cin, torch.empty((B, h, w, 328), dtype=torch.float16, device=cuda)))
+    with pytest.raises(RuntimeError):
+        ops.corr_lookup_gather_nhwc_h(pyr, cin, taps, bias, cin, fl, look)
+
+
 def test_engine_on_a_device_that_is_not_current(cuda):
     """engine, warp and masks on cuda:1 while cuda:0 is current (PDCNetAux(device=cuda:N))."""
     if torch.cuda.device_count() < 2:

@@ -301,6 +301,7 @@ static void glue16_case(int B, int h, int w) {
   SD(sdof_corr_pyramid_layout_ex((int64_t)npix, h, w, levels, 2, &lay));
   uint16_t* pyr = dhalves((size_t)lay.total_floats, 0x3000);
   float* coords = dfloats(npix * 2, 10.f);
+  float* coords2 = dalloc<float>(npix * 2);
   uint16_t* corr16 = dalloc<uint16_t>(npix * 328);
   float* flow = dfloats(npix * 2, 3.f);
   float* wT = dfloats(7 * 7 * 2 * 128, 0.1f);
@@ -327,6 +328,9 @@ static void glue16_case(int B, int h, int w) {
     SD(sdof_gru_update_h(zr16, zrmap, q16, qmap, hid, hx16, 256, h16, (int64_t)npix, nullptr));
     SD(sdof_flowhead2_taps_h(x16, w2, (int64_t)npix, scratch, nullptr));
     SD(sdof_flowhead2_gather_update(scratch, 0.1f, -0.1f, coords, flow, nullptr, 0, 0, B, h, w, nullptr));
+    // the deferred form of the same update: applied inside the next lookup / convf1
+    SD(sdof_corr_lookup_gather_h(pyr, 2, coords, it ? scratch : nullptr, 0.1f, -0.1f, coords2, flow, B, h, w, h, w, levels, r, corr16, 328, nullptr));
+    SD(sdof_conv7x7_c2_relu_coords_h(coords, it ? scratch : nullptr, 0.1f, -0.1f, wT, bias, f1, B, h, w, nullptr));
   }
   double* stats = dalloc<double>((size_t)B * 256 * 2);
   CK(cudaMemset(stats, 0, (size_t)B * 256 * 2 * sizeof(double)));
