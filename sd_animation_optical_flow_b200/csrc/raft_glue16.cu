@@ -10,6 +10,7 @@
 //   conv7x7_c2_relu_h: BasicMotionEncoder.convf1 on the fp32 flow -> fp16 [B,h,w,128]                     (update.py:85,93)
 //   flowhead2_taps_h : the taps kernel of FlowHead.conv2 reading fp16 activations                          (update.py:10,14)
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "sdof_common.cuh"
 
@@ -333,7 +334,12 @@ int sdof_flowhead2_taps_h(const void* x16, const float* w2, int64_t npix, float*
                "sdof_flowhead2_taps_h: misaligned pointer");
   if (npix <= 0) return SDOF_OK;
   const int64_t want = ceil_div64(ceil_div64(npix, 2), 8);
-  const int64_t cap = sm_count();
+  int cap_mul = 1;             // CTAs per SM (each stages the 18 KB filter once); SDOF_FH_CAP_H overrides for experiments
+  if (const char* e = getenv("SDOF_FH_CAP_H")) {
+    cap_mul = atoi(e);
+    if (cap_mul < 1 || cap_mul > 8) cap_mul = 1;
+  }
+  const int64_t cap = (int64_t)sm_count() * cap_mul;
   SDOF_CUDA(launch_pdl(flowhead2_taps_h_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, as_stream(stream),
                        reinterpret_cast<const __half*>(x16), w2, scratch, npix));
   SDOF_LAUNCH_CHECK("flowhead2_taps_h_kernel");
