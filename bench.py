@@ -248,7 +248,7 @@ def run_ours(args):
                      mixed_precision=args.mixed_precision, channels_last=args.channels_last, device=dev, seed=WEIGHT_SEED,
                      flow_head_scale=FLOW_HEAD_SCALE, cudnn_benchmark=not args.no_cudnn_benchmark,
                      fast_options=dict(side_streams=not args.no_side_streams, own_convf1=not args.cudnn_convf1, own_fh2=not args.cudnn_fh2,
-                                       corr_storage=args.corr_storage, tc_gru=args.tc_gru, fnet_fp16=not args.no_fnet_fp16, cnet_fp16=not args.no_cnet_fp16, loop_fp16=not args.no_loop_fp16, defer_coords=not args.no_defer_coords))
+                                       corr_storage=args.corr_storage, tc_gru=args.tc_gru, fnet_fp16=not args.no_fnet_fp16, cnet_fp16=not args.no_cnet_fp16, loop_fp16=not args.no_loop_fp16, defer_coords=not args.no_defer_coords, convf1_gemm=not args.no_convf1_gemm))
 
     def step():
         flow = eng.estimate_flow(d1, d2)                 # [1,768,512,2]
@@ -643,6 +643,7 @@ def main():
     ap.add_argument('--tc-gru', action='store_true', help='SepConvGRU on the tcgen05 kernels of csrc/conv_tc.cu instead of cuDNN + glue (A/B switch)')
     ap.add_argument('--no-fnet-fp16', action='store_true', help='feature encoder in TF32 (fp32 activations) instead of fp16 (A/B switch)')
     ap.add_argument('--no-cnet-fp16', action='store_true', help='context encoder in TF32 instead of fp16 (A/B switch)')
+    ap.add_argument('--no-convf1-gemm', action='store_true', help='convf1 as the hand-written fp32 FMA kernel instead of im2col + cuDNN 1x1 tensor-core convolution (A/B switch)')
     ap.add_argument('--no-defer-coords', action='store_true', help='separate coords-update kernel after the flow head instead of applying it in the next lookup / convf1 (A/B switch)')
     ap.add_argument('--no-loop-fp16', action='store_true', help='update block in TF32 with fp32 activations instead of fp16 (A/B switch)')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-on-this-GPU leg')

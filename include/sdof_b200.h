@@ -366,6 +366,12 @@ int sdof_corr_lookup_gather_h(const void* pyramid, int elem_bytes, const float* 
                               int out_channels, sdof_stream_t stream);
 int sdof_conv7x7_c2_relu_coords_h(const float* coords, const float* taps, float tap_bias_x, float tap_bias_y, const float* wT, const float* bias,
                                   void* out16, int B, int h, int w, sdof_stream_t stream);
+/* BasicMotionEncoder.convf1 (update.py:85,93) as a tensor-core GEMM: the im2col rows of the 7x7 x 2-channel convolution of
+ * flow = coords + gather(taps) - pixel grid (taps may be NULL), fp16 with a hi/lo split of the flow:
+ *   out16 [B,h,w,out_channels] halves, row = [49 taps x (fx_hi, fy_hi) | 49 taps x (fx_lo, fy_lo) | zeros], tap = ky*7 + kx, taps outside
+ *   the image 0.  A 1x1 convolution of these rows with the filter [128][tap][ci] repeated for both halves is convf1. */
+int sdof_flow_im2col7_h(const float* coords, const float* taps, float tap_bias_x, float tap_bias_y, void* out16, int out_channels, int B, int h,
+                        int w, sdof_stream_t stream);
 int sdof_motion_tail16_h(const void* mc16, const void* mf16, const float* bias, const float* flow, int64_t npix, void* hx16, int hx16_stride,
                          sdof_stream_t stream);
 int sdof_gru_rh_h(const void* zr16, int zr_channels, const float* zrmap, const float* h, void* rh16, int64_t npix, sdof_stream_t stream);

@@ -62,6 +62,7 @@ SIGNATURES = {
     'sdof_conv7x7_c2_relu_h': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     'sdof_corr_lookup_gather_h': (c_int, [_P, c_int, _P, _P, c_float, c_float, _P, _P] + [c_int] * 7 + [_P, c_int, _P]),
     'sdof_conv7x7_c2_relu_coords_h': (c_int, [_P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
+    'sdof_flow_im2col7_h': (c_int, [_P, _P, c_float, c_float, _P, c_int, c_int, c_int, c_int, _P]),
     'sdof_motion_tail16_h': (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, _P]),
     'sdof_gru_rh_h': (c_int, [_P, c_int, _P, _P, _P, c_int64, _P]),
     'sdof_gru_update_h': (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, c_int64, _P]),

@@ -175,6 +175,60 @@ __global__ void __launch_bounds__(kH7Threads) conv7x7_c2_relu_h_kernel(const flo
 
 // ---- flow-head taps on fp16 activations: y[p][tap][co] = <x[p, :], w[tap][co][:]>, a warp owns 2 pixels, lanes split the 256
 // channels (8 each), two transposing butterflies reduce the 36 partials (same scheme as flowhead2_taps_kernel<2>)
+// ---- convf1 as a tensor-core GEMM: the im2col matrix of the 7x7 x 2-channel convolution, in fp16 with a hi/lo split of the flow
+// (flow = hi + lo to 2^-22 relative, so the fp16 operand costs no accuracy; the filter is the fp16-rounded one for both halves).
+// Row of pixel p (out_channels halves, >= 392): [tap 0..48: (fx_hi, fy_hi)] [tap 0..48: (fx_lo, fy_lo)] [zeros], tap = ky * 7 + kx,
+// out-of-image taps 0 (the convolution's zero padding).  A cuDNN 1x1 convolution over these rows runs in ~4.7 us at 96x64 where
+// the 7x7 convolution itself stays on a CUDA-core engine (9-13 us in cuDNN with 4, 8 or 16 padded input channels; 12.6 us for the
+// FMA kernel above, whose SM time also delays the correlation branch running beside it).  The flow is coords + gather(taps) - grid
+// as in sdof_conv7x7_c2_relu_coords_h.
+constexpr int kI2cTile = 8, kI2cThreads = 256, kI2cPatch = kI2cTile + 6;
+
+__global__ void __launch_bounds__(kI2cThreads) flow_im2col7_h_kernel(const float2* __restrict__ coords, const float* __restrict__ taps, float2 tap_bias,
+                                                                    __half2* __restrict__ out, int words_per_px, int h, int w, int tiles_x,
+                                                                    int tiles_y) {
+  __shared__ float2 patch[kI2cPatch * kI2cPatch];
+  const int tile = blockIdx.x;
+  const int b = tile / (tiles_x * tiles_y);
+  const int trem = tile - b * tiles_x * tiles_y;
+  const int ty0 = (trem / tiles_x) * kI2cTile, tx0 = (trem % tiles_x) * kI2cTile;
+  pdl_wait();
+  pdl_trigger();
+  const float2* cb = coords + (int64_t)b * h * w;
+  for (int i = threadIdx.x; i < kI2cPatch * kI2cPatch; i += kI2cThreads) {
+    const int py = i / kI2cPatch, pxx = i - py * kI2cPatch;
+    const int y = ty0 + py - 3, x = tx0 + pxx - 3;
+    float2 v = make_float2(0.f, 0.f);
+    if ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) {
+      v = cb[y * w + x];
+      if (taps) {
+        const float2 d = flowhead2_gather(taps, tap_bias, (int64_t)b * h * w + y * w + x, y, x, h, w);
+        v.x += d.x;
+        v.y += d.y;
+      }
+      v.x -= (float)x;
+      v.y -= (float)y;
+    }
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int total = kI2cTile * kI2cTile * words_per_px;
+  for (int i = threadIdx.x; i < total; i += kI2cThreads) {
+    const int px = i / words_per_px, k = i - px * words_per_px;
+    const int r = px / kI2cTile, c = px - r * kI2cTile;
+    const int y = ty0 + r, x = tx0 + c;
+    if (y >= h || x >= w) continue;
+    __half2 o = __floats2half2_rn(0.f, 0.f);
+    if (k < 98) {
+      const int t = k < 49 ? k : k - 49;
+      const float2 f = patch[(r + t / 7) * kI2cPatch + c + t % 7];
+      const __half hx = __float2half_rn(f.x), hy = __float2half_rn(f.y);
+      o = k < 49 ? __halves2half2(hx, hy) : __floats2half2_rn(f.x - __half2float(hx), f.y - __half2float(hy));
+    }
+    out[((int64_t)b * h * w + (int64_t)y * w + x) * words_per_px + k] = o;
+  }
+}
+
 __device__ __forceinline__ float reduce_transpose32(float (&v)[32], int lane) {
 #pragma unroll
   for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
@@ -324,6 +378,24 @@ static int conv7x7_c2_relu_h_impl(const float* flow, const float* wT, const floa
                        reinterpret_cast<const float2*>(flow), wT, bias, reinterpret_cast<__half*>(out16), h, w, tx, ty,
                        reinterpret_cast<const float2*>(coords), taps, make_float2(tap_bias_x, tap_bias_y)));
   SDOF_LAUNCH_CHECK("conv7x7_c2_relu_h_kernel");
+  return SDOF_OK;
+}
+
+int sdof_flow_im2col7_h(const float* coords, const float* taps, float tap_bias_x, float tap_bias_y, void* out16, int out_channels, int B, int h,
+                        int w, sdof_stream_t stream) {
+  using namespace sdof;
+  SDOF_REQUIRE(coords && out16, "sdof_flow_im2col7_h: NULL pointer");
+  SDOF_REQUIRE(B >= 0 && h >= 1 && w >= 1, "sdof_flow_im2col7_h: bad sizes");
+  SDOF_REQUIRE(out_channels >= 196 && out_channels <= 512 && out_channels % 8 == 0, "sdof_flow_im2col7_h: out_channels must be a multiple of 8 in [196, 512]");
+  SDOF_REQUIRE(((reinterpret_cast<uintptr_t>(coords) | reinterpret_cast<uintptr_t>(taps)) & 7) == 0 && (reinterpret_cast<uintptr_t>(out16) & 3) == 0,
+               "sdof_flow_im2col7_h: misaligned pointer");
+  if (B == 0) return SDOF_OK;
+  const int tx = ceil_div(w, kI2cTile), ty = ceil_div(h, kI2cTile);
+  const int64_t tiles = (int64_t)tx * ty * B;
+  SDOF_REQUIRE(tiles < 0x7fffffffLL, "sdof_flow_im2col7_h: too many tiles");
+  SDOF_CUDA(launch_pdl(flow_im2col7_h_kernel, dim3((unsigned)tiles), dim3(kI2cThreads), 0, as_stream(stream), reinterpret_cast<const float2*>(coords),
+                       taps, make_float2(tap_bias_x, tap_bias_y), reinterpret_cast<__half2*>(out16), out_channels / 2, h, w, tx, ty));
+  SDOF_LAUNCH_CHECK("flow_im2col7_h_kernel");
   return SDOF_OK;
 }
 

@@ -594,6 +594,26 @@ def conv7x7_c2_relu_coords_h(coords: torch.Tensor, taps: torch.Tensor | None, ta
     return out16
 
 
+def flow_im2col7_h(coords: torch.Tensor, taps: torch.Tensor | None, tap_bias, out16: torch.Tensor) -> torch.Tensor:
+    """im2col rows of the 7x7 x 2-channel convolution of flow = coords + gather(taps) - grid, fp16 hi/lo split (include/sdof_b200.h):
+    out16 [B,h,w,Kpad] with Kpad >= 196 a multiple of 8.  `im2col7_weight` builds the matching 1x1 filter."""
+    B, h, w, _ = coords.shape
+    check(load().sdof_flow_im2col7_h(ptr(coords), ptr(taps), float(tap_bias[0]), float(tap_bias[1]), ptr(out16), out16.shape[-1], B, h, w,
+                                     stream_ptr(out16.device)), 'sdof_flow_im2col7_h')
+    return out16
+
+
+def im2col7_weight(weight: torch.Tensor, kpad: int = 200) -> torch.Tensor:
+    """convf1's filter [Cout,2,7,7] -> the fp16 1x1 filter [Cout,kpad,1,1] (channels-last) over flow_im2col7_h's rows: [tap][ci] for
+    the hi half, the same again for the lo half, zeros for the padding."""
+    co = weight.shape[0]
+    wk = weight.detach().float().permute(0, 2, 3, 1).reshape(co, 98)            # [Cout][(ky*7+kx)*2 + ci]
+    full = torch.zeros((co, kpad), device=weight.device, dtype=torch.float32)
+    full[:, :98] = wk
+    full[:, 98:196] = wk
+    return full.half().view(co, kpad, 1, 1).contiguous(memory_format=torch.channels_last)
+
+
 def conv7x7_c2_relu_h(flow_nhwc: torch.Tensor, wT: torch.Tensor, bias: torch.Tensor, out16: torch.Tensor) -> torch.Tensor:
     B, h, w, _ = flow_nhwc.shape
     check(load().sdof_conv7x7_c2_relu_h(ptr(flow_nhwc), ptr(wT), ptr(bias), ptr(out16), B, h, w, stream_ptr(out16.device)),

@@ -175,7 +175,7 @@ class KeyFeatures:
 class FastRaft:
     def __init__(self, model, corr_precision: str = 'fp16', side_streams: bool = True, own_convf1: bool = True,
                  own_fh2: bool = True, corr_storage: str | None = None, tc_gru: bool = False, fnet_fp16: bool = True, cnet_fp16: bool = True, loop_fp16: bool = True,
-                 defer_coords: bool = True):
+                 defer_coords: bool = True, convf1_gemm: bool = True):
         """side_streams / own_convf1 / own_fh2 switch the side-stream branches and the two hand-written
         convolutions off (cuDNN + flow_update instead): A/B switches for bench.py, results are identical.
         corr_storage: 'fp16' / 'fp32' pyramid storage (default: fp16 with 16-bit correlation operands, else fp32)."""
@@ -252,10 +252,14 @@ class FastRaft:
             self.q_w16 = [half_wbp((w, None, pad)) for (w, _, pad) in self.q]
             self.fh1_16 = half_wbp(self.fh1)
             self.mask0_16, self.mask2_16 = half_wbp(self.mask0), half_wbp((self.mask2[0], None, self.mask2[2]))
+            # convf1 as a 1x1 tensor-core convolution over fp16 im2col rows (ops.flow_im2col7_h): [tap][ci] x (hi | lo) + padding
+            self.convf1_k16 = 200
+            self.convf1_gemm16 = (ops.im2col7_weight(e.convf1.weight, self.convf1_k16), h16(e.convf1.bias.detach()), (0, 0))
         self.hidden = model.hidden_dim
         self.cdim = model.context_dim
         self._side = {}
         self.defer_coords = bool(defer_coords)
+        self.convf1_gemm = bool(convf1_gemm)     # convf1 = im2col kernel + cuDNN 1x1 tensor-core convolution (fp16 loop with deferred coords)
         self._fused_relu_ok = None
         # fnet_fp16: the feature encoder's activations / cuDNN convolutions in fp16 (TF32-equivalent operand precision, half
         # the bytes through the InstanceNorm kernels); its output feeds the correlation, whose operands are fp16 anyway.
@@ -327,6 +331,7 @@ class FastRaft:
         H16 = torch.empty((B, h, w, hd), device=dev, dtype=f16)           # dense fp16 copy of h for the flow / mask heads
         MF16 = torch.empty((B, h, w, 128), device=dev, dtype=f16)
         F1_16 = torch.empty((B, h, w, 128), device=dev, dtype=f16)
+        I2C16 = torch.empty((B, h, w, self.convf1_k16), device=dev, dtype=f16) if (self.defer_coords and self.convf1_gemm) else None
         corr16 = torch.empty((B, h, w, self.corr_ch16), device=dev, dtype=f16)
         H16.copy_(H)
         HX16[..., :hd] = H16
@@ -342,11 +347,15 @@ class FastRaft:
                 taps = fh_scratch if it > 0 else None
             side.wait_stream(main)
             with torch.cuda.stream(side):                                 # flow branch (update.py:93-94)
-                if defer:
-                    ops.conv7x7_c2_relu_coords_h(cin, taps, self._fh2_bias, self.convf1_t, self.convf1[1], F1_16)
+                if defer and self.convf1_gemm:
+                    ops.flow_im2col7_h(cin, taps, self._fh2_bias, I2C16)
+                    f1 = self._conv16_relu(I2C16, self.convf1_gemm16)
+                elif defer:
+                    f1 = ops.conv7x7_c2_relu_coords_h(cin, taps, self._fh2_bias, self.convf1_t, self.convf1[1], F1_16)
                 else:
-                    ops.conv7x7_c2_relu_h(flow, self.convf1_t, self.convf1[1], F1_16)
-                f2 = self._conv16_relu(F1_16, self.convf2_16)
+                    f1 = ops.conv7x7_c2_relu_h(flow, self.convf1_t, self.convf1[1], F1_16)
+                f2 = self._conv16_relu(f1, self.convf2_16)
+                del f1
                 MF16.copy_(self._conv(f2, self.conv_flo_16))
                 del f2
             if defer:                                                     # correlation branch (update.py:91-92)
