@@ -11,6 +11,6 @@ import json; d=json.load(open('gpurun_out/r2f_bench_n1.json')); print('value',d[
 echo "=== launch list (warm caches)"
 timeout 900 ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2f_launches_step.csv python tools/profile_step.py step fp16 > gpurun_out/r2f_ncu_step.log 2>&1; echo "rc=$?"; wc -l gpurun_out/r2f_launches_step.csv
 echo "=== full set"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_pyramid_resident|corr_prep16|corr_absmax|corr_lookup_kernel|warp_cubic_u8c3|warp_mask_composite|instnorm_stats|instnorm_apply|conv7x7|flowhead2_taps|flowhead2_gather|blur_composite|motion_tail16_h|gru_rh_h|gru_update_h" -s 44 -c 22 -o /tmp/r2f_kernels -f python tools/profile_step.py kernels fp16 > gpurun_out/r2f_ncu_full.log 2>&1; echo "rc=$?"
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_pyramid_resident|corr_prep16|corr_absmax|corr_lookup_kernel|warp_cubic_u8c3|warp_mask_composite|instnorm_stats|instnorm_apply|conv7x7|flowhead2_taps|flowhead2_gather|blur_composite|motion_tail16_h|gru_rh_h|gru_update_h|flow_im2col7" -s 46 -c 23 -o /tmp/r2f_kernels -f python tools/profile_step.py kernels fp16 > gpurun_out/r2f_ncu_full.log 2>&1; echo "rc=$?"
 python tools/summarize_ncu.py /tmp/r2f_kernels.ncu-rep "ncu --set full, hand-written kernels at the batch-1 / 32-frame sizes (round 2, final)" > gpurun_out/r2f_kernels_ncu_summary.txt 2>&1; wc -l gpurun_out/r2f_kernels_ncu_summary.txt
 echo "=== sanitizers"; tools/run_sanitizer.sh gpurun_out > gpurun_out/r2f_san.log 2>&1; tail -12 gpurun_out/r2f_san.log; rm -f gpurun_out/sanitize_driver

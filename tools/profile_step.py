@@ -89,6 +89,7 @@ else:
     x16 = torch.relu(hf(1, 96, 64, 256))
     bias128 = torch.randn((128,), generator=g, device=dev)
     scratch = torch.empty((96 * 64 * 18,), device=dev)
+    i2c16 = torch.empty((1, 96, 64, 200), dtype=torch.float16, device=dev)
     for _ in range(3):
         pyr = ops.corr_volume_pyramid(f1, f2, 4, prec, 'fp16' if prec in ('fp16', 'bf16') else 'fp32')
         ops.corr_lookup(pyr, coords, 4)
@@ -107,4 +108,5 @@ else:
         ops.gru_rh_h(zr16, zrmap, hid, rh16)
         ops.gru_update_h(zr16, zrmap, q16, qmap, hid, hx16, h16)
         ops.flowhead2_update_h(x16, w2, (0.1, 0.2), c1, fl, scratch)
+        ops.flow_im2col7_h(c1, scratch, (0.1, 0.2), i2c16)
     torch.cuda.synchronize()

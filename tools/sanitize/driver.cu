@@ -302,6 +302,7 @@ static void glue16_case(int B, int h, int w) {
   uint16_t* pyr = dhalves((size_t)lay.total_floats, 0x3000);
   float* coords = dfloats(npix * 2, 10.f);
   float* coords2 = dalloc<float>(npix * 2);
+  uint16_t* i2c = dalloc<uint16_t>(npix * 200);
   uint16_t* corr16 = dalloc<uint16_t>(npix * 328);
   float* flow = dfloats(npix * 2, 3.f);
   float* wT = dfloats(7 * 7 * 2 * 128, 0.1f);
@@ -331,6 +332,7 @@ static void glue16_case(int B, int h, int w) {
     // the deferred form of the same update: applied inside the next lookup / convf1
     SD(sdof_corr_lookup_gather_h(pyr, 2, coords, it ? scratch : nullptr, 0.1f, -0.1f, coords2, flow, B, h, w, h, w, levels, r, corr16, 328, nullptr));
     SD(sdof_conv7x7_c2_relu_coords_h(coords, it ? scratch : nullptr, 0.1f, -0.1f, wT, bias, f1, B, h, w, nullptr));
+    SD(sdof_flow_im2col7_h(coords, it ? scratch : nullptr, 0.1f, -0.1f, i2c, 200, B, h, w, nullptr));
   }
   double* stats = dalloc<double>((size_t)B * 256 * 2);
   CK(cudaMemset(stats, 0, (size_t)B * 256 * 2 * sizeof(double)));
